@@ -1,0 +1,161 @@
+/* qpb200.h -- C ABI of libqpb200.so: the B200-native (sm_100a) OSQP-style ADMM QP solver.
+ *
+ *     minimise 0.5 x'Px + q'x   subject to   l <= Ax <= u
+ *
+ * This is the boundary a Julia `ccall` (or any FFI) binds to replace the reference's hot path
+ *     SolveQuadraticProgram!(vX, mP, vQ, mA, vL, vU, LinSysSolInit, LinSysSol!; kw...)
+ *         /root/reference/SolveQuadraticProgram.jl:14-76   (ADMM driver)
+ *         /root/reference/SolveQuadraticProgram.jl:79-112  (CheckConvergence)
+ *         /root/reference/LinearSystemSolvers.jl:16-229    (the (Init, Sol!) KKT-solve plugins)
+ * Plain C: pointers and sizes only, no exceptions, no torch/CUDA types.  Everything below a
+ * handle runs on the GPU in hand-written CUDA kernels; there is no CPU fallback: on a machine
+ * without an sm_100 device `*_create` fails with QPB200_ERR_DEVICE.
+ *
+ * Sparse matrices come in exactly as Julia's SparseMatrixCSC{Float64,Int64} stores them:
+ * colptr[ncols+1], rowval[nnz], nzval[nnz], 64-bit indices, `index_base` = 1 from Julia (0 from
+ * C / scipy).  P must hold both triangles (the reference multiplies by mP as given).
+ * Host arrays are borrowed only for the duration of the call.
+ */
+#ifndef QPB200_H
+#define QPB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QPB200_VERSION 100 /* 0.1.0 */
+
+/* ---- status codes (0 = OK, negative = error; "did not converge" is NOT an error) ---------- */
+#define QPB200_OK 0
+#define QPB200_ERR_ARG (-1)       /* bad argument / inconsistent dimensions                      */
+#define QPB200_ERR_NONFINITE (-2) /* NaN/Inf in P, A, q (l/u may be +-Inf) or l > u              */
+#define QPB200_ERR_CUDA (-3)      /* CUDA runtime error (see qpb200_last_error)                  */
+#define QPB200_ERR_NCCL (-4)      /* NCCL error / NCCL library not loadable                      */
+#define QPB200_ERR_FACTOR (-5)    /* Cholesky breakdown (non-positive pivot) in the dense path   */
+#define QPB200_ERR_DEVICE (-6)    /* no CUDA device of compute capability 10.x                   */
+
+/* ---- ConvergenceFlag, numerically identical to the Julia enum (SolveQuadraticProgram.jl:12) */
+#define QPB200_CONV_NUM_ITR 1   /* convNumItr   : iteration limit reached                        */
+#define QPB200_CONV_ADMM 2      /* convAdmm     : ||x-xprev||inf, ||z-zprev||inf <= min(eps)*1e-2 */
+#define QPB200_CONV_PRIM_DUAL 3 /* convPrimDual : primal and dual residual tests passed          */
+
+/* ---- linear-system solver for the x~ step (replaces the (Init, Sol!) pair) ----------------- */
+#define QPB200_LINSOLVE_PCG 0      /* matrix-free (P)CG on K = P + sigma I + rho A'A
+                                      (LinOpCg!/LinMapsCg!, LinearSystemSolvers.jl:145-229)       */
+#define QPB200_LINSOLVE_CHOLESKY 1 /* dense Cholesky of K (batched path; the reduced form of the
+                                      direct plugins LaLdl/QDLdl/FacLdl, :16-107)                 */
+#define QPB200_PRECOND_NONE 0      /* IterativeSolvers.cg! exactly as the reference calls it      */
+#define QPB200_PRECOND_JACOBI 1    /* Pl = Diagonal(diag(P) + sigma + rho colsumsq(A))            */
+
+/* Settings: the keyword arguments of SolveQuadraticProgram! 1:1 (SolveQuadraticProgram.jl:15-17),
+ * then the plugin kwargs (LinearSystemSolvers.jl:125), then what is new here.                    */
+typedef struct qpb200_settings {
+    int64_t max_iter;     /* numIterations = 5000                                                 */
+    double eps_abs;       /* eps_abs (ϵAbs) = 1e-6                                                */
+    double eps_rel;       /* eps_rel (ϵRel) = 1e-6                                                */
+    double rho;           /* ρ = 1                                                                */
+    double sigma;         /* σ = 1e-6                                                             */
+    double alpha;         /* α = 1.6                                                              */
+    double delta;         /* δ = 1e-6        accepted, unused (as in the reference)               */
+    int32_t adaptive_rho; /* adptΡ = false                                                        */
+    int32_t lin_solver;   /* QPB200_LINSOLVE_*                                                    */
+    double rho_factor;    /* fctrΡ = 5                                                            */
+    int64_t check_every;  /* numItrConv = 25                                                      */
+    int64_t polish_iter;  /* numItrPolish = 10   accepted, unused                                 */
+    double minres_eps;    /* ϵMinres = 1e-6      accepted, unused                                 */
+    int64_t minres_iter;  /* numItrMinres = 500  accepted, unused                                 */
+    double pcg_eps;       /* ϵPcg = 1e-6  (abstol of cg!)                                         */
+    int64_t pcg_max_iter; /* numItrPcg = 1000                                                     */
+    double pcg_rel_eps;   /* reltol of cg!; <0 means the library default sqrt(eps(Float64))       */
+    int32_t precond;      /* QPB200_PRECOND_* (default JACOBI)                                    */
+    int32_t device;       /* CUDA device ordinal; -1 = the calling thread's current device        */
+    int32_t spmv_loader;  /* 0 = auto, 1 = coalesced LDG tiles, 2 = TMA bulk-copy staged tiles    */
+    int32_t reserved_i[7];
+    double reserved_d[4];
+} qpb200_settings;
+
+typedef struct qpb200_info {
+    int32_t conv_flag;       /* QPB200_CONV_*                                                      */
+    int32_t reserved;
+    int64_t iterations;      /* ADMM iterations executed (a multiple of check_every unless capped) */
+    double rho_final;
+    double res_prim;         /* ||Ax - z||inf at the last check                                    */
+    double res_dual;         /* ||Px + q + A'y||inf at the last check                              */
+    int64_t rho_updates;     /* times the rho trigger fired (= refactorisations)                   */
+    int64_t pcg_iters_total; /* CG iterations summed over all ADMM iterations                      */
+    int64_t pcg_maxed;       /* ADMM iterations whose CG stopped on pcg_max_iter                   */
+    double solve_ms;         /* device time of the solve, CUDA events                              */
+    double setup_ms;         /* host wall time of create (conversion + upload)                     */
+    int64_t kernel_launches; /* kernels launched by the last solve                                 */
+} qpb200_info;
+
+typedef struct qpb200_handle qpb200_handle;             /* one sparse QP on one GPU               */
+typedef struct qpb200_batch qpb200_batch;               /* a batch of small dense QPs on one GPU  */
+
+/* ---- library -------------------------------------------------------------------------------- */
+int qpb200_version(void);
+int qpb200_device_count(void);                          /* sm_100 devices visible, or error < 0   */
+void qpb200_default_settings(qpb200_settings *s);       /* defaults of SolveQuadraticProgram.jl:15-17 */
+const char *qpb200_last_error(void);                    /* thread-local message of the last failure */
+
+/* ---- single sparse QP: replaces SolveQuadraticProgram! + LinOpCgInit/LinOpCg! ---------------- */
+int qpb200_create(qpb200_handle **out, int64_t n, int64_t m,
+                  const int64_t *P_colptr, const int64_t *P_rowval, const double *P_nzval,
+                  const int64_t *A_colptr, const int64_t *A_rowval, const double *A_nzval,
+                  const double *q, const double *l, const double *u,
+                  const qpb200_settings *settings, int32_t index_base);
+/* x_inout[n]: start point in (vX), solution out.  z_out[m], y_out[m] may be NULL.              */
+int qpb200_solve(qpb200_handle *h, double *x_inout, double *z_out, double *y_out, qpb200_info *info);
+int qpb200_update_vectors(qpb200_handle *h, const double *q, const double *l, const double *u); /* any may be NULL */
+int qpb200_update_settings(qpb200_handle *h, const qpb200_settings *settings);
+void qpb200_destroy(qpb200_handle *h);
+
+/* The operators of the path on their own (SparseArrays mul!, SolveQuadraticProgram.jl:85-89,
+ * LinearSystemSolvers.jl:135,139,153-155): which = 0: y[n] = P x[n]; 1: y[m] = A x[n];
+ * 2: y[n] = A' x[m]; 3: y[n] = (P + sigma I + rho A'A) x[n].  Host vectors in and out.          */
+int qpb200_apply(qpb200_handle *h, int32_t which, const double *x, double *y);
+/* Same operator, device-resident vectors, `reps` back-to-back launches timed with CUDA events; an
+ * L2-flushing write precedes every launch when flush_l2 != 0.  ms_out = mean ms per launch.      */
+int qpb200_time_apply(qpb200_handle *h, int32_t which, int32_t reps, int32_t flush_l2, double *ms_out);
+/* Algorithmic bytes of one launch of `which` (SURVEY.md section 8(d) formula).                    */
+int64_t qpb200_apply_bytes(qpb200_handle *h, int32_t which);
+
+/* ---- batch of small dense QPs (MPC-style): replaces SolveQuadraticProgram! + a direct plugin --
+ * P: batch blocks n x n column-major; A: batch blocks m x n column-major; q[batch*n];
+ * l, u[batch*m]; X_inout[batch*n]; flags/iters[batch] (may be NULL).                              */
+int qpb200_batch_create(qpb200_batch **out, int64_t batch, int64_t n, int64_t m,
+                        const double *P, const double *A, const double *q, const double *l, const double *u,
+                        const qpb200_settings *settings);
+int qpb200_batch_solve(qpb200_batch *h, double *X_inout, int32_t *flags, int64_t *iters, qpb200_info *info);
+void qpb200_batch_destroy(qpb200_batch *h);
+
+/* ---- one large sparse QP row-partitioned over several GPUs, one rank (process or thread) per GPU.
+ * Rank r owns rows [row_begin, row_end) of A (and of l, u, z, y) and the same-numbered share of P's
+ * columns; the CSC arrays passed are that slice: A_slice is (row_end-row_begin) x n with LOCAL row
+ * indices, P_slice is n x n holding only the columns [pcol_begin, pcol_end).  x, q are replicated.
+ * nccl_unique_id: 128 bytes from qpb200_dist_unique_id on rank 0, distributed by the caller.      */
+int qpb200_dist_unique_id(void *id128);
+int qpb200_dist_create(qpb200_handle **out, int32_t rank, int32_t nranks, const void *nccl_unique_id,
+                       int64_t n, int64_t m_local,
+                       const int64_t *P_colptr, const int64_t *P_rowval, const double *P_nzval,
+                       const int64_t *A_colptr, const int64_t *A_rowval, const double *A_nzval,
+                       const double *q, const double *l_local, const double *u_local,
+                       const qpb200_settings *settings, int32_t index_base);
+/* Collective: every rank calls it.  x_inout[n] (replicated), z_out/y_out[m_local] or NULL.        */
+int qpb200_dist_solve(qpb200_handle *h, double *x_inout, double *z_out, double *y_out, qpb200_info *info);
+
+/* ---- host-only introspection (no GPU needed; used by the CPU test-suite) --------------------------
+ * Builds the tile plan the kernels consume for a CSR matrix given by rowptr[rows+1] (int32, 0-based):
+ * tiles_out[4*i..] = {first row, #rows, first nnz, #nnz | flags} (flags: bit30 continues a long row,
+ * bit29 the row continues), cta_begin_out[grid+1] = tile range of each CTA.  Returns the number of
+ * tiles (> tiles_cap means tiles_out was too small), or an error < 0.  *lpr_out = lanes per row.      */
+int64_t qpb200_debug_tile_plan(int32_t rows, const int32_t *rowptr, int32_t grid, int32_t *tiles_out,
+                               int64_t tiles_cap, int32_t *cta_begin_out, int32_t *lpr_out);
+int32_t qpb200_debug_tile_nnz(void);   /* kTileNnz */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QPB200_H */

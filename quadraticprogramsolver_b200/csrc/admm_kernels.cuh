@@ -1,0 +1,279 @@
+// admm_kernels.cuh -- the persistent ADMM kernel (whole solve on the device) and the stand-alone
+// SpMV kernels built on spmv_core.cuh.
+//
+// Reference path restated on the GPU (file:line in /root/reference):
+//   SolveQuadraticProgram!  SolveQuadraticProgram.jl:14-76     outer loop, relaxation, clip, dual update
+//   CheckConvergence        SolveQuadraticProgram.jl:79-112    residual inf-norms, adaptive rho, flags
+//   LinOpCg!                LinearSystemSolvers.jl:145-186     rhs, matrix-free K, z~ = A x~
+//   IterativeSolvers.cg!    (third party, v0.9.x algorithm)    CGIterable / PCGIterable
+//
+// Data layout: the operator is held as two tiled CSR matrices,
+//     H = [P  A']   n x (n+m)   (row j = row j of P followed by column j of A, columns shifted by n)
+//     A             m x n
+// and the vectors that H gathers from are stored as contiguous pairs [n-part ; m-part]:
+//     XY = [x ; y]      XG = [x~ ; g]  with g = rho (z~ - z) + y      UT = [u ; rho A u]
+// so that  K u = H*UT + sigma u,   b - K x~ = sigma (x - x~) - q - H*XG,   [Px ; A'y] = split sums of H*XY.
+#pragma once
+#include "spmv_core.cuh"
+
+namespace qpb {
+
+struct AdmmSettingsDev {
+    long long max_iter;
+    long long check_every;
+    long long pcg_max_iter;
+    double eps_abs, eps_rel, rho, sigma, alpha, rho_factor, pcg_eps, pcg_rel_eps;
+    int adaptive_rho;
+};
+
+struct AdmmInfoDev {
+    int conv_flag;
+    int pad;
+    long long iterations;
+    double rho_final, res_prim, res_dual;
+    long long rho_updates, pcg_iters_total, pcg_maxed;
+    long long n_h_passes, n_a_passes;   // matrix passes executed (for the roofline accounting)
+};
+
+struct SparseProblemDev {
+    int n, m;
+    CsrTiled H, A;
+    const double *q, *l, *u;    // problem vectors
+    const double *dP, *dAA;     // diag(P), column square sums of A (Jacobi)
+    double *XY, *XG, *UT;       // vector pairs, n + m each
+    double *z, *zt;             // m
+    double *r, *c, *zp, *dinv;  // n
+    double normQ;
+    GridSync gs;
+    AdmmSettingsDev s;
+    AdmmInfoDev *info;
+};
+
+__device__ __forceinline__ double clamp_julia(double x, double lo, double hi) {
+    return x > hi ? hi : (x < lo ? lo : x);   // Julia's clamp: NaN passes through
+}
+
+// =============================================================================================
+// Stand-alone SpMV (operator unit tests, SpMV roofline measurement).
+//   mode 0: y[rows] = M x            mode 1 (split): y0 = M[:, :split] x[:split], y1 = M[:, split:] x[split:]
+// =============================================================================================
+template <bool TMA, bool SPLIT>
+__global__ void __launch_bounds__(kThreads, 2) spmv_kernel(CsrTiled M, const double *x, double *y0, double *y1) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SpmvSmem &sm = *reinterpret_cast<SpmvSmem *>(smem_raw);
+    PipeState ps;
+    spmv_smem_init(sm, ps);
+    auto epi = [&](int row, double s0, double s1) {
+        y0[row] = s0;
+        if (SPLIT) y1[row] = s1;
+    };
+    spmv_tiles<TMA, SPLIT>(M, x, sm, ps, epi);
+}
+
+// =============================================================================================
+// The persistent ADMM kernel.  Cooperative launch, grid = co-resident CTAs (<= 2 per SM).
+// Every scalar (rho, alpha_cg, beta, residuals, flags) is recomputed identically by every thread
+// from bit-identical all-reduced values, so control flow is uniform across the grid.
+// =============================================================================================
+template <bool TMA, bool PRE>
+__global__ void __launch_bounds__(kThreads, 2) admm_kernel(SparseProblemDev p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SpmvSmem &sm = *reinterpret_cast<SpmvSmem *>(smem_raw);
+    PipeState ps;
+    spmv_smem_init(sm, ps);
+    SyncState st;
+    st.epoch = 0;
+
+    const int n = p.n, m = p.m;
+    const int gtid = blockIdx.x * kThreads + threadIdx.x;
+    const int gstride = gridDim.x * kThreads;
+    double *const x = p.XY, *const y = p.XY + n;
+    double *const xt = p.XG, *const g = p.XG + n;
+    double *const u = p.UT, *const t = p.UT + n;
+    double *const zpv = PRE ? p.zp : p.r;   // un-preconditioned: "z" of PCG is r itself
+
+    double rho = p.s.rho, rho1 = 1.0 / rho;                         // SolveQuadraticProgram.jl:30
+    const double alpha = p.s.alpha, alpha1 = 1.0 - alpha;           // :31
+    const double sigma = p.s.sigma;
+    const double eps_admm = fmin(p.s.eps_abs, p.s.eps_rel) * 1e-2;  // :34
+    double rhorho = rho;                                            // :43
+    int conv_flag = 1;                                              // :33 convNumItr
+    long long rho_updates = 0, pcg_total = 0, pcg_maxed = 0, n_h = 0, n_a = 0;
+    double res_prim = nan(""), res_dual = nan("");
+    const double reltol = p.s.pcg_rel_eps;
+    bool dinv_ready = false;
+
+    long long ii = 0;
+    for (ii = 1; ii <= p.s.max_iter; ++ii) {                        // :45
+        // ---- rho trigger (:46-52) -> "refactorisation": Jacobi diagonal and g depend on rho
+        bool changed = false;
+        if (p.s.adaptive_rho && ((rhorho * p.s.rho_factor < rho) || (rhorho > p.s.rho_factor * rho))) {
+            rho = rhorho;
+            rho1 = 1.0 / rho;
+            changed = true;
+            ++rho_updates;
+        }
+        if (changed || !dinv_ready) {
+            if (PRE)
+                for (int j = gtid; j < n; j += gstride) p.dinv[j] = 1.0 / (p.dP[j] + sigma + rho * p.dAA[j]);
+            if (changed)
+                for (int i = gtid; i < m; i += gstride) g[i] = rho * (p.zt[i] - p.z[i]) + y[i];
+            dinv_ready = true;
+            grid_barrier(p.gs, st);
+        }
+
+        // ---- [P1] r0 = b - K x~  with b = sigma x - q + A'(rho z - y)   (LinearSystemSolvers.jl:178-180
+        //      and the first MV product of cg!); u = Pl \ r0
+        double acc[2] = {0.0, 0.0};
+        {
+            auto epi = [&](int j, double s0, double) {
+                const double rj = sigma * (x[j] - xt[j]) - p.q[j] - s0;
+                p.r[j] = rj;
+                const double zj = PRE ? p.dinv[j] * rj : rj;
+                if (PRE) p.zp[j] = zj;
+                u[j] = zj;
+                acc[0] += rj * rj;
+                acc[1] += rj * zj;
+            };
+            spmv_tiles<TMA, false>(p.H, p.XG, sm, ps, epi);
+            ++n_h;
+        }
+        grid_barrier_reduce<2, false>(p.gs, st, acc, sm.red, sm.bcast);
+        double residual = sqrt(acc[0]);
+        double rz = acc[1];
+        const double tol = fmax(reltol * residual, p.s.pcg_eps);     // cg_iterator!: max(reltol*|r0|, abstol)
+
+        // ---- PCG loop (CGIterable / PCGIterable)
+        long long k = 0;
+        while (k < p.s.pcg_max_iter && !(residual <= tol)) {
+            // [S2] t = rho * A u
+            {
+                auto epi = [&](int i, double s0, double) { t[i] = rho * s0; };
+                spmv_tiles<TMA, false>(p.A, u, sm, ps, epi);
+                ++n_a;
+            }
+            grid_barrier(p.gs, st);
+            // [S3] c = P u + rho A'(A u) + sigma u ; u.c      (LinearSystemSolvers.jl:152-157)
+            double uc[1] = {0.0};
+            {
+                auto epi = [&](int j, double s0, double) {
+                    const double uj = u[j];
+                    const double cj = s0 + sigma * uj;
+                    p.c[j] = cj;
+                    uc[0] += uj * cj;
+                };
+                spmv_tiles<TMA, false>(p.H, p.UT, sm, ps, epi);
+                ++n_h;
+            }
+            grid_barrier_reduce<1, false>(p.gs, st, uc, sm.red, sm.bcast);
+            if (!(uc[0] > 0.0)) break;                               // breakdown guard (K is SPD)
+            const double a_cg = rz / uc[0];
+            // [S4] x~ += a u ; r -= a c ; z = Pl \ r ; |r|^2, r.z
+            double acc2[2] = {0.0, 0.0};
+            for (int j = gtid; j < n; j += gstride) {
+                xt[j] += a_cg * u[j];
+                const double rj = p.r[j] - a_cg * p.c[j];
+                p.r[j] = rj;
+                const double zj = PRE ? p.dinv[j] * rj : rj;
+                if (PRE) p.zp[j] = zj;
+                acc2[0] += rj * rj;
+                acc2[1] += rj * zj;
+            }
+            grid_barrier_reduce<2, false>(p.gs, st, acc2, sm.red, sm.bcast);
+            residual = sqrt(acc2[0]);
+            const double rz_new = acc2[1];
+            ++k;
+            if (k < p.s.pcg_max_iter && !(residual <= tol)) {
+                // [S1] u = z + beta u
+                const double beta = rz_new / rz;
+                for (int j = gtid; j < n; j += gstride) u[j] = zpv[j] + beta * u[j];
+                grid_barrier(p.gs, st);
+            }
+            rz = rz_new;
+        }
+        pcg_total += k;
+        if (k >= p.s.pcg_max_iter && !(residual <= tol)) ++pcg_maxed;
+
+        // ---- [Upd] z~ = A x~ (LinearSystemSolvers.jl:183) fused with SolveQuadraticProgram.jl:56-61
+        const bool do_check = (ii % p.s.check_every) == 0;           // :63
+        double nrm[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};          // dx dz rp nAx nZ rd|nPx|nAty packed below
+        {
+            auto epi = [&](int i, double s0, double) {
+                const double zt_i = s0;
+                const double z_old = p.z[i], y_old = y[i];
+                const double zr = alpha * zt_i + alpha1 * z_old;
+                const double z_new = clamp_julia(zr + rho1 * y_old, p.l[i], p.u[i]);   // :60
+                const double y_new = y_old + rho * (zr - z_new);                       // :61
+                p.z[i] = z_new;
+                y[i] = y_new;
+                p.zt[i] = zt_i;
+                g[i] = rho * (zt_i - z_new) + y_new;
+                nrm[1] = nanmax(nrm[1], fabs(z_new - z_old));
+            };
+            spmv_tiles<TMA, false>(p.A, xt, sm, ps, epi);
+            ++n_a;
+        }
+        for (int j = gtid; j < n; j += gstride) {
+            const double x_old = x[j];
+            const double x_new = alpha * xt[j] + alpha1 * x_old;      // :57
+            x[j] = x_new;
+            nrm[0] = nanmax(nrm[0], fabs(x_new - x_old));
+        }
+        grid_barrier(p.gs, st);
+
+        if (do_check) {
+            // ---- [Chk] CheckConvergence (:79-112): A x, P x, A' y and their inf-norms in two passes
+            {
+                auto epi = [&](int i, double s0, double) {
+                    const double zi = p.z[i];
+                    nrm[2] = nanmax(nrm[2], fabs(s0 - zi));           // |Ax - z|
+                    nrm[3] = nanmax(nrm[3], fabs(s0));                // |Ax|
+                    nrm[3] = nanmax(nrm[3], fabs(zi));                // |z|   (maxNormPrim = max of both)
+                };
+                spmv_tiles<TMA, false>(p.A, x, sm, ps, epi);
+                ++n_a;
+            }
+            {
+                auto epi = [&](int j, double s0, double s1) {
+                    nrm[4] = nanmax(nrm[4], fabs(s0 + p.q[j] + s1));  // |Px + q + A'y|
+                    nrm[5] = nanmax(nrm[5], fabs(s0));                // |Px|
+                    nrm[5] = nanmax(nrm[5], fabs(s1));                // |A'y|
+                };
+                spmv_tiles<TMA, true>(p.H, p.XY, sm, ps, epi);
+                ++n_h;
+            }
+            grid_barrier_reduce<7, true>(p.gs, st, nrm, sm.red, sm.bcast);
+            const double dx = nrm[0], dz = nrm[1];
+            res_prim = nrm[2];
+            res_dual = nrm[4];
+            const double max_prim = nrm[3];
+            const double max_dual = nanmax(nrm[5], p.normQ);
+            if (p.s.adaptive_rho) {                                   // :92-96
+                const double num = res_prim * max_dual, den = res_dual * max_prim;
+                rhorho = clamp_julia(rho * sqrt(num / den), 1e-3, 1e6);
+            }
+            const double eps_prim = p.s.eps_abs + p.s.eps_rel * max_prim;   // :99
+            const double eps_dual = p.s.eps_abs + p.s.eps_rel * max_dual;   // :100
+            if ((res_prim < eps_prim) && (res_dual < eps_dual)) conv_flag = 3;   // :102
+            if ((dx <= eps_admm) && (dz <= eps_admm)) conv_flag = 2;             // :105 (overrides)
+            if (conv_flag != 1) break;                                // :66
+        }
+    }
+    if (ii > p.s.max_iter) ii = p.s.max_iter;
+
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        AdmmInfoDev &o = *p.info;
+        o.conv_flag = conv_flag;
+        o.iterations = ii;
+        o.rho_final = rho;
+        o.res_prim = res_prim;
+        o.res_dual = res_dual;
+        o.rho_updates = rho_updates;
+        o.pcg_iters_total = pcg_total;
+        o.pcg_maxed = pcg_maxed;
+        o.n_h_passes = n_h;
+        o.n_a_passes = n_a;
+    }
+}
+
+}  // namespace qpb

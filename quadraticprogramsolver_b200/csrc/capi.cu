@@ -1,0 +1,133 @@
+// capi.cu -- the extern "C" surface declared in include/qpb200.h.
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "host_common.h"
+#include "sparse_solver.h"
+
+struct qpb200_handle {
+    qpb::SparseSolver solver;
+};
+
+extern "C" {
+
+int qpb200_version(void) { return QPB200_VERSION; }
+
+const char *qpb200_last_error(void) { return qpb::last_error().c_str(); }
+
+int qpb200_device_count(void) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess) return qpb::fail(QPB200_ERR_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    int ok = 0;
+    for (int d = 0; d < count; ++d) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, d) == cudaSuccess && p.major == 10) ++ok;
+    }
+    return ok;
+}
+
+void qpb200_default_settings(qpb200_settings *s) {
+    if (!s) return;
+    std::memset(s, 0, sizeof(*s));
+    s->max_iter = 5000;          // SolveQuadraticProgram.jl:15
+    s->eps_abs = 1e-6;
+    s->eps_rel = 1e-6;
+    s->rho = 1.0;                // :16
+    s->sigma = 1e-6;
+    s->alpha = 1.6;
+    s->delta = 1e-6;
+    s->adaptive_rho = 0;
+    s->lin_solver = QPB200_LINSOLVE_PCG;
+    s->rho_factor = 5.0;         // :17
+    s->check_every = 25;
+    s->polish_iter = 10;
+    s->minres_eps = 1e-6;
+    s->minres_iter = 500;
+    s->pcg_eps = 1e-6;           // LinearSystemSolvers.jl:125
+    s->pcg_max_iter = 1000;
+    s->pcg_rel_eps = -1.0;       // IterativeSolvers default sqrt(eps)
+    s->precond = QPB200_PRECOND_JACOBI;
+    s->device = -1;
+    s->spmv_loader = 0;
+}
+
+int qpb200_create(qpb200_handle **out, int64_t n, int64_t m, const int64_t *P_colptr, const int64_t *P_rowval,
+                  const double *P_nzval, const int64_t *A_colptr, const int64_t *A_rowval, const double *A_nzval,
+                  const double *q, const double *l, const double *u, const qpb200_settings *settings, int32_t index_base) {
+    if (!out) return qpb::fail(QPB200_ERR_ARG, "qpb200_create: out is NULL");
+    *out = nullptr;
+    qpb200_settings s;
+    if (settings) s = *settings;
+    else qpb200_default_settings(&s);
+    qpb200_handle *h = new (std::nothrow) qpb200_handle();
+    if (!h) return qpb::fail(QPB200_ERR_ARG, "out of host memory");
+    const int rc = h->solver.init(n, m, P_colptr, P_rowval, P_nzval, A_colptr, A_rowval, A_nzval, q, l, u, s, index_base);
+    if (rc != QPB200_OK) {
+        delete h;
+        return rc;
+    }
+    *out = h;
+    return QPB200_OK;
+}
+
+int qpb200_solve(qpb200_handle *h, double *x_inout, double *z_out, double *y_out, qpb200_info *info) {
+    if (!h) return qpb::fail(QPB200_ERR_ARG, "qpb200_solve: handle is NULL");
+    return h->solver.solve(x_inout, z_out, y_out, info);
+}
+
+int qpb200_update_vectors(qpb200_handle *h, const double *q, const double *l, const double *u) {
+    if (!h) return qpb::fail(QPB200_ERR_ARG, "qpb200_update_vectors: handle is NULL");
+    return h->solver.update_vectors(q, l, u);
+}
+
+int qpb200_update_settings(qpb200_handle *h, const qpb200_settings *settings) {
+    if (!h || !settings) return qpb::fail(QPB200_ERR_ARG, "qpb200_update_settings: NULL argument");
+    return h->solver.settings_to_dev(*settings);
+}
+
+void qpb200_destroy(qpb200_handle *h) { delete h; }
+
+int qpb200_apply(qpb200_handle *h, int32_t which, const double *x, double *y) {
+    if (!h) return qpb::fail(QPB200_ERR_ARG, "qpb200_apply: handle is NULL");
+    return h->solver.apply(which, x, y);
+}
+
+int qpb200_time_apply(qpb200_handle *h, int32_t which, int32_t reps, int32_t flush_l2, double *ms_out) {
+    if (!h) return qpb::fail(QPB200_ERR_ARG, "qpb200_time_apply: handle is NULL");
+    return h->solver.time_apply(which, reps, flush_l2, ms_out);
+}
+
+int64_t qpb200_apply_bytes(qpb200_handle *h, int32_t which) {
+    if (!h) return 0;
+    return which == 100 ? h->solver.solve_bytes() : h->solver.spmv_bytes(which);
+}
+
+int64_t qpb200_debug_tile_plan(int32_t rows, const int32_t *rowptr, int32_t grid, int32_t *tiles_out, int64_t tiles_cap,
+                               int32_t *cta_begin_out, int32_t *lpr_out) {
+    if (rows < 0 || !rowptr || grid <= 0) return qpb::fail(QPB200_ERR_ARG, "qpb200_debug_tile_plan: bad argument");
+    qpb::HostCsr M;
+    M.rows = rows;
+    M.cols = 0;
+    M.ptr.assign(rowptr, rowptr + rows + 1);
+    qpb::HostTiles T;
+    qpb::build_tiles(M, qpb::kTileNnz, T);
+    qpb::assign_tiles(T, grid);
+    const int64_t nt = (int64_t)T.tiles.size();
+    if (tiles_out && nt <= tiles_cap)
+        for (int64_t i = 0; i < nt; ++i) {
+            tiles_out[4 * i + 0] = T.tiles[(size_t)i].x;
+            tiles_out[4 * i + 1] = T.tiles[(size_t)i].y;
+            tiles_out[4 * i + 2] = T.tiles[(size_t)i].z;
+            tiles_out[4 * i + 3] = T.tiles[(size_t)i].w;
+        }
+    if (cta_begin_out)
+        for (int b = 0; b <= grid; ++b) cta_begin_out[b] = T.cta_begin[(size_t)b];
+    if (lpr_out) *lpr_out = T.lpr;
+    return nt;
+}
+
+int32_t qpb200_debug_tile_nnz(void) { return qpb::kTileNnz; }
+
+}  // extern "C"

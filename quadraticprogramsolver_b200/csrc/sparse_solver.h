@@ -1,0 +1,39 @@
+// sparse_solver.h -- the object behind a qpb200_handle (single GPU, sparse QP).
+#pragma once
+#include "admm_kernels.cuh"
+#include "host_common.h"
+
+namespace qpb {
+
+struct SparseSolver {
+    int n = 0, m = 0, device = -1, num_sms = 0, grid = 0;
+    int64_t nnzP = 0, nnzA = 0;
+    bool use_tma = true, use_pre = true;
+    qpb200_settings settings{};
+    SparseProblemDev prob{};
+    AdmmInfoDev last_info{};
+    DeviceArena arena;
+    double *d_q = nullptr, *d_l = nullptr, *d_u = nullptr;
+    double *scratch = nullptr, *flush_buf = nullptr;
+    unsigned long long *sync_words = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double setup_ms = 0.0;
+
+    ~SparseSolver();
+    int init(int64_t n, int64_t m, const int64_t *Pp, const int64_t *Pi, const double *Pv, const int64_t *Ap,
+             const int64_t *Ai, const double *Av, const double *q, const double *l, const double *u,
+             const qpb200_settings &s, int32_t base);
+    int settings_to_dev(const qpb200_settings &s);
+    int reset_state(const double *x0_host);
+    int launch_admm();
+    int solve(double *x_inout, double *z_out, double *y_out, qpb200_info *info);
+    int apply(int which, const double *x_host, double *y_host);
+    int apply_device(int which, const double *x, double *y);
+    int time_apply(int which, int reps, int flush_l2, double *ms_out);
+    int update_vectors(const double *q, const double *l, const double *u);
+    int64_t spmv_bytes(int which) const;
+    int64_t solve_bytes() const;
+};
+
+}  // namespace qpb

@@ -1,0 +1,189 @@
+// spmv_core.cuh -- tiled CSR SpMV ("CSR-stream") device core, used by the stand-alone SpMV kernel
+// and by every matrix phase of the persistent ADMM kernel.
+//
+// Replaces SparseArrays/MKLSparse `mul!` (reference call sites LinearSystemSolvers.jl:135,139,
+// 153-155 and SolveQuadraticProgram.jl:85-89).
+//
+// Layout (HBM): CSR with int32 row pointers / column indices and FP64 values.  The row range is cut
+// on the host into *tiles*: maximal runs of consecutive rows holding <= kTileNnz non-zeros (a row
+// longer than that is split into segments that stay on one CTA).  Each CTA owns a contiguous,
+// nnz-balanced run of tiles (static => bitwise reproducible).  Per tile:
+//   1. the tile's (col,val) stream is brought in fully coalesced -- either by a 1-D TMA bulk copy
+//      (cp.async.bulk -> shared memory, mbarrier-tracked, multi-stage) or by coalesced LDGs,
+//   2. every thread forms products val[k] * x[col[k]] (x gathered through L1/L2) into shared memory,
+//   3. `lpr` lanes per row sum the row's products out of shared memory and hand the row sum to the
+//      phase's epilogue functor (which fuses the vector update / norm / dot product of that phase).
+// Algorithmic bytes per launch: 12*nnz + 4*(rows+1) + 8*cols + 8*rows.
+#pragma once
+#include "device_utils.cuh"
+
+namespace qpb {
+
+constexpr int kTileNnz = 2048;          // non-zeros per tile
+constexpr int kTilePad = 8;             // alignment slack of a TMA-staged tile
+constexpr int kStages = 3;              // TMA pipeline depth
+constexpr int kTileCap = kTileNnz + kTilePad;
+
+// tile descriptor: x = first row, y = #rows, z = first nnz (k0), w = #nnz | flags
+constexpr int kTileContFromPrev = 1 << 30;   // this tile continues a long row started earlier
+constexpr int kTileContToNext = 1 << 29;     // the long row continues into the next tile
+constexpr int kTileNkMask = (1 << 24) - 1;
+
+struct CsrTiled {
+    int rows, cols;
+    const int *rowptr;     // rows + 1
+    const int *rowmid;     // rows, optional: first nnz of the second column block (split sums)
+    const int *col;        // nnz (+ padding)
+    const double *val;     // nnz (+ padding)
+    const int4 *tiles;     // ntiles
+    const int *cta_begin;  // grid + 1: tile range of every CTA
+    int ntiles;
+    int lpr;               // lanes per row in the row-sum step (power of two, <= 32)
+};
+
+// Shared memory of one CTA.
+struct __align__(128) SpmvSmem {
+    double val[kStages][kTileCap];   // TMA: staged values, overwritten in place by the products
+                                     // LDG: buffers 0/1 hold the products (ping-pong)
+    int col[kStages][kTileCap];      // TMA only
+    uint64_t full[kStages];          // mbarriers
+    double red[kWarps * kMaxRed];
+    double bcast[kMaxRed];
+    double carry[2];                 // running sums of a long row
+};
+
+struct PipeState {     // uniform across the CTA
+    uint32_t parity;   // bit s = parity to wait for on stage s
+};
+
+// ---- row-sum step shared by both loaders ---------------------------------------------------
+// prod: shared products of this tile, element k of the tile at prod[k] (k relative to k0).
+template <bool SPLIT, class Epi>
+__device__ __forceinline__ void tile_row_sums(const CsrTiled &M, const int4 td, const double *prod, SpmvSmem &sm,
+                                              Epi &epi) {
+    const int row0 = td.x, nrows = td.y, k0 = td.z;
+    const int nk = td.w & kTileNkMask;
+    const bool from_prev = td.w & kTileContFromPrev, to_next = td.w & kTileContToNext;
+    if (from_prev || to_next) {
+        // one segment of a long row: whole-CTA sum, carried across the row's tiles
+        double s[2] = {0.0, 0.0};
+        const int mid = SPLIT ? (M.rowmid[row0] - k0) : nk;
+        for (int k = threadIdx.x; k < nk; k += kThreads) {
+            if (!SPLIT || k < mid) s[0] += prod[k];
+            else s[1] += prod[k];
+        }
+        block_reduce<2, false>(s, sm.red);
+        if (threadIdx.x == 0) {
+            const double c0 = (from_prev ? sm.carry[0] : 0.0) + s[0];
+            const double c1 = (from_prev ? sm.carry[1] : 0.0) + s[1];
+            if (to_next) { sm.carry[0] = c0; sm.carry[1] = c1; }
+            else epi(row0, c0, c1);
+        }
+        return;
+    }
+    const int lpr = M.lpr;
+    const int groups = kThreads / lpr;
+    const int g = threadIdx.x / lpr, gl = threadIdx.x % lpr;
+    for (int rb = 0; rb < nrows; rb += groups) {
+        const int r = rb + g;
+        double s0 = 0.0, s1 = 0.0;
+        if (r < nrows) {
+            const int row = row0 + r;
+            const int a = __ldg(M.rowptr + row) - k0, b = __ldg(M.rowptr + row + 1) - k0;
+            if (!SPLIT) {
+                for (int k = a + gl; k < b; k += lpr) s0 += prod[k];
+            } else {
+                const int mid = __ldg(M.rowmid + row) - k0;
+                for (int k = a + gl; k < mid; k += lpr) s0 += prod[k];
+                for (int k = mid + gl; k < b; k += lpr) s1 += prod[k];
+            }
+        }
+        for (int o = lpr >> 1; o > 0; o >>= 1) {
+            s0 += __shfl_down_sync(0xffffffffu, s0, o, lpr);
+            if (SPLIT) s1 += __shfl_down_sync(0xffffffffu, s1, o, lpr);
+        }
+        if (r < nrows && gl == 0) epi(row0 + r, s0, s1);
+    }
+}
+
+// ---- loader 1: coalesced LDG tiles -----------------------------------------------------------
+// x: the gathered vector (mutable between phases: plain loads, never ld.global.nc).
+template <bool SPLIT, class Epi>
+__device__ __forceinline__ void spmv_tiles_ldg(const CsrTiled &M, const double *x, SpmvSmem &sm, Epi &epi) {
+    const int tb = M.cta_begin[blockIdx.x], te = M.cta_begin[blockIdx.x + 1];
+    for (int t = tb; t < te; ++t) {
+        const int4 td = __ldg(M.tiles + t);
+        const int k0 = td.z, nk = td.w & kTileNkMask;
+        double *prod = sm.val[(t - tb) & 1];
+        const int *col = M.col + k0;
+        const double *val = M.val + k0;
+#pragma unroll 4
+        for (int k = threadIdx.x; k < nk; k += kThreads) {
+            const int c = __ldg(col + k);
+            const double v = __ldg(val + k);
+            prod[k] = v * x[c];
+        }
+        __syncthreads();
+        tile_row_sums<SPLIT>(M, td, prod, sm, epi);
+    }
+    __syncthreads();
+}
+
+// ---- loader 2: TMA bulk-copy staged tiles ------------------------------------------------------
+__device__ __forceinline__ void tma_issue_tile(const CsrTiled &M, const int4 td, SpmvSmem &sm, int stage) {
+    const int k0 = td.z, nk = td.w & kTileNkMask;
+    const int k0a = k0 & ~3;                            // 16-byte aligned start for both arrays
+    const int cnt = ((k0 + nk - k0a) + 3) & ~3;         // <= kTileNnz + 6
+    mbar_expect_tx(&sm.full[stage], static_cast<uint32_t>(cnt) * 12u);
+    tma_load_1d(sm.val[stage], M.val + k0a, static_cast<uint32_t>(cnt) * 8u, &sm.full[stage]);
+    tma_load_1d(sm.col[stage], M.col + k0a, static_cast<uint32_t>(cnt) * 4u, &sm.full[stage]);
+}
+
+template <bool SPLIT, class Epi>
+__device__ __forceinline__ void spmv_tiles_tma(const CsrTiled &M, const double *x, SpmvSmem &sm, PipeState &ps,
+                                               Epi &epi) {
+    const int tb = M.cta_begin[blockIdx.x], te = M.cta_begin[blockIdx.x + 1];
+    const int nt = te - tb;
+    // the stages were last touched through the generic proxy (previous phase's row sums)
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int pre = nt < (kStages - 1) ? nt : (kStages - 1);
+        for (int i = 0; i < pre; ++i) tma_issue_tile(M, __ldg(M.tiles + tb + i), sm, i % kStages);
+    }
+    for (int i = 0; i < nt; ++i) {
+        const int s = i % kStages;
+        const int4 td = __ldg(M.tiles + tb + i);
+        const int k0 = td.z, nk = td.w & kTileNkMask;
+        const int off = k0 & 3;
+        mbar_wait(&sm.full[s], (ps.parity >> s) & 1u);
+        ps.parity ^= (1u << s);
+        double *val = sm.val[s] + off;
+        const int *col = sm.col[s] + off;
+#pragma unroll 4
+        for (int k = threadIdx.x; k < nk; k += kThreads) val[k] = val[k] * x[col[k]];
+        fence_proxy_async_smem();   // our generic accesses to the stages (incl. tile i-1's reads) before the refill
+        __syncthreads();
+        if (threadIdx.x == 0 && i + kStages - 1 < nt)
+            tma_issue_tile(M, __ldg(M.tiles + tb + i + kStages - 1), sm, (i + kStages - 1) % kStages);
+        tile_row_sums<SPLIT>(M, td, val, sm, epi);
+    }
+    __syncthreads();
+}
+
+template <bool TMA, bool SPLIT, class Epi>
+__device__ __forceinline__ void spmv_tiles(const CsrTiled &M, const double *x, SpmvSmem &sm, PipeState &ps, Epi &epi) {
+    if (TMA) spmv_tiles_tma<SPLIT>(M, x, sm, ps, epi);
+    else spmv_tiles_ldg<SPLIT>(M, x, sm, epi);
+}
+
+__device__ __forceinline__ void spmv_smem_init(SpmvSmem &sm, PipeState &ps) {
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&sm.full[s], 1);
+        mbar_init_fence();
+    }
+    ps.parity = 0;
+    __syncthreads();
+}
+
+}  // namespace qpb

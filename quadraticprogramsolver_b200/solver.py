@@ -1,0 +1,199 @@
+"""Host-side mirror of the reference's solver interface over the C ABI.
+
+The reference entry point is (SolveQuadraticProgram.jl:14-17)
+
+    SolveQuadraticProgram!(vX, mP, vQ, mA, vL, vU, LinSysSolInit, LinSysSol!;
+        numIterations = 5000, ϵAbs = 1e-6, ϵRel = 1e-6, ρ = 1, σ = 1e-6, α = 1.6, δ = 1e-6,
+        adptΡ = false, fctrΡ = 5, numItrConv = 25, numItrPolish = 10, ϵMinres = 1e-6, numItrMinres = 500)
+
+Here it is :func:`SolveQuadraticProgram_` (``!`` -> trailing underscore) with the same positional
+arguments, the same keyword names (Python accepts the Greek identifiers; ASCII aliases are accepted
+too) and the same return value (the ``ConvergenceFlag``), mutating ``vX`` in place.  The plugin pair
+is the singleton pair ``(B200Init, B200Sol)``: passing it selects the GPU path, exactly as a Julia
+call site would swap ``FacLdlInit, FacLdl!`` for ``B200Init, B200Sol!`` (see julia/QPB200.jl).
+``SolveQuadraticProgram(P, q, A, l, u; ...)`` is the convenience form BASELINE.json names.
+
+Julia is not available in this environment, so this module -- not julia/QPB200.jl -- is what the
+test-suite drives; both are thin and call the same C symbols in the same order.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _lib
+from ._lib import Info, QPB200Error, Settings  # noqa: F401
+
+
+class ConvergenceFlag(enum.IntEnum):
+    """``@enum ConvergenceFlag convNumItr = 1 convAdmm convPrimDual`` (SolveQuadraticProgram.jl:12)."""
+    convNumItr = 1
+    convAdmm = 2
+    convPrimDual = 3
+
+
+class _Plugin:
+    def __init__(self, name):
+        self._name = name
+
+    def __repr__(self):
+        return self._name
+
+
+#: the (Init, Sol!) pair that selects the B200 path (LinearSystemSolvers.jl:16,28 are the CPU pairs)
+B200Init = _Plugin("B200Init")
+B200Sol = _Plugin("B200Sol!")
+
+_ALIASES = {
+    "ϵAbs": "epsAbs", "ϵRel": "epsRel", "ρ": "rho", "σ": "sigma", "α": "alpha", "δ": "delta",
+    "adptΡ": "adptRho", "fctrΡ": "fctrRho", "ϵMinres": "epsMinres", "ϵPcg": "epsPcg",
+    # Python NFKC-normalises identifiers: the reference's lunate epsilon (U+03F5) arrives as U+03B5
+    "εAbs": "epsAbs", "εRel": "epsRel", "εMinres": "epsMinres", "εPcg": "epsPcg",
+}
+_DEFAULTS = dict(numIterations=5000, epsAbs=1e-6, epsRel=1e-6, rho=1.0, sigma=1e-6, alpha=1.6, delta=1e-6,
+                 adptRho=False, fctrRho=5.0, numItrConv=25, numItrPolish=10, epsMinres=1e-6, numItrMinres=500,
+                 # plugin kwargs (LinearSystemSolvers.jl:125) and the new ones
+                 epsPcg=1e-6, numItrPcg=1000, relPcg=-1.0, linSolver="pcg", precond="jacobi", device=-1,
+                 spmvLoader="auto")
+
+
+def make_settings(**kw) -> Settings:
+    """Keyword arguments of ``SolveQuadraticProgram!`` -> ``qpb200_settings``."""
+    opts = dict(_DEFAULTS)
+    for k, v in kw.items():
+        k = _ALIASES.get(k, k)
+        if k not in opts:
+            raise TypeError(f"SolveQuadraticProgram: unknown keyword argument {k!r}")
+        opts[k] = v
+    s = _lib.default_settings()
+    s.max_iter = int(opts["numIterations"])
+    s.eps_abs = float(opts["epsAbs"]); s.eps_rel = float(opts["epsRel"])
+    s.rho = float(opts["rho"]); s.sigma = float(opts["sigma"]); s.alpha = float(opts["alpha"])
+    s.delta = float(opts["delta"])
+    s.adaptive_rho = int(bool(opts["adptRho"]))
+    s.rho_factor = float(opts["fctrRho"])
+    s.check_every = int(opts["numItrConv"])
+    s.polish_iter = int(opts["numItrPolish"]); s.minres_eps = float(opts["epsMinres"])
+    s.minres_iter = int(opts["numItrMinres"])
+    s.pcg_eps = float(opts["epsPcg"]); s.pcg_max_iter = int(opts["numItrPcg"]); s.pcg_rel_eps = float(opts["relPcg"])
+    s.lin_solver = {"pcg": _lib.LINSOLVE_PCG, "cholesky": _lib.LINSOLVE_CHOLESKY}[str(opts["linSolver"]).lstrip(":")]
+    s.precond = {"none": _lib.PRECOND_NONE, "jacobi": _lib.PRECOND_JACOBI}[str(opts["precond"]).lstrip(":")]
+    s.device = int(opts["device"])
+    s.spmv_loader = {"auto": 0, "ldg": 1, "tma": 2}[str(opts["spmvLoader"])]
+    return s
+
+
+def _pd(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _p64(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int64))
+
+
+def _csc_arrays(mat):
+    """scipy matrix -> (colptr, rowval, nzval) int64/int64/float64, 0-based -- SparseMatrixCSC layout."""
+    mat = sp.csc_matrix(mat)
+    if not mat.has_sorted_indices:
+        mat = mat.sorted_indices()
+    return (np.ascontiguousarray(mat.indptr, dtype=np.int64), np.ascontiguousarray(mat.indices, dtype=np.int64),
+            np.ascontiguousarray(mat.data, dtype=np.float64))
+
+
+class QPB200Solver:
+    """A ``qpb200_handle``: the problem uploaded once, device-resident state, repeated solves."""
+
+    def __init__(self, mP, vQ, mA, vL, vU, **kw):
+        lib = _lib.load()
+        self.n = int(mP.shape[0])
+        self.m = int(mA.shape[0])
+        if mP.shape != (self.n, self.n) or mA.shape[1] != self.n:
+            raise ValueError("dimension mismatch between P and A")
+        vQ = np.ascontiguousarray(vQ, dtype=np.float64); vL = np.ascontiguousarray(vL, dtype=np.float64)
+        vU = np.ascontiguousarray(vU, dtype=np.float64)
+        if vQ.shape != (self.n,) or vL.shape != (self.m,) or vU.shape != (self.m,):
+            raise ValueError("dimension mismatch in q, l or u")
+        Pp, Pi, Pv = _csc_arrays(mP)
+        Ap, Ai, Av = _csc_arrays(mA)
+        self.settings = make_settings(**kw)
+        self._h = C.c_void_p()
+        _lib.check(lib.qpb200_create(C.byref(self._h), self.n, self.m, _p64(Pp), _p64(Pi), _pd(Pv), _p64(Ap), _p64(Ai),
+                                     _pd(Av), _pd(vQ), _pd(vL), _pd(vU), C.byref(self.settings), 0))
+        self.info = None
+
+    def solve(self, vX, want_zy: bool = False):
+        """Solve from start point ``vX`` (mutated in place).  Returns the ConvergenceFlag."""
+        if vX.dtype != np.float64 or not vX.flags.c_contiguous or vX.shape != (self.n,):
+            raise ValueError("vX must be a contiguous float64 vector of length n")
+        info = Info()
+        z = np.empty(self.m) if want_zy else None
+        y = np.empty(self.m) if want_zy else None
+        _lib.check(_lib.load().qpb200_solve(self._h, _pd(vX), _pd(z) if want_zy else None, _pd(y) if want_zy else None,
+                                            C.byref(info)))
+        self.info = info.as_dict()
+        if want_zy:
+            self.info["z"] = z
+            self.info["y"] = y
+        return ConvergenceFlag(info.conv_flag)
+
+    def update_vectors(self, vQ=None, vL=None, vU=None):
+        arr = [None if v is None else np.ascontiguousarray(v, dtype=np.float64) for v in (vQ, vL, vU)]
+        _lib.check(_lib.load().qpb200_update_vectors(self._h, *[None if a is None else _pd(a) for a in arr]))
+
+    def update_settings(self, **kw):
+        self.settings = make_settings(**kw)
+        _lib.check(_lib.load().qpb200_update_settings(self._h, C.byref(self.settings)))
+
+    def apply(self, which: int, x):
+        """Operators of the path: 0: P x, 1: A x, 2: A' x, 3: (P + sigma I + rho A'A) x."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty(self.m if which == 1 else self.n)
+        _lib.check(_lib.load().qpb200_apply(self._h, which, _pd(x), _pd(y)))
+        return y
+
+    def time_apply(self, which: int, reps: int = 20, flush_l2: bool = True) -> float:
+        ms = C.c_double(0.0)
+        _lib.check(_lib.load().qpb200_time_apply(self._h, which, reps, int(flush_l2), C.byref(ms)))
+        return ms.value
+
+    def apply_bytes(self, which: int) -> int:
+        return int(_lib.load().qpb200_apply_bytes(self._h, which))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.load().qpb200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def SolveQuadraticProgram_(vX, mP, vQ, mA, vL, vU, LinSysSolInit=B200Init, LinSysSol=B200Sol, **kw):
+    """``SolveQuadraticProgram!`` on the B200 (SolveQuadraticProgram.jl:14-76).  Mutates ``vX``
+    (start point in, solution out) and returns the ``ConvergenceFlag`` -- nothing else, like the
+    reference.  Only the ``(B200Init, B200Sol)`` plugin pair exists here: there is no CPU path."""
+    if LinSysSolInit is not B200Init or LinSysSol is not B200Sol:
+        raise TypeError("quadraticprogramsolver_b200 only provides the (B200Init, B200Sol) plugin pair; "
+                        "the CPU plugins live in the reference")
+    with QPB200Solver(mP, vQ, mA, vL, vU, **kw) as s:
+        return s.solve(vX)
+
+
+def SolveQuadraticProgram(P, q, A, l, u, x0=None, **kw):
+    """Convenience form named by BASELINE.json: returns ``(x, flag, info)``."""
+    x = np.zeros(P.shape[0]) if x0 is None else np.array(x0, dtype=np.float64)
+    with QPB200Solver(P, q, A, l, u, **kw) as s:
+        flag = s.solve(x, want_zy=True)
+        return x, flag, s.info

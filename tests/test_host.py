@@ -1,0 +1,197 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol of include/qpb200.h,
+argument validation / error codes, the settings mirror, and the SpMV tile plan (emulated in numpy)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from quadraticprogramsolver_b200 import _lib
+from quadraticprogramsolver_b200.problems import config_cfg1, sprandn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "qpb200.h")).read()
+    declared = set(re.findall(r"\b(qpb200_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.EXPORTS)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert lib.qpb200_version() == 100
+
+
+def test_struct_layout_matches_header(lib, tmp_path):
+    src = tmp_path / "sz.c"
+    src.write_text('#include "qpb200.h"\n#include <stdio.h>\n#include <stddef.h>\nint main(){printf("%zu %zu %zu %zu\\n", '
+                   'sizeof(qpb200_settings), sizeof(qpb200_info), offsetof(qpb200_settings, pcg_eps), '
+                   'offsetof(qpb200_info, solve_ms));return 0;}')
+    exe = tmp_path / "sz"
+    import subprocess
+    subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    a, b, c, d = map(int, subprocess.check_output([str(exe)]).split())
+    assert a == C.sizeof(_lib.Settings) and b == C.sizeof(_lib.Info)
+    assert c == _lib.Settings.pcg_eps.offset and d == _lib.Info.solve_ms.offset
+
+
+def test_default_settings_match_reference_kwargs(lib):
+    s = _lib.default_settings()
+    # SolveQuadraticProgram.jl:15-17 and LinearSystemSolvers.jl:125
+    assert (s.max_iter, s.eps_abs, s.eps_rel, s.rho, s.sigma, s.alpha) == (5000, 1e-6, 1e-6, 1.0, 1e-6, 1.6)
+    assert (s.adaptive_rho, s.rho_factor, s.check_every) == (0, 5.0, 25)
+    assert (s.pcg_eps, s.pcg_max_iter) == (1e-6, 1000)
+    assert (s.delta, s.polish_iter, s.minres_eps, s.minres_iter) == (1e-6, 10, 1e-6, 500)
+
+
+def test_settings_mirror_accepts_reference_keyword_names(lib):
+    from quadraticprogramsolver_b200.solver import make_settings
+    s = make_settings(numIterations=50000, ϵAbs=1e-7, ϵRel=1e-7, ρ=0.1, adptΡ=True, σ=1e-5, α=1.5, fctrΡ=4, numItrConv=10)
+    assert (s.max_iter, s.eps_abs, s.eps_rel, s.rho, s.adaptive_rho) == (50000, 1e-7, 1e-7, 0.1, 1)
+    assert (s.sigma, s.alpha, s.rho_factor, s.check_every) == (1e-5, 1.5, 4.0, 10)
+    with pytest.raises(TypeError):
+        make_settings(notAKeyword=1)
+
+
+def _create(lib, P, q, A, l, u, base=0, settings=None):
+    from quadraticprogramsolver_b200.solver import _csc_arrays, _p64, _pd
+    Pp, Pi, Pv = _csc_arrays(P)
+    Ap, Ai, Av = _csc_arrays(A)
+    h = C.c_void_p()
+    s = settings or _lib.default_settings()
+    rc = lib.qpb200_create(C.byref(h), P.shape[0], A.shape[0], _p64(Pp + base), _p64(Pi + base), _pd(Pv),
+                           _p64(Ap + base), _p64(Ai + base), _pd(Av), _pd(q), _pd(l), _pd(u), C.byref(s), base)
+    return rc, h
+
+
+def test_argument_validation_error_codes(lib):
+    """Validation runs before the device is touched, so these codes are observable without a GPU."""
+    P, q, A, l, u = config_cfg1()
+    qbad = q.copy(); qbad[3] = np.nan
+    rc, _ = _create(lib, P, qbad, A, l, u)
+    assert rc == _lib.ERR_NONFINITE and b"q[3]" in lib.qpb200_last_error()
+    lbad = l.copy(); lbad[0] = u[0] + 1.0
+    rc, _ = _create(lib, P, q, A, lbad, u)
+    assert rc == _lib.ERR_NONFINITE
+    Pbad = P.copy(); Pbad.data[0] = np.inf
+    rc, _ = _create(lib, Pbad, q, A, l, u)
+    assert rc == _lib.ERR_NONFINITE
+    rc, _ = _create(lib, P, q, A, l, u, base=2)
+    assert rc == _lib.ERR_ARG
+    s = _lib.default_settings(); s.rho = -1.0
+    rc, _ = _create(lib, P, q, A, l, u, settings=s)
+    assert rc in (_lib.ERR_ARG, _lib.ERR_DEVICE)   # settings are checked right after the device probe
+    # good arguments: on a machine without a B200 the library must refuse loudly (no CPU fallback)
+    rc, h = _create(lib, P, q, A, l, u, base=1)
+    msg = lib.qpb200_last_error()
+    if lib.qpb200_device_count() <= 0:
+        assert rc == _lib.ERR_DEVICE and b"no CPU fallback" in msg
+    else:
+        assert rc == 0
+        lib.qpb200_destroy(h)
+
+
+def test_python_mirror_rejects_foreign_plugins_and_bad_dims(lib):
+    from quadraticprogramsolver_b200.solver import QPB200Solver, SolveQuadraticProgram_
+    P, q, A, l, u = config_cfg1()
+    with pytest.raises(TypeError):
+        SolveQuadraticProgram_(np.zeros(100), P, q, A, l, u, object(), object())
+    with pytest.raises(ValueError):
+        QPB200Solver(P, q[:-1], A, l, u)
+
+
+# ---------------------------------------------------------------------------------------------------
+# tile plan: emulate exactly what the kernel does with (tiles, cta_begin) and compare with scipy
+# ---------------------------------------------------------------------------------------------------
+def _plan(lib, M, grid):
+    M = sp.csr_matrix(M)
+    ptr = np.ascontiguousarray(M.indptr, dtype=np.int32)
+    cap = M.shape[0] + M.nnz // 64 + 16
+    tiles = np.zeros((cap, 4), dtype=np.int32)
+    cta = np.zeros(grid + 1, dtype=np.int32)
+    lpr = C.c_int32(0)
+    p32 = C.POINTER(C.c_int32)
+    nt = lib.qpb200_debug_tile_plan(M.shape[0], ptr.ctypes.data_as(p32), grid, tiles.ctypes.data_as(p32), cap,
+                                    cta.ctypes.data_as(p32), C.byref(lpr))
+    assert 0 <= nt <= cap
+    return tiles[:nt], cta, lpr.value
+
+
+def _emulate(M, x, tiles, cta, T):
+    M = sp.csr_matrix(M)
+    y = np.full(M.shape[0], np.nan)
+    written = np.zeros(M.shape[0], dtype=int)
+    assert cta[0] == 0 and cta[-1] == len(tiles) and np.all(np.diff(cta) >= 0)
+    next_row, next_k = 0, 0
+    for b in range(len(cta) - 1):
+        carry = None
+        for t in range(cta[b], cta[b + 1]):
+            row0, nrows, k0, w = (int(v) for v in tiles[t])
+            nk = w & ((1 << 24) - 1)
+            from_prev, to_next = bool(w & (1 << 30)), bool(w & (1 << 29))
+            assert nk <= T and k0 == next_k
+            next_k = k0 + nk
+            prod = M.data[k0:k0 + nk] * x[M.indices[k0:k0 + nk]]
+            if from_prev or to_next:
+                assert nrows == 1
+                assert from_prev == (carry is not None), "a long row must stay on one CTA"
+                s = (carry or 0.0) + prod.sum()
+                if to_next:
+                    carry = s
+                else:
+                    y[row0] = s; written[row0] += 1; carry = None
+                    assert next_k == M.indptr[row0 + 1]
+                    next_row = row0 + 1
+            else:
+                assert carry is None and row0 == next_row and k0 == M.indptr[row0]
+                for r in range(row0, row0 + nrows):
+                    a, e = M.indptr[r] - k0, M.indptr[r + 1] - k0
+                    assert 0 <= a <= e <= nk
+                    y[r] = prod[a:e].sum(); written[r] += 1
+                next_row = row0 + nrows
+        assert carry is None
+    assert next_row == M.shape[0] and next_k == M.nnz
+    assert np.all(written == 1)
+    return y
+
+
+@pytest.mark.parametrize("case", ["random", "long_rows", "empty_rows", "dense", "tiny", "all_empty"])
+@pytest.mark.parametrize("grid", [1, 7, 296])
+def test_tile_plan_covers_matrix_exactly_once(lib, case, grid):
+    rng = np.random.default_rng(5)
+    T = lib.qpb200_debug_tile_nnz()
+    if case == "random":
+        M = sprandn(rng, 3000, 2000, 0.01).tocsr()
+    elif case == "long_rows":     # rows longer than a tile, incl. exact multiples of the tile size
+        M = sprandn(rng, 40, 3 * T + 5, 0.02).tolil()
+        M[3, :] = rng.standard_normal(3 * T + 5)
+        M[4, :2 * T] = rng.standard_normal(2 * T)
+        M[17, :T + 1] = 1.0
+        M[39, :] = 2.0
+        M = M.tocsr()
+    elif case == "empty_rows":
+        M = sprandn(rng, 20000, 50, 0.002).tocsr()
+    elif case == "dense":
+        M = sp.csr_matrix(rng.standard_normal((300, 300)))
+    elif case == "tiny":
+        M = sp.csr_matrix(np.array([[1.0, 0.0], [0.0, 0.0], [2.0, 3.0]]))
+    else:
+        M = sp.csr_matrix((5000, 10))
+    x = rng.standard_normal(M.shape[1])
+    tiles, cta, lpr = _plan(lib, M, grid)
+    assert lpr in (1, 2, 4, 8, 16, 32)
+    y = _emulate(M, x, tiles, cta, T)
+    ref = M @ x
+    assert np.allclose(y, ref, rtol=1e-12, atol=1e-12)
+
+
+def test_tile_plan_is_balanced(lib):
+    rng = np.random.default_rng(6)
+    M = sprandn(rng, 200000, 100000, 5e-5).tocsr()
+    tiles, cta, _ = _plan(lib, M, 296)
+    nk = tiles[:, 3] & ((1 << 24) - 1)
+    per_cta = np.array([nk[cta[b]:cta[b + 1]].sum() for b in range(296)])
+    assert per_cta.sum() == M.nnz
+    assert per_cta.max() <= 1.25 * per_cta.mean() + lib.qpb200_debug_tile_nnz()

@@ -1,0 +1,118 @@
+"""CPU tests of the oracle itself (the reference's RunTests.jl strategy with the absent OSQP/Gurobi
+cross-check replaced by an independent KKT certificate) and of the golden fixtures."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import c_oracle, qp_oracle
+from quadraticprogramsolver_b200.problems import (GenerateRandomQP, ProblemClass, config_cfg1, config_cfg3_batch,
+                                                  config_cfg4, config_cfg5)
+
+# RunTests.jl:50-56
+RUNTESTS_KW = dict(numIterations=50000, epsAbs=1e-7, epsRel=1e-7, rho=0.1, adptRho=True)
+ABS_DEV_THR = 1e-5   # RunTests.jl:58
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def _dims(pc, n):
+    # RunTests.jl:29-47: equality class uses m = 5 / 50, the rest the OSQP-paper defaults
+    return {ProblemClass.equalityConstrainedQp: {10: 5, 100: 50}[n]}.get(pc, 0)
+
+
+@pytest.mark.parametrize("pc", list(ProblemClass))
+@pytest.mark.parametrize("seed", [1234, 1235, 1236])
+def test_direct_mode_kkt_certificate_n10(pc, seed):
+    P, q, A, l, u = GenerateRandomQP(pc, 10, numConstraints=_dims(pc, 10), seed=seed)
+    x, flag, info = qp_oracle.solve(P, q, A, l, u, mode="D", **RUNTESTS_KW)
+    assert flag != qp_oracle.ConvergenceFlag.convNumItr
+    cert = qp_oracle.kkt_certificate(P, q, A, l, u, x, info["y"])
+    scale = 1.0 + max(np.max(np.abs(q)), np.max(np.abs(x)))
+    assert cert["stationarity"] <= 1e-5 * scale
+    assert cert["primal_infeasibility"] <= 1e-5 * scale
+    assert cert["complementarity"] <= 1e-4 * scale
+
+
+@pytest.mark.parametrize("pc", [ProblemClass.randomQp, ProblemClass.inequalityConstrainedQp,
+                                ProblemClass.equalityConstrainedQp, ProblemClass.portfolioOptimization,
+                                ProblemClass.isotonicRegression])
+def test_modes_agree_n100(pc):
+    """Modes D (what the reference's tests run), C, M (its CG plugins) and J agree to RunTests' 1e-5."""
+    P, q, A, l, u = GenerateRandomQP(pc, 100, numConstraints=_dims(pc, 100), seed=1234)
+    xs = {mode: qp_oracle.solve(P, q, A, l, u, mode=mode, **RUNTESTS_KW) for mode in "DCMJ"}
+    for mode in "CMJ":
+        assert np.max(np.abs(xs[mode][0] - xs["D"][0])) <= ABS_DEV_THR, mode
+        assert xs[mode][1] != qp_oracle.ConvergenceFlag.convNumItr
+
+
+@pytest.mark.parametrize("pc", [ProblemClass.lassoOptimization, ProblemClass.huberFitting,
+                                ProblemClass.supportVectorMachine])
+def test_modes_agree_inf_bounds(pc):
+    """The classes with +-Inf bounds (GenerateQuadraticProgram.jl:60-61,76,91-92)."""
+    P, q, A, l, u = GenerateRandomQP(pc, 10, seed=1234)
+    assert np.isinf(l).any() or np.isinf(u).any()
+    xd = qp_oracle.solve(P, q, A, l, u, mode="D", **RUNTESTS_KW)[0]
+    xm = qp_oracle.solve(P, q, A, l, u, mode="M", **RUNTESTS_KW)[0]
+    assert np.max(np.abs(xm - xd)) <= ABS_DEV_THR
+
+
+@pytest.mark.parametrize("precond", [0, 1])
+def test_c_restatement_matches_python(precond):
+    """qp_oracle.c vs qp_oracle.py (independently written; tight inner solve so the trajectory is
+    well defined)."""
+    for seed in (1234, 7):
+        P, q, A, l, u = config_cfg1(seed)
+        kw = dict(numIterations=5000, epsAbs=1e-6, epsRel=1e-6, rho=1.0, epsPcg=1e-10)
+        x, f, i = qp_oracle.solve(P, q, A, l, u, mode="J" if precond else "M", **kw)
+        xc, fc, ic = c_oracle.solve_sparse(P, q, A, l, u, precond=precond, **kw)
+        assert int(f) == fc
+        assert i["iterations"] == ic["iterations"]
+        assert np.max(np.abs(x - xc)) <= 1e-9 * (1 + np.max(np.abs(x)))
+
+
+def test_c_dense_batch_matches_python_direct():
+    P, q, A, l, u = config_cfg3_batch(6, n=16, m=24, seed=3)
+    X, flags, iters, _, rc = c_oracle.solve_dense_batch(P, q, A, l, u)
+    assert rc == 0
+    for b in range(6):
+        x, f, i = qp_oracle.solve(sp.csc_matrix(P[b]), q[b], sp.csc_matrix(A[b].T), l[b], u[b], mode="D")
+        assert int(f) == flags[b] and i["iterations"] == iters[b]
+        assert np.max(np.abs(x - X[b])) <= 1e-9 * (1 + np.max(np.abs(x)))
+
+
+def test_adaptive_rho_nan_is_ignored():
+    """0/0 in the rho update gives NaN; Julia's clamp passes it through and the trigger's comparisons
+    are false (SolveQuadraticProgram.jl:47,95)."""
+    assert np.isnan(qp_oracle._clamp(float("nan"), 1e-3, 1e6))
+    n = 4
+    P = sp.identity(n, format="csc")
+    A = sp.identity(n, format="csc")
+    x, flag, info = qp_oracle.solve(P, np.zeros(n), A, -np.ones(n), np.ones(n), mode="D", adptRho=True)
+    assert np.all(x == 0.0) and info["rho"] == 1.0 and flag != qp_oracle.ConvergenceFlag.convNumItr
+
+
+def test_config_shapes():
+    P, q, A, l, u = config_cfg5(scale=0.002)
+    assert P.shape == (2000, 2000) and A.shape == (4000, 2000)
+    assert abs(A.nnz / 4000 - 5) < 1.0
+    P, q, A, l, u = config_cfg4(scale=0.01)
+    assert P.shape == (500, 500) and A.shape == (300, 500)
+    assert np.isinf(l[:250]).all() and (l[250:] == u[250:]).all()
+
+
+@pytest.mark.skipif(not GOLDEN, reason="no golden fixtures")
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_golden_fixtures_reproduce(path):
+    """The committed fixtures (tests/golden/make_golden.py) pin the oracle against regressions."""
+    g = np.load(path)
+    P = sp.csc_matrix((g["P_data"], g["P_indices"], g["P_indptr"]), shape=tuple(g["P_shape"]))
+    A = sp.csc_matrix((g["A_data"], g["A_indices"], g["A_indptr"]), shape=tuple(g["A_shape"]))
+    kw = {k[3:]: g[k].item() for k in g.files if k.startswith("kw_")}
+    mode = str(g["mode"])
+    x, flag, info = qp_oracle.solve(P, g["q"], A, g["l"], g["u"], mode=mode, **kw)
+    assert int(flag) == int(g["flag"])
+    assert info["iterations"] == int(g["iterations"])
+    assert np.max(np.abs(x - g["x"])) <= 1e-9 * (1 + np.max(np.abs(g["x"])))
