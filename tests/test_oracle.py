@@ -27,6 +27,9 @@ def _dims(pc, n):
 @pytest.mark.parametrize("seed", [1234, 1235, 1236])
 def test_direct_mode_kkt_certificate_n10(pc, seed):
     P, q, A, l, u = GenerateRandomQP(pc, 10, numConstraints=_dims(pc, 10), seed=seed)
+    empty = np.diff(sp.csr_matrix(A).indptr) == 0
+    if np.any(empty & ((l > 0) | (u < 0))):
+        pytest.skip("structurally infeasible instance (empty row of A with 0 outside [l, u])")
     x, flag, info = qp_oracle.solve(P, q, A, l, u, mode="D", **RUNTESTS_KW)
     assert flag != qp_oracle.ConvergenceFlag.convNumItr
     cert = qp_oracle.kkt_certificate(P, q, A, l, u, x, info["y"])
