@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py -- ADMM iterations/s of the B200 path on BASELINE.json's headline configuration.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg5|cfg2|cfg3]
+
+Workload at N = 1 (default): configs[4], the 1M-variable sparse QP the metric's target is quoted on
+(n = 1e6, m = 2e6, d = 5e-6, same recipe as GenerateRandomQP(randomQp) with the bounds centred on A x* so
+that the QP is feasible -- see quadraticprogramsolver_b200/problems.py::config_sparse).  A *step* is one
+pass of the hot path over that QP: ADMM iterations 1..ITERS of SolveQuadraticProgram! from x = 0
+(ITERS = 100, four convergence checks), with the reference's default settings and Jacobi-PCG.
+
+  value : ADMM iterations/s, problem resident in HBM, device time (CUDA events inside qpb200_solve)
+  e2e   : same metric through the public call SolveQuadraticProgram(P, q, A, l, u) with HOST buffers:
+          qpb200_create (conversion + upload) + qpb200_solve (+ x, z, y download) + destroy, wall clock
+  roofline : the persistent ADMM kernel (the one launch of a step): algorithmic bytes of the matrix and
+          vector passes it executed / its CUDA-event duration, against the measured HBM
+          peak of MEASURED_PEAKS.json; plus the stand-alone SpMV numbers
+  cpu_baseline : oracle/qp_oracle.c (a compiled restatement -- Julia is unavailable) on all host
+          cores, same QP, same settings, a time-bounded sample of the same iterations
+
+`--impl reference` times that CPU restatement alone (kind "port").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+ITERS = 100                     # ADMM iterations per step
+CPU_SAMPLE_SECONDS = 20.0       # bounded CPU sample
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.thread, self.gpu_index = [], None, None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu_index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max((float(r[3]) for r in self.rows if len(r) > 3 and r[3].replace('.', '', 1).isdigit()),
+                                   default=None),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_workload(name, scale):
+    from quadraticprogramsolver_b200 import problems
+    t0 = time.time()
+    if name == "cfg5":
+        P, q, A, l, u = problems.config_cfg5(seed=1234, scale=scale)
+        desc = f"cfg5 sparse QP n={P.shape[0]} m={A.shape[0]} nnz(P)={P.nnz} nnz(A)={A.nnz} (randomQp recipe, d=5/n, feasible bounds)"
+    elif name == "cfg2":
+        P, q, A, l, u = problems.config_cfg2(seed=1234)
+        desc = f"cfg2 sparse QP n={P.shape[0]} m={A.shape[0]} nnz(P)={P.nnz} nnz(A)={A.nnz} (d=1e-3, feasible bounds)"
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    return (P, q, A, l, u), desc, time.time() - t0
+
+
+def solver_kwargs():
+    # reference defaults (SolveQuadraticProgram.jl:15-17, LinearSystemSolvers.jl:125) + iteration cap
+    return dict(numIterations=ITERS, epsAbs=1e-6, epsRel=1e-6, rho=1.0, sigma=1e-6, alpha=1.6, adptRho=False,
+                numItrConv=25, epsPcg=1e-6, numItrPcg=1000)
+
+
+def cpu_sample(prob, precond, seconds):
+    """Time-bounded run of the compiled oracle on the same QP (all host threads)."""
+    from oracle import c_oracle
+    P, q, A, l, u = prob
+    kw = solver_kwargs()
+    x, flag, info = c_oracle.solve_sparse(P, q, A, l, u, precond=precond, time_limit_s=seconds, **kw)
+    its, sec = info["iterations"], info["solve_seconds"]
+    return {"value": its / sec, "unit": "iter/s", "cores": c_oracle.num_threads(), "kind": "port",
+            "sample": f"ADMM iterations 1..{its} of the same QP ({sec:.1f} s wall, oracle/qp_oracle.c, "
+                      f"{'Jacobi-PCG' if precond else 'un-preconditioned CG (reference)'}, OpenMP)",
+            "cg_iters_per_s": info["cg_iters_total"] / sec, "iterations": its, "host_cpus": os.cpu_count()}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    prob, desc, gen_s = make_workload(args.workload, args.scale)
+    per_step = max(2.0, min(CPU_SAMPLE_SECONDS, 150.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_sample(prob, 1, per_step)
+    vals, samples = [], []
+    t0 = time.time()
+    for _ in range(args.steps):
+        s = cpu_sample(prob, 1, per_step)
+        vals.append(s["value"]); samples.append(s)
+    wall = time.time() - t0
+    its = sum(s["iterations"] for s in samples)
+    value = its / sum(s["iterations"] / s["value"] for s in samples)
+    cb = dict(samples[-1]); cb["value"] = value
+    line = {"impl": "reference", "metric": "admm_iters_per_s", "value": value, "unit": "iter/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "iters_per_step": "time-bounded sample", "linear_solver": "jacobi-pcg eps 1e-6"},
+            "cpu_baseline": cb,
+            "e2e": {"value": value, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def run_b200(args):
+    import ctypes as C
+
+    from quadraticprogramsolver_b200 import _lib, solver as S
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
+    import torch
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = dist_mod
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    prob, desc, gen_s = make_workload(args.workload, args.scale)
+    P, q, A, l, u = prob
+    n, m = P.shape[0], A.shape[0]
+    kw = solver_kwargs()
+    kw["device"] = local_rank
+    peak, peak_src = load_peaks()
+
+    # ---- device-resident arm ------------------------------------------------------------------
+    # N > 1: until the row-partitioned path is selected every rank holds a replica ("replicas only")
+    s = S.QPB200Solver(P, q, A, l, u, **kw)
+    x = np.zeros(n)
+    for _ in range(args.warmup):
+        x[:] = 0.0
+        s.solve(x)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    dev_ms, iters, pcg, launches, bytes_total = 0.0, 0, 0, 0, 0
+    for _ in range(args.steps):
+        x[:] = 0.0
+        s.solve(x)
+        dev_ms += s.info["solve_ms"]; iters += s.info["iterations"]; pcg += s.info["pcg_iters_total"]
+        launches += s.info["kernel_launches"]
+        bytes_total += s.apply_bytes(100)
+    barrier()
+    wall_resident = time.perf_counter() - t0
+    clocks = sampler.stop()
+    flag = int(s.info["conv_flag"])
+    if dist is not None:
+        t = torch.tensor([dev_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms = float(t.item())
+    value = world * iters / (dev_ms * 1e-3)
+    achieved = bytes_total / 1e9 / (dev_ms * 1e-3)
+
+    # stand-alone SpMV (the operator the north_star quotes): L2 flushed between launches
+    spmv = {}
+    if rank == 0:
+        for which, name in ((1, "A"), (4, "H=[P A']")):
+            ms = s.time_apply(which, reps=20, flush_l2=True)
+            gb = s.apply_bytes(which) / 1e9
+            spmv[name] = {"ms": ms, "GBs": gb / (ms * 1e-3), "frac": gb / (ms * 1e-3) / peak}
+    s.close()
+
+    # ---- end-to-end arm: host buffers -> create -> solve -> results on host, every step --------
+    Pp, Pi, Pv = S._csc_arrays(P)
+    Ap, Ai, Av = S._csc_arrays(A)
+    h2d = Pp.nbytes + Pi.nbytes + Pv.nbytes + Ap.nbytes + Ai.nbytes + Av.nbytes + q.nbytes + l.nbytes + u.nbytes + 8 * n
+    d2h = 8 * (n + 2 * m)
+    e2e_steps = max(1, min(args.steps, 3))
+    S.SolveQuadraticProgram(P, q, A, l, u, **kw)          # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    e2e_iters = 0
+    for _ in range(e2e_steps):
+        xx, fl, info = S.SolveQuadraticProgram(P, q, A, l, u, **kw)
+        e2e_iters += info["iterations"]
+        launches_e2e = info["kernel_launches"]
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_wall], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_wall = float(t.item())
+    e2e_value = world * e2e_iters / e2e_wall
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    line = {
+        "metric": "admm_iters_per_s", "value": value, "unit": "iter/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_ms / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak" if world > 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "iters_per_step": ITERS, "settings": "reference defaults (rho=1, sigma=1e-6, alpha=1.6, "
+                   "eps 1e-6, check every 25), Jacobi-PCG abstol 1e-6", "parallelism": "1 GPU" if world == 1 else
+                   f"{world} replicas (one per GPU)", "l2": "matrix streams (0.55 GB per operator application) exceed the 126 MB L2; "
+                   "stand-alone SpMV timings flush L2 between launches", "conv_flag": flag,
+                   "pcg_iters_per_step": pcg / max(1, args.steps), "gen_s": round(gen_s, 1)},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "iter/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "steps": e2e_steps, "ms_per_step": 1e3 * e2e_wall / e2e_steps},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "admm_kernel (persistent; 1 launch per step)", "peak_source": peak_src,
+                     "spmv": spmv, "note": "cfg5's uniformly random columns make every 8-byte gather of x move a 32-byte L2 "
+                     "sector; see DESIGN.md (L2-sector bound) and profiles/"},
+        "cg_iters_per_s": pcg / (dev_ms * 1e-3),
+    }
+    if world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_sample(prob, 1, CPU_SAMPLE_SECONDS)
+        line["cpu_baseline_reference_cg"] = cpu_sample(prob, 0, CPU_SAMPLE_SECONDS / 2)
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg5", choices=["cfg5", "cfg2"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink cfg5 (tests only)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -18,8 +18,12 @@ __global__ void scale_kernel(double *v, double a, int n) {
 __global__ void axpy_kernel(double *y, const double *x, double a, int n) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) y[i] += a * x[i];
 }
-__global__ void flush_kernel(double *buf, size_t n, double v) {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) buf[i] = v;
+// L2 flush by READING a buffer larger than L2 (a writing flush would leave dirty lines whose
+// write-back is then charged to the kernel being timed)
+__global__ void flush_kernel(const double *buf, size_t n, double *sink) {
+    double s = 0.0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) s += buf[i];
+    if (s == 123.456) *sink = s;
 }
 
 static int upload_tiled(DeviceArena &ar, const HostCsr &M, const HostTiles &T, CsrTiled &d) {
@@ -374,7 +378,10 @@ int SparseSolver::time_apply(int which, int reps, int flush_l2, double *ms_out) 
     if (reps <= 0 || !ms_out) return fail(QPB200_ERR_ARG, "qpb200_time_apply: reps > 0 and ms_out required");
     QPB_CUDA(cudaSetDevice(device));
     const size_t flush_n = (size_t)48 << 20;   // 48 Mi doubles = 384 MiB > 126 MB L2
-    if (flush_l2 && !flush_buf) QPB_CUDA(cudaMalloc(&flush_buf, flush_n * sizeof(double)));
+    if (flush_l2 && !flush_buf) {
+        QPB_CUDA(cudaMalloc(&flush_buf, flush_n * sizeof(double)));
+        QPB_CUDA(cudaMemset(flush_buf, 0, flush_n * sizeof(double)));
+    }
     const size_t nm = (size_t)n + (size_t)m;
     // deterministic non-trivial input
     std::vector<double> hx(nm);
@@ -382,7 +389,7 @@ int SparseSolver::time_apply(int which, int reps, int flush_l2, double *ms_out) 
     QPB_CUDA(cudaMemcpyAsync(prob.UT, hx.data(), nm * sizeof(double), cudaMemcpyHostToDevice, stream));
     double total = 0.0;
     for (int r = -2; r < reps; ++r) {     // 2 untimed warm-up launches
-        if (flush_l2) flush_kernel<<<1024, 256, 0, stream>>>(flush_buf, flush_n, (double)r);
+        if (flush_l2) flush_kernel<<<2048, 256, 0, stream>>>(flush_buf, flush_n, scratch);
         QPB_CUDA(cudaEventRecord(ev0, stream));
         int rc = 0;
         if (which == 3) {

@@ -23,6 +23,7 @@ constexpr int kTileNnz = 2048;          // non-zeros per tile
 constexpr int kTilePad = 8;             // alignment slack of a TMA-staged tile
 constexpr int kStages = 3;              // TMA pipeline depth
 constexpr int kTileCap = kTileNnz + kTilePad;
+constexpr int kGatherBatch = 4;        // independent x-gathers issued back to back per thread
 
 // tile descriptor: x = first row, y = #rows, z = first nnz (k0), w = #nnz | flags
 constexpr int kTileContFromPrev = 1 << 30;   // this tile continues a long row started earlier
@@ -117,11 +118,20 @@ __device__ __forceinline__ void spmv_tiles_ldg(const CsrTiled &M, const double *
         double *prod = sm.val[(t - tb) & 1];
         const int *col = M.col + k0;
         const double *val = M.val + k0;
-#pragma unroll 4
-        for (int k = threadIdx.x; k < nk; k += kThreads) {
-            const int c = __ldg(col + k);
-            const double v = __ldg(val + k);
-            prod[k] = v * x[c];
+        for (int kb = threadIdx.x; kb < nk; kb += kThreads * kGatherBatch) {
+            int c[kGatherBatch];
+            double v[kGatherBatch], xv[kGatherBatch];
+#pragma unroll
+            for (int j = 0; j < kGatherBatch; ++j) {
+                const int k = kb + j * kThreads;
+                c[j] = (k < nk) ? __ldg(col + k) : 0;
+                v[j] = (k < nk) ? __ldg(val + k) : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < kGatherBatch; ++j) xv[j] = (kb + j * kThreads < nk) ? x[c[j]] : 0.0;   // independent gathers in flight
+#pragma unroll
+            for (int j = 0; j < kGatherBatch; ++j)
+                if (kb + j * kThreads < nk) prod[kb + j * kThreads] = v[j] * xv[j];
         }
         __syncthreads();
         tile_row_sums<SPLIT>(M, td, prod, sm, epi);
@@ -160,8 +170,21 @@ __device__ __forceinline__ void spmv_tiles_tma(const CsrTiled &M, const double *
         ps.parity ^= (1u << s);
         double *val = sm.val[s] + off;
         const int *col = sm.col[s] + off;
-#pragma unroll 4
-        for (int k = threadIdx.x; k < nk; k += kThreads) val[k] = val[k] * x[col[k]];
+        for (int kb = threadIdx.x; kb < nk; kb += kThreads * kGatherBatch) {
+            int c[kGatherBatch];
+            double v[kGatherBatch], xv[kGatherBatch];
+#pragma unroll
+            for (int j = 0; j < kGatherBatch; ++j) {
+                const int k = kb + j * kThreads;
+                c[j] = (k < nk) ? col[k] : 0;
+                v[j] = (k < nk) ? val[k] : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < kGatherBatch; ++j) xv[j] = (kb + j * kThreads < nk) ? x[c[j]] : 0.0;   // independent gathers in flight
+#pragma unroll
+            for (int j = 0; j < kGatherBatch; ++j)
+                if (kb + j * kThreads < nk) val[kb + j * kThreads] = v[j] * xv[j];
+        }
         fence_proxy_async_smem();   // our generic accesses to the stages (incl. tile i-1's reads) before the refill
         __syncthreads();
         if (threadIdx.x == 0 && i + kStages - 1 < nt)

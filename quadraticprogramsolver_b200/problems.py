@@ -204,22 +204,41 @@ def config_cfg1(seed: int = 1234):
     return GenerateRandomQP(ProblemClass.randomQp, 100, seed=seed)
 
 
-def config_sparse(n: int, m: int, density: float, seed: int = 1234):
+def config_sparse(n: int, m: int, density: float, seed: int = 1234, feasible: bool = True):
     """Same recipe as randomQp with the density parameterised (cfg2: n=1e4, m=2e4, d=1e-3;
-    cfg5: n=1e6, m=2e6, d=5e-6)."""
-    return GenerateRandomQP(ProblemClass.randomQp, n, numConstraints=m, seed=seed, densityFctr=density)
+    cfg5: n=1e6, m=2e6, d=5e-6).
+
+    With m = 2n two-sided rows around 0 plus 15 % equality rows -- and, at ~5 non-zeros per row, empty
+    rows of A whose equality value is not 0 -- the literal recipe is primal infeasible (ADMM then runs
+    to the iteration cap with ||Ax - z||inf stuck near 1).  ``feasible=True`` (default) keeps the recipe's
+    structure but centres the bounds on A x* for a random x*: l = A x* - rand, u = A x* + rand,
+    equality rows l = u = A x* (15 %), and the reference's ``u = 1`` quirk becomes u = A x* + 1 (15 %),
+    so x* is feasible by construction (as BASELINE.md does for cfg4)."""
+    mP, vQ, mA, vL, vU = GenerateRandomQP(ProblemClass.randomQp, n, numConstraints=m, seed=seed, densityFctr=density)
+    if feasible:
+        rng = np.random.default_rng(seed + 7919)
+        centre = mA @ rng.standard_normal(n)
+        mm = mA.shape[0]
+        vL = centre - rng.random(mm)
+        vU = centre + rng.random(mm)
+        vI = rng.random(mm) <= 0.15
+        vL[vI] = centre[vI]
+        vU[vI] = centre[vI]
+        vI = rng.random(mm) <= 0.15
+        vU[vI] = centre[vI] + 1.0
+    return mP, vQ, mA, vL, vU
 
 
-def config_cfg2(seed: int = 1234):
-    return config_sparse(10_000, 20_000, 1e-3, seed)
+def config_cfg2(seed: int = 1234, feasible: bool = True):
+    return config_sparse(10_000, 20_000, 1e-3, seed, feasible)
 
 
-def config_cfg5(seed: int = 1234, scale: float = 1.0):
+def config_cfg5(seed: int = 1234, scale: float = 1.0, feasible: bool = True):
     """configs[4]: n=1M, m=2M, d=5e-6.  ``scale`` < 1 shrinks n, m and raises the density so that
     the non-zeros per row stay the same (5 per row of M and of A) -- used by tests."""
     n = int(round(1_000_000 * scale))
     m = 2 * n
-    return config_sparse(n, m, 5.0 / n, seed)
+    return config_sparse(n, m, 5.0 / n, seed, feasible)
 
 
 def config_cfg4(seed: int = 1234, scale: float = 1.0):
