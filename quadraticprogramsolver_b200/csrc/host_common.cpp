@@ -135,6 +135,17 @@ void assign_tiles(HostTiles &t, int grid) {
     // anything left (rounding) goes to the last CTA
 }
 
+bool all_finite(const double *v, size_t count) {
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    size_t i = 0;
+    for (; i + 8 <= count; i += 8)
+        for (int j = 0; j < 8; ++j) acc[j] += v[i + j] * 0.0;
+    for (; i < count; ++i) acc[0] += v[i] * 0.0;
+    double s = 0.0;
+    for (int j = 0; j < 8; ++j) s += acc[j];
+    return s == 0.0;
+}
+
 int check_device(int device) {
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);

@@ -79,6 +79,9 @@ void build_tiles(const HostCsr &M, int tile_nnz, HostTiles &out);
 void assign_tiles(HostTiles &t, int grid);
 int choose_lpr(const HostCsr &M);
 
+// true iff every entry is finite (vectorisable: v * 0 is NaN exactly for NaN / +-Inf)
+bool all_finite(const double *v, size_t count);
+
 int check_device(int device);   // 0 or QPB200_ERR_DEVICE / QPB200_ERR_CUDA
 
 }  // namespace qpb

@@ -197,3 +197,70 @@ def SolveQuadraticProgram(P, q, A, l, u, x0=None, **kw):
     with QPB200Solver(P, q, A, l, u, **kw) as s:
         flag = s.solve(x, want_zy=True)
         return x, flag, s.info
+
+
+class QPB200Batch:
+    """A ``qpb200_batch``: ``batch`` independent small dense QPs on one GPU (configs[2]).
+
+    ``P[batch, n, n]`` and ``A[batch, n, m]`` hold each problem's block column-major (``A[b, j, i] =
+    A_b[i, j]``; see ``problems.config_cfg3_batch``); ``q[batch, n]``, ``l, u[batch, m]``."""
+
+    def __init__(self, P, q, A_cm, l, u, **kw):
+        lib = _lib.load()
+        P = np.ascontiguousarray(P, dtype=np.float64); A_cm = np.ascontiguousarray(A_cm, dtype=np.float64)
+        q = np.ascontiguousarray(q, dtype=np.float64); l = np.ascontiguousarray(l, dtype=np.float64)
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        self.batch, self.n = int(P.shape[0]), int(P.shape[1])
+        self.m = int(A_cm.shape[2])
+        if P.shape != (self.batch, self.n, self.n) or A_cm.shape != (self.batch, self.n, self.m):
+            raise ValueError("P must be [batch, n, n] and A [batch, n, m] (column-major m x n blocks)")
+        if q.shape != (self.batch, self.n) or l.shape != (self.batch, self.m) or u.shape != (self.batch, self.m):
+            raise ValueError("dimension mismatch in q, l or u")
+        kw.setdefault("linSolver", "cholesky")
+        unblocked = bool(kw.pop("unblockedCholesky", False))
+        self.settings = make_settings(**kw)
+        self.settings.reserved_i[0] = 1 if unblocked else 0
+        self._h = C.c_void_p()
+        _lib.check(lib.qpb200_batch_create(C.byref(self._h), self.batch, self.n, self.m, _pd(P), _pd(A_cm), _pd(q), _pd(l),
+                                           _pd(u), C.byref(self.settings)))
+        self.info = None
+
+    def solve(self, X=None):
+        """Returns ``(X, flags, iters)``; ``X`` (start points, default zeros) is mutated in place."""
+        if X is None:
+            X = np.zeros((self.batch, self.n))
+        if X.dtype != np.float64 or not X.flags.c_contiguous or X.shape != (self.batch, self.n):
+            raise ValueError("X must be a contiguous float64 array [batch, n]")
+        flags = np.zeros(self.batch, dtype=np.int32)
+        iters = np.zeros(self.batch, dtype=np.int64)
+        info = Info()
+        _lib.check(_lib.load().qpb200_batch_solve(self._h, _pd(X), flags.ctypes.data_as(C.POINTER(C.c_int32)), _p64(iters),
+                                                  C.byref(info)))
+        self.info = info.as_dict()
+        return X, flags, iters
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.load().qpb200_batch_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def SolveQuadraticProgramBatch(P, q, A_cm, l, u, X0=None, **kw):
+    """Batched form: every problem is solved as ``SolveQuadraticProgram!`` with a direct (exact-solve)
+    plugin would.  Returns ``(X, flags, iters, info)``."""
+    with QPB200Batch(P, q, A_cm, l, u, **kw) as b:
+        X = None if X0 is None else np.array(X0, dtype=np.float64)
+        X, flags, iters = b.solve(X)
+        return X, flags, iters, b.info

@@ -1,0 +1,85 @@
+"""GPU parity tests of the batched dense path (configs[2]) against the oracle's exact-solve mode D --
+the configuration the reference's own tests run (FacLdl, RunTests.jl:55-56)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import c_oracle, qp_oracle
+from quadraticprogramsolver_b200.problems import config_cfg3_batch
+
+pytestmark = pytest.mark.gpu
+
+
+def _S():
+    from quadraticprogramsolver_b200 import solver
+    return solver
+
+
+def _check(X, flags, iters, Xr, fr, ir, tol=1e-6):
+    assert np.array_equal(flags, fr), f"flags differ at {np.nonzero(flags != fr)[0][:8]}"
+    assert np.max(np.abs(iters - ir)) <= 2, f"iterations differ: {np.max(np.abs(iters - ir))}"
+    err = np.max(np.abs(X - Xr), axis=1)
+    ref = 1.0 + np.max(np.abs(Xr), axis=1)
+    assert np.all(err <= tol * ref), f"max |x - x_ref| / (1+|x_ref|) = {np.max(err / ref):.3e}"
+
+
+@pytest.mark.parametrize("unblocked", [False, True])
+@pytest.mark.parametrize("kw", [dict(), dict(rho=0.1, adptRho=True, epsAbs=1e-7, epsRel=1e-7, numIterations=50000)],
+                         ids=["defaults", "runtests_adaptive_rho"])
+def test_cfg3_shape_matches_oracle(lib, kw, unblocked):
+    """n = 64, m = 96: the configs[2] shape; both Cholesky variants (DMMA-blocked / unblocked)."""
+    P, q, A, l, u = config_cfg3_batch(96, 64, 96, seed=1234)
+    X, flags, iters, info = _S().SolveQuadraticProgramBatch(P, q, A, l, u, unblockedCholesky=unblocked, **kw)
+    Xr, fr, ir, _, rc = c_oracle.solve_dense_batch(P, q, A, l, u, **kw)
+    assert rc == 0
+    _check(X, flags, iters, Xr, fr, ir)
+    assert info["iterations"] == int(iters.sum())
+
+
+@pytest.mark.parametrize("n,m", [(8, 4), (30, 45), (64, 128), (63, 97), (1, 1)])
+def test_padded_shapes(lib, n, m):
+    """n < 64 and m not a multiple of 4 are zero padded inside the kernel."""
+    P, q, A, l, u = config_cfg3_batch(20, n, m, seed=5)
+    X, flags, iters, info = _S().SolveQuadraticProgramBatch(P, q, A, l, u)
+    Xr, fr, ir, _, rc = c_oracle.solve_dense_batch(P, q, A, l, u)
+    _check(X, flags, iters, Xr, fr, ir)
+
+
+def test_against_python_direct_plugin(lib):
+    """Against qp_oracle.py mode D = the KKT-matrix LDL' solve of LinearSystemSolvers.jl:16-107."""
+    P, q, A, l, u = config_cfg3_batch(4, 64, 96, seed=9)
+    X, flags, iters, _ = _S().SolveQuadraticProgramBatch(P, q, A, l, u)
+    for b in range(4):
+        x, f, i = qp_oracle.solve(sp.csc_matrix(P[b]), q[b], sp.csc_matrix(A[b].T), l[b], u[b], mode="D")
+        assert int(f) == flags[b] and abs(i["iterations"] - iters[b]) <= 2
+        assert np.max(np.abs(x - X[b])) <= 1e-6 * (1 + np.max(np.abs(x)))
+
+
+def test_start_points_and_more_problems_than_ctas(lib):
+    """More QPs than resident CTAs (persistent loop over the batch) and non-zero start points."""
+    P, q, A, l, u = config_cfg3_batch(1500, 16, 24, seed=2)
+    X0 = np.random.default_rng(0).standard_normal((1500, 16))
+    X, flags, iters, _ = _S().SolveQuadraticProgramBatch(P, q, A, l, u, X0=X0)
+    Xr, fr, ir, _, rc = c_oracle.solve_dense_batch(P, q, A, l, u, x0=X0)
+    _check(X, flags, iters, Xr, fr, ir)
+
+
+def test_breakdown_is_reported(lib):
+    """An indefinite P makes a pivot non-positive: QPB200_ERR_FACTOR, not a silent wrong answer."""
+    from quadraticprogramsolver_b200 import _lib
+    P, q, A, l, u = config_cfg3_batch(3, 8, 4, seed=1)
+    P[1] = -10.0 * np.eye(8)
+    with pytest.raises(_lib.QPB200Error) as e:
+        _S().SolveQuadraticProgramBatch(P, q, A, l, u, sigma=1e-6)
+    assert e.value.code == _lib.ERR_FACTOR
+
+
+def test_batch_argument_validation(lib):
+    from quadraticprogramsolver_b200 import _lib
+    P, q, A, l, u = config_cfg3_batch(3, 8, 4, seed=1)
+    q2 = q.copy(); q2[2, 1] = np.inf
+    with pytest.raises(_lib.QPB200Error) as e:
+        _S().SolveQuadraticProgramBatch(P, q2, A, l, u)
+    assert e.value.code == _lib.ERR_NONFINITE
+    with pytest.raises(ValueError):
+        _S().QPB200Batch(P, q[:, :-1], A, l, u)
