@@ -35,6 +35,7 @@ struct DenseBatchParams {
     long long *iters;
     int *factor_fail;            // set to 1 if any pivot was not positive
     unsigned long long *totals;  // [0] iterations, [1] rho updates
+    unsigned int *queue;         // next problem index (zeroed before every launch)
     int blocked_chol;
     AdmmSettingsDev s;
 };
@@ -248,22 +249,31 @@ __device__ __forceinline__ void trtri_packed(const DenseSmem &sm) {
     __syncthreads();
 }
 
-// y_j = sum_i A[i, j] v_i for j = 0..63 : thread (j = tid % 64, half = tid / 64), skewed start so that
-// the 16 lanes of a phase hit 16 different banks with the un-padded leading dimension
-__device__ __forceinline__ double at_times_v_partial(const double *As, int mp, const double *v) {
-    const int j = threadIdx.x & 63, half = threadIdx.x >> 6;
-    const int hlen = mp >> 1;                 // mp is a multiple of 4 -> halves of even length
-    const double *col = As + (size_t)mp * j + half * hlen;
-    const double *vv = v + half * hlen;
-    double s0 = 0.0, s1 = 0.0;
-    int i = j % hlen;
-    for (int c = 0; c < hlen; c += 2) {
+// Mapping of the per-iteration matrix-vector products: output o = tid >> 1 is computed by the two adjacent
+// lanes h = tid & 1 (each one half of the sum) and combined with one shuffle -- no shared-memory round trip.
+//
+// s_o = sum_i A[i, o] v_i (o = 0..63): lane h sums rows [h*hlen, (h+1)*hlen), starting at a lane-dependent
+// offset so that the 16 lanes of a shared-memory phase hit 16 different banks although the leading
+// dimension mp is a multiple of 16.
+__device__ __forceinline__ double at_times_v(const double *As, int mp, const double *v) {
+    const int o = threadIdx.x >> 1, h = threadIdx.x & 1;
+    const int hlen = mp >> 1;                 // mp is a multiple of 4
+    const double *col = As + (size_t)mp * o + h * hlen;
+    const double *vv = v + h * hlen;
+    const int i0 = (threadIdx.x & 15) < hlen ? (threadIdx.x & 15) : 0;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int i = i0;
+    for (; i + 4 <= hlen; i += 4) {
         s0 += col[i] * vv[i];
-        i = (i + 1 == hlen) ? 0 : i + 1;
-        s1 += col[i] * vv[i];
-        i = (i + 1 == hlen) ? 0 : i + 1;
+        s1 += col[i + 1] * vv[i + 1];
+        s2 += col[i + 2] * vv[i + 2];
+        s3 += col[i + 3] * vv[i + 3];
     }
-    return s0 + s1;
+    for (; i < hlen; ++i) s0 += col[i] * vv[i];
+    for (i = 0; i < i0; ++i) s1 += col[i] * vv[i];
+    double s = (s0 + s1) + (s2 + s3);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    return s;
 }
 
 // block-wide max of `nv` values held per thread (NaN-propagating), broadcast to all threads
@@ -297,7 +307,14 @@ __global__ void __launch_bounds__(kDThreads) dense_batch_kernel(DenseBatchParams
     const double eps_admm = fmin(p.s.eps_abs, p.s.eps_rel) * 1e-2;
     unsigned long long tot_iters = 0, tot_rho = 0;
 
-    for (int b = blockIdx.x; b < p.batch; b += gridDim.x) {
+    __shared__ int next_b;
+    for (;;) {
+        // dynamic work queue: iteration counts vary by 100x between problems, static striding leaves a long tail
+        __syncthreads();
+        if (tid == 0) next_b = (int)atomicAdd(p.queue, 1u);
+        __syncthreads();
+        const int b = next_b;
+        if (b >= p.batch) break;
         const double *Pg = p.P + (size_t)b * n * n;
         const double *Ag = p.A + (size_t)b * m * n;
         __syncthreads();
@@ -349,53 +366,66 @@ __global__ void __launch_bounds__(kDThreads) dense_batch_kernel(DenseBatchParams
             }
             __syncthreads();
             // ---- rhs = sigma x - q + A' w,  w = rho z - y      (LinearSystemSolvers.jl:37-38 reduced)
-            sm.part[tid] = at_times_v_partial(sm.As, mp, sm.w);
-            __syncthreads();
-            if (tid < kDN) sm.rhs[tid] = sigma * sm.x[tid] - sm.q[tid] + (sm.part[tid] + sm.part[tid + 64]);
-            __syncthreads();
-            // ---- t = Linv rhs   (row i: j = 0..i, split between the two halves)
+            const int o = tid >> 1, h = tid & 1;
             {
-                const int i = tid & 63, th = tid >> 6;
-                const int mid = (i + 1) >> 1;
-                const int ja = th == 0 ? 0 : mid, jb = th == 0 ? mid : i + 1;
-                const double *row = sm.Lp + pidx(i, 0);
-                double s = 0.0;
-                for (int j = ja; j < jb; ++j) s += row[j] * sm.rhs[j];
-                sm.part[tid] = s;
+                const double s = at_times_v(sm.As, mp, sm.w);
+                if (h == 0) sm.rhs[o] = sigma * sm.x[o] - sm.q[o] + s;
             }
             __syncthreads();
-            if (tid < kDN) sm.tt[tid] = sm.part[tid] + sm.part[tid + 64];
-            __syncthreads();
-            // ---- x~ = Linv' t   (row i: k = i..63)
+            // ---- t = Linv rhs   (row o: j = 0..o, split between the two lanes)
             {
-                const int i = tid & 63, th = tid >> 6;
-                const int mid = i + ((kDN - i + 1) >> 1);
-                const int ka = th == 0 ? i : mid, kb = th == 0 ? mid : kDN;
-                double s = 0.0;
-                for (int k = ka; k < kb; ++k) s += sm.Lp[pidx(k, i)] * sm.tt[k];
-                sm.part[tid] = s;
+                const int mid = (o + 1) >> 1;
+                const int ja = h == 0 ? 0 : mid, jb = h == 0 ? mid : o + 1;
+                const double *row = sm.Lp + pidx(o, 0);
+                double s0 = 0.0, s1 = 0.0;
+                int j = ja;
+                for (; j + 2 <= jb; j += 2) {
+                    s0 += row[j] * sm.rhs[j];
+                    s1 += row[j + 1] * sm.rhs[j + 1];
+                }
+                if (j < jb) s0 += row[j] * sm.rhs[j];
+                double s = s0 + s1;
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                if (h == 0) sm.tt[o] = s;
             }
             __syncthreads();
+            // ---- x~ = Linv' t   (column o: k = o..63), then the x relaxation (:57)
             double dx = 0.0, dz = 0.0;
-            if (tid < kDN) {
-                const double xt = sm.part[tid] + sm.part[tid + 64];
-                sm.xt[tid] = xt;
-                const double x_old = sm.x[tid];
-                const double x_new = alpha * xt + alpha1 * x_old;            // :57
-                sm.x[tid] = x_new;
-                dx = fabs(x_new - x_old);
+            {
+                const int mid = o + ((kDN - o + 1) >> 1);
+                const int ka = h == 0 ? o : mid, kb = h == 0 ? mid : kDN;
+                double s0 = 0.0, s1 = 0.0;
+                int k = ka;
+                int idx = pidx(ka, o);
+                for (; k + 2 <= kb; k += 2) {
+                    s0 += sm.Lp[idx] * sm.tt[k];
+                    s1 += sm.Lp[idx + k + 1] * sm.tt[k + 1];
+                    idx += 2 * k + 3;
+                }
+                if (k < kb) s0 += sm.Lp[idx] * sm.tt[k];
+                double s = s0 + s1;
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                if (h == 0) {
+                    sm.xt[o] = s;
+                    const double x_old = sm.x[o];
+                    const double x_new = alpha * s + alpha1 * x_old;         // :57
+                    sm.x[o] = x_new;
+                    dx = fabs(x_new - x_old);
+                }
             }
             __syncthreads();
             // ---- z~ = A x~, then the z / y update (:59-61), row-local
             if (tid < m) {
                 const double *row = sm.As + tid;
-                double s0 = 0.0, s1 = 0.0;
-#pragma unroll 8
-                for (int j = 0; j < kDN; j += 2) {
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll 4
+                for (int j = 0; j < kDN; j += 4) {
                     s0 += row[(size_t)mp * j] * sm.xt[j];
                     s1 += row[(size_t)mp * (j + 1)] * sm.xt[j + 1];
+                    s2 += row[(size_t)mp * (j + 2)] * sm.xt[j + 2];
+                    s3 += row[(size_t)mp * (j + 3)] * sm.xt[j + 3];
                 }
-                const double zt = s0 + s1;
+                const double zt = (s0 + s1) + (s2 + s3);
                 const double z_old = sm.z[tid], y_old = sm.y[tid];
                 const double zr = alpha * zt + alpha1 * z_old;
                 const double z_new = clamp_julia(zr + rho1 * y_old, sm.l[tid], sm.u[tid]);
@@ -417,24 +447,15 @@ __global__ void __launch_bounds__(kDThreads) dense_batch_kernel(DenseBatchParams
                     nr[2] = fabs(s0 - zi);
                     nr[3] = nanmax(fabs(s0), fabs(zi));
                 }
-                const double aty_part = at_times_v_partial(sm.As, mp, sm.y);
-                double px_part = 0.0;
-                {
-                    const int i = tid & 63, th = tid >> 6;
-                    if (i < n) {
-                        const int ja = th == 0 ? 0 : (n >> 1), jb = th == 0 ? (n >> 1) : n;
-                        for (int j = ja; j < jb; ++j) px_part += __ldg(Pg + i + (size_t)n * j) * sm.x[j];
-                    }
+                const double aty = at_times_v(sm.As, mp, sm.y);
+                double px = 0.0;
+                if (o < n) {
+                    const int ja = h == 0 ? 0 : (n >> 1), jb = h == 0 ? (n >> 1) : n;
+                    for (int j = ja; j < jb; ++j) px += __ldg(Pg + o + (size_t)n * j) * sm.x[j];
                 }
-                sm.part[tid] = aty_part;
-                sm.tt[tid & 63] = 0.0;
-                __syncthreads();
-                if (tid >= 64) sm.tt[tid - 64] = px_part;
-                __syncthreads();
-                if (tid < kDN) {
-                    const double aty = sm.part[tid] + sm.part[tid + 64];
-                    const double px = px_part + sm.tt[tid];
-                    nr[4] = fabs(px + sm.q[tid] + aty);
+                px += __shfl_xor_sync(0xffffffffu, px, 1);
+                if (h == 0) {
+                    nr[4] = fabs(px + sm.q[o] + aty);
                     nr[5] = nanmax(fabs(px), fabs(aty));
                 }
                 block_max<6>(nr, sm.red);
@@ -546,6 +567,7 @@ int qpb200_batch_create(qpb200_batch **out, int64_t batch, int64_t n, int64_t m,
     QPB_CUDA_H(B.arena.alloc(&B.prm.iters, (size_t)batch));
     QPB_CUDA_H(B.arena.alloc(&B.prm.factor_fail, 1, true));
     QPB_CUDA_H(B.arena.alloc(&B.prm.totals, 4, true));
+    QPB_CUDA_H(B.arena.alloc(&B.prm.queue, 4, true));
     QPB_CUDA_H(cudaStreamCreateWithFlags(&B.stream, cudaStreamNonBlocking));
     QPB_CUDA_H(cudaEventCreate(&B.ev0));
     QPB_CUDA_H(cudaEventCreate(&B.ev1));
@@ -584,6 +606,7 @@ int qpb200_batch_solve(qpb200_batch *h, double *X_inout, int32_t *flags, int64_t
     QPB_CUDA(cudaMemcpyAsync(B.prm.X, X_inout, nx * sizeof(double), cudaMemcpyHostToDevice, B.stream));
     QPB_CUDA(cudaMemsetAsync(B.prm.totals, 0, 4 * sizeof(unsigned long long), B.stream));
     QPB_CUDA(cudaMemsetAsync(B.prm.factor_fail, 0, sizeof(int), B.stream));
+    QPB_CUDA(cudaMemsetAsync(B.prm.queue, 0, 4 * sizeof(unsigned int), B.stream));
     QPB_CUDA(cudaEventRecord(B.ev0, B.stream));
     dense_batch_kernel<<<B.grid, kDThreads, B.smem, B.stream>>>(B.prm);
     QPB_CUDA(cudaGetLastError());

@@ -57,11 +57,29 @@ struct PipeState {     // uniform across the CTA
     uint32_t parity;   // bit s = parity to wait for on stage s
 };
 
+// Row pointers of the first row-sum round, fetched *before* the gather phase so that their L2 latency
+// overlaps the gathers (ncu r1: 13 % of the stall samples sat on these loads).
+struct RowPre {
+    int a, b, mid;
+};
+
+template <bool SPLIT>
+__device__ __forceinline__ RowPre prefetch_rowptr(const CsrTiled &M, const int4 td) {
+    RowPre rp{0, 0, 0};
+    const int r = threadIdx.x / M.lpr;
+    if (r < td.y && !(td.w & (kTileContFromPrev | kTileContToNext))) {
+        rp.a = __ldg(M.rowptr + td.x + r);
+        rp.b = __ldg(M.rowptr + td.x + r + 1);
+        if (SPLIT) rp.mid = __ldg(M.rowmid + td.x + r);
+    }
+    return rp;
+}
+
 // ---- row-sum step shared by both loaders ---------------------------------------------------
 // prod: shared products of this tile, element k of the tile at prod[k] (k relative to k0).
 template <bool SPLIT, class Epi>
 __device__ __forceinline__ void tile_row_sums(const CsrTiled &M, const int4 td, const double *prod, SpmvSmem &sm,
-                                              Epi &epi) {
+                                              const RowPre pre, Epi &epi) {
     const int row0 = td.x, nrows = td.y, k0 = td.z;
     const int nk = td.w & kTileNkMask;
     const bool from_prev = td.w & kTileContFromPrev, to_next = td.w & kTileContToNext;
@@ -90,11 +108,12 @@ __device__ __forceinline__ void tile_row_sums(const CsrTiled &M, const int4 td, 
         double s0 = 0.0, s1 = 0.0;
         if (r < nrows) {
             const int row = row0 + r;
-            const int a = __ldg(M.rowptr + row) - k0, b = __ldg(M.rowptr + row + 1) - k0;
+            const int a = (rb == 0 ? pre.a : __ldg(M.rowptr + row)) - k0;
+            const int b = (rb == 0 ? pre.b : __ldg(M.rowptr + row + 1)) - k0;
             if (!SPLIT) {
                 for (int k = a + gl; k < b; k += lpr) s0 += prod[k];
             } else {
-                const int mid = __ldg(M.rowmid + row) - k0;
+                const int mid = (rb == 0 ? pre.mid : __ldg(M.rowmid + row)) - k0;
                 for (int k = a + gl; k < mid; k += lpr) s0 += prod[k];
                 for (int k = mid + gl; k < b; k += lpr) s1 += prod[k];
             }
@@ -116,6 +135,7 @@ __device__ __forceinline__ void spmv_tiles_ldg(const CsrTiled &M, const double *
         const int4 td = __ldg(M.tiles + t);
         const int k0 = td.z, nk = td.w & kTileNkMask;
         double *prod = sm.val[(t - tb) & 1];
+        const RowPre pre = prefetch_rowptr<SPLIT>(M, td);
         const int *col = M.col + k0;
         const double *val = M.val + k0;
         for (int kb = threadIdx.x; kb < nk; kb += kThreads * kGatherBatch) {
@@ -134,7 +154,7 @@ __device__ __forceinline__ void spmv_tiles_ldg(const CsrTiled &M, const double *
                 if (kb + j * kThreads < nk) prod[kb + j * kThreads] = v[j] * xv[j];
         }
         __syncthreads();
-        tile_row_sums<SPLIT>(M, td, prod, sm, epi);
+        tile_row_sums<SPLIT>(M, td, prod, sm, pre, epi);
     }
     __syncthreads();
 }
@@ -166,6 +186,7 @@ __device__ __forceinline__ void spmv_tiles_tma(const CsrTiled &M, const double *
         const int4 td = __ldg(M.tiles + tb + i);
         const int k0 = td.z, nk = td.w & kTileNkMask;
         const int off = k0 & 3;
+        const RowPre pre = prefetch_rowptr<SPLIT>(M, td);
         mbar_wait(&sm.full[s], (ps.parity >> s) & 1u);
         ps.parity ^= (1u << s);
         double *val = sm.val[s] + off;
@@ -189,7 +210,7 @@ __device__ __forceinline__ void spmv_tiles_tma(const CsrTiled &M, const double *
         __syncthreads();
         if (threadIdx.x == 0 && i + kStages - 1 < nt)
             tma_issue_tile(M, __ldg(M.tiles + tb + i + kStages - 1), sm, (i + kStages - 1) % kStages);
-        tile_row_sums<SPLIT>(M, td, val, sm, epi);
+        tile_row_sums<SPLIT>(M, td, val, sm, pre, epi);
     }
     __syncthreads();
 }
