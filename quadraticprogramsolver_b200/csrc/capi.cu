@@ -6,10 +6,6 @@
 #include "host_common.h"
 #include "sparse_solver.h"
 
-struct qpb200_handle {
-    qpb::SparseSolver solver;
-};
-
 extern "C" {
 
 int qpb200_version(void) { return QPB200_VERSION; }
@@ -74,6 +70,7 @@ int qpb200_create(qpb200_handle **out, int64_t n, int64_t m, const int64_t *P_co
 
 int qpb200_solve(qpb200_handle *h, double *x_inout, double *z_out, double *y_out, qpb200_info *info) {
     if (!h) return qpb::fail(QPB200_ERR_ARG, "qpb200_solve: handle is NULL");
+    if (h->dist) return qpb::fail(QPB200_ERR_ARG, "qpb200_solve: distributed handle, call qpb200_dist_solve on every rank");
     return h->solver.solve(x_inout, z_out, y_out, info);
 }
 

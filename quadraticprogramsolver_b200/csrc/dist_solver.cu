@@ -1,15 +1,243 @@
-// dist_solver.cu -- row-partitioned multi-GPU sparse path (placeholder until the NCCL path lands).
+// dist_solver.cu -- host side of the row-partitioned multi-GPU sparse path (one rank per GPU).
+// NCCL is loaded at run time (dlopen "libnccl.so.2"), so libqpb200.so itself has no NCCL dependency and
+// shares the NCCL a host application (e.g. torch) has already loaded.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "dist_kernels.cuh"
 #include "host_common.h"
+#include "sparse_solver.h"
+
+namespace qpb {
+
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi *nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api.lib ? &api : nullptr;
+    tried = true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *nm : names) {
+        api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (api.lib) break;
+    }
+    if (!api.lib) return nullptr;
+    api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.lib, "ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.lib, "ncclCommInitRank");
+    api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.lib, "ncclCommDestroy");
+    api.AllReduce = (decltype(api.AllReduce))dlsym(api.lib, "ncclAllReduce");
+    api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.lib, "ncclGetErrorString");
+    if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllReduce || !api.GetErrorString) {
+        dlclose(api.lib);
+        api.lib = nullptr;
+        return nullptr;
+    }
+    return &api;
+}
+
+#define QPB_NCCL(call)                                                                                          \
+    do {                                                                                                        \
+        ncclResult_t r_ = (call);                                                                               \
+        if (r_ != ncclSuccess)                                                                                  \
+            return ::qpb::fail(QPB200_ERR_NCCL, "%s failed: %s (%s:%d)", #call, api->GetErrorString(r_), __FILE__, __LINE__); \
+    } while (0)
+
+struct DistContext {
+    int rank = 0, nranks = 1;
+    ncclComm_t comm = nullptr;
+    DistBuffers buf{};
+    DistState *host_state = nullptr;   // pinned mirror
+    long long launches = 0, allreduces = 0;
+};
+
+void dist_destroy(DistContext *d) {
+    if (!d) return;
+    NcclApi *api = nccl_api();
+    if (d->comm && api) api->CommDestroy(d->comm);
+    if (d->host_state) cudaFreeHost(d->host_state);
+    delete d;
+}
+
+static int launch_seg(SparseSolver &s, DistContext &d, int seg, int do_check) {
+    void *args[] = {(void *)&s.prob, (void *)&d.buf, (void *)&seg, (void *)&do_check};
+    const void *fn = s.use_tma ? (s.use_pre ? (const void *)admm_dist_kernel<true, true> : (const void *)admm_dist_kernel<true, false>)
+                               : (s.use_pre ? (const void *)admm_dist_kernel<false, true> : (const void *)admm_dist_kernel<false, false>);
+    QPB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(s.grid), dim3(kThreads), args, sizeof(SpmvSmem), s.stream));
+    ++d.launches;
+    return QPB200_OK;
+}
+
+static int read_state(SparseSolver &s, DistContext &d) {
+    QPB_CUDA(cudaMemcpyAsync(d.host_state, d.buf.state, sizeof(DistState), cudaMemcpyDeviceToHost, s.stream));
+    QPB_CUDA(cudaStreamSynchronize(s.stream));
+    return QPB200_OK;
+}
+
+int dist_solve(SparseSolver &s, DistContext &d, double *x_inout, double *z_out, double *y_out, qpb200_info *info) {
+    NcclApi *api = nccl_api();
+    if (!api) return fail(QPB200_ERR_NCCL, "libnccl.so.2 could not be loaded");
+    if (!x_inout) return fail(QPB200_ERR_ARG, "qpb200_dist_solve: x_inout is NULL");
+    QPB_CUDA(cudaSetDevice(s.device));
+    const int n = s.n, m = s.m;
+    int rc = s.reset_state(x_inout);
+    if (rc) return rc;
+    DistState init;
+    std::memset(&init, 0, sizeof(init));
+    init.conv_flag = 1;
+    init.rho = s.prob.s.rho;
+    init.rho1 = 1.0 / init.rho;
+    init.rhorho = init.rho;
+    init.res_prim = NAN;
+    init.res_dual = NAN;
+    *d.host_state = init;
+    QPB_CUDA(cudaMemcpyAsync(d.buf.state, d.host_state, sizeof(DistState), cudaMemcpyHostToDevice, s.stream));
+    QPB_CUDA(cudaStreamSynchronize(s.stream));
+    d.launches = 0;
+    d.allreduces = 0;
+    const long long max_iter = s.prob.s.max_iter, check_every = s.prob.s.check_every;
+    QPB_CUDA(cudaEventRecord(s.ev0, s.stream));
+    long long ii = 0;
+    for (ii = 1; ii <= max_iter; ++ii) {
+        if ((rc = launch_seg(s, d, kSegBegin, 0))) return rc;
+        QPB_NCCL(api->AllReduce(d.buf.wbuf, d.buf.wbuf, (size_t)n, ncclDouble, ncclSum, d.comm, s.stream));
+        ++d.allreduces;
+        if ((rc = launch_seg(s, d, kSegPcgInit, 0))) return rc;
+        if ((rc = read_state(s, d))) return rc;
+        while (d.host_state->cont) {
+            QPB_NCCL(api->AllReduce(d.buf.wbuf, d.buf.wbuf, (size_t)n, ncclDouble, ncclSum, d.comm, s.stream));
+            ++d.allreduces;
+            if ((rc = launch_seg(s, d, kSegPcgStep, 0))) return rc;
+            if ((rc = read_state(s, d))) return rc;
+        }
+        const int do_check = (ii % check_every) == 0;
+        if ((rc = launch_seg(s, d, kSegUpdate, do_check))) return rc;
+        if (do_check) {
+            QPB_NCCL(api->AllReduce(d.buf.wbuf2, d.buf.wbuf2, (size_t)2 * n, ncclDouble, ncclSum, d.comm, s.stream));
+            QPB_NCCL(api->AllReduce(d.buf.state->lmax, d.buf.state->lmax, 4, ncclDouble, ncclMax, d.comm, s.stream));
+            d.allreduces += 2;
+            if ((rc = launch_seg(s, d, kSegCheck, 1))) return rc;
+            if ((rc = read_state(s, d))) return rc;
+            if (d.host_state->conv_flag != 1) break;
+        }
+    }
+    if (ii > max_iter) ii = max_iter;
+    QPB_CUDA(cudaEventRecord(s.ev1, s.stream));
+    if ((rc = read_state(s, d))) return rc;
+    QPB_CUDA(cudaMemcpyAsync(x_inout, s.prob.XY, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    if (z_out && m) QPB_CUDA(cudaMemcpyAsync(z_out, s.prob.z, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    if (y_out && m) QPB_CUDA(cudaMemcpyAsync(y_out, s.prob.XY + n, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    QPB_CUDA(cudaStreamSynchronize(s.stream));
+    float ms = 0.f;
+    QPB_CUDA(cudaEventElapsedTime(&ms, s.ev0, s.ev1));
+    const DistState &S = *d.host_state;
+    s.last_info.conv_flag = S.conv_flag;
+    s.last_info.iterations = ii;
+    s.last_info.pcg_iters_total = S.pcg_total;
+    s.last_info.n_h_passes = S.n_h;
+    s.last_info.n_a_passes = S.n_a;
+    if (info) {
+        std::memset(info, 0, sizeof(*info));
+        info->conv_flag = S.conv_flag;
+        info->iterations = ii;
+        info->rho_final = S.rho;
+        info->res_prim = S.res_prim;
+        info->res_dual = S.res_dual;
+        info->rho_updates = S.rho_updates;
+        info->pcg_iters_total = S.pcg_total;
+        info->pcg_maxed = S.pcg_maxed;
+        info->solve_ms = ms;
+        info->setup_ms = s.setup_ms;
+        info->kernel_launches = d.launches;
+    }
+    return QPB200_OK;
+}
+
+int dist_init(SparseSolver &s, DistContext *&out, int rank, int nranks, const void *unique_id) {
+    NcclApi *api = nccl_api();
+    if (!api) return fail(QPB200_ERR_NCCL, "libnccl.so.2 could not be loaded (dlopen)");
+    if (nranks < 1 || rank < 0 || rank >= nranks || !unique_id) return fail(QPB200_ERR_ARG, "qpb200_dist_create: bad rank / nranks / id");
+    DistContext *d = new (std::nothrow) DistContext();
+    if (!d) return fail(QPB200_ERR_ARG, "out of host memory");
+    out = d;
+    d->rank = rank;
+    d->nranks = nranks;
+    ncclUniqueId id;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+    std::memcpy(&id, unique_id, sizeof(id));
+    QPB_CUDA(cudaSetDevice(s.device));
+    QPB_NCCL(api->CommInitRank(&d->comm, nranks, id, rank));
+    QPB_CUDA(s.arena.alloc(&d->buf.state, 1, true));
+    QPB_CUDA(s.arena.alloc(&d->buf.wbuf, (size_t)s.n + 8, true));
+    QPB_CUDA(s.arena.alloc(&d->buf.wbuf2, (size_t)2 * s.n + 8, true));
+    QPB_CUDA(cudaMallocHost(&d->host_state, sizeof(DistState)));
+    for (const void *fn : {(const void *)admm_dist_kernel<true, true>, (const void *)admm_dist_kernel<true, false>,
+                           (const void *)admm_dist_kernel<false, true>, (const void *)admm_dist_kernel<false, false>}) {
+        QPB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpmvSmem)));
+        int per_sm = 0;
+        QPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, sizeof(SpmvSmem)));
+        if (per_sm * s.num_sms < s.grid)
+            return fail(QPB200_ERR_CUDA, "segment kernel cannot be co-resident at grid %d (%d per SM)", s.grid, per_sm);
+    }
+    // Jacobi diagonal pieces are partial sums over the ranks' slices: combine once
+    QPB_NCCL(api->AllReduce(s.prob.dP, const_cast<double *>(s.prob.dP), (size_t)s.n, ncclDouble, ncclSum, d->comm, s.stream));
+    QPB_NCCL(api->AllReduce(s.prob.dAA, const_cast<double *>(s.prob.dAA), (size_t)s.n, ncclDouble, ncclSum, d->comm, s.stream));
+    QPB_CUDA(cudaStreamSynchronize(s.stream));
+    return QPB200_OK;
+}
+
+}  // namespace qpb
+
+using namespace qpb;
 
 extern "C" {
-int qpb200_dist_unique_id(void *) { return qpb::fail(QPB200_ERR_NCCL, "qpb200_dist_unique_id: not implemented in this build"); }
-int qpb200_dist_create(qpb200_handle **out, int32_t, int32_t, const void *, int64_t, int64_t, const int64_t *, const int64_t *,
-                       const double *, const int64_t *, const int64_t *, const double *, const double *, const double *,
-                       const double *, const qpb200_settings *, int32_t) {
-    if (out) *out = nullptr;
-    return qpb::fail(QPB200_ERR_NCCL, "qpb200_dist_create: not implemented in this build");
+
+int qpb200_dist_unique_id(void *id128) {
+    NcclApi *api = nccl_api();
+    if (!api) return fail(QPB200_ERR_NCCL, "libnccl.so.2 could not be loaded (dlopen)");
+    if (!id128) return fail(QPB200_ERR_ARG, "qpb200_dist_unique_id: NULL");
+    ncclUniqueId id;
+    QPB_NCCL(api->GetUniqueId(&id));
+    std::memcpy(id128, &id, sizeof(id));
+    return QPB200_OK;
 }
-int qpb200_dist_solve(qpb200_handle *, double *, double *, double *, qpb200_info *) {
-    return qpb::fail(QPB200_ERR_NCCL, "qpb200_dist_solve: not implemented in this build");
+
+int qpb200_dist_create(qpb200_handle **out, int32_t rank, int32_t nranks, const void *nccl_unique_id, int64_t n,
+                       int64_t m_local, const int64_t *P_colptr, const int64_t *P_rowval, const double *P_nzval,
+                       const int64_t *A_colptr, const int64_t *A_rowval, const double *A_nzval, const double *q,
+                       const double *l_local, const double *u_local, const qpb200_settings *settings, int32_t index_base) {
+    if (!out) return fail(QPB200_ERR_ARG, "qpb200_dist_create: out is NULL");
+    *out = nullptr;
+    qpb200_settings s;
+    if (settings) s = *settings;
+    else qpb200_default_settings(&s);
+    qpb200_handle *h = new (std::nothrow) qpb200_handle();
+    if (!h) return fail(QPB200_ERR_ARG, "out of host memory");
+    int rc = h->solver.init(n, m_local, P_colptr, P_rowval, P_nzval, A_colptr, A_rowval, A_nzval, q, l_local, u_local, s, index_base);
+    if (rc == QPB200_OK) rc = dist_init(h->solver, h->dist, rank, nranks, nccl_unique_id);
+    if (rc != QPB200_OK) {
+        qpb200_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return QPB200_OK;
 }
+
+int qpb200_dist_solve(qpb200_handle *h, double *x_inout, double *z_out, double *y_out, qpb200_info *info) {
+    if (!h || !h->dist) return fail(QPB200_ERR_ARG, "qpb200_dist_solve: not a distributed handle");
+    return dist_solve(h->solver, *h->dist, x_inout, z_out, y_out, info);
 }
+
+}  // extern "C"

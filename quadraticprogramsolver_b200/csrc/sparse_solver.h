@@ -36,4 +36,14 @@ struct SparseSolver {
     int64_t solve_bytes() const;
 };
 
+struct DistContext;                       // dist_solver.cu
+void dist_destroy(DistContext *d);
+
 }  // namespace qpb
+
+// the object behind the opaque C handle
+struct qpb200_handle {
+    qpb::SparseSolver solver;
+    qpb::DistContext *dist = nullptr;     // non-null for handles made by qpb200_dist_create
+    ~qpb200_handle() { qpb::dist_destroy(dist); }
+};

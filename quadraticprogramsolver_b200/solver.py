@@ -264,3 +264,73 @@ def SolveQuadraticProgramBatch(P, q, A_cm, l, u, X0=None, **kw):
         X = None if X0 is None else np.array(X0, dtype=np.float64)
         X, flags, iters = b.solve(X)
         return X, flags, iters, b.info
+
+
+class QPB200DistSolver:
+    """One large sparse QP row-partitioned over the ranks of a ``torch.distributed`` group (one rank per
+    GPU).  Every rank constructs it with the full problem (or pre-sliced parts via ``presliced``) and calls
+    :meth:`solve` collectively.  NCCL carries the n-vector all-reduces."""
+
+    def __init__(self, mP, vQ, mA, vL, vU, group=None, presliced=None, **kw):
+        import torch
+        import torch.distributed as dist
+        from . import partition
+        lib = _lib.load()
+        self.rank = dist.get_rank(group)
+        self.nranks = dist.get_world_size(group)
+        self.n = int(mP.shape[0])
+        if presliced is None:
+            presliced = partition.slice_problem(mP, mA, vL, vU, self.rank, self.nranks)
+        P_r, A_r, l_r, u_r, self.rows, self.cols = presliced
+        self.m_local = int(A_r.shape[0])
+        # rank 0 creates the NCCL id; the group (any backend) carries its 128 bytes
+        idbuf = np.zeros(128, dtype=np.uint8)
+        if self.rank == 0:
+            _lib.check(lib.qpb200_dist_unique_id(idbuf.ctypes.data_as(C.c_void_p)))
+        box = [idbuf.tobytes()]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        idbuf = np.frombuffer(box[0], dtype=np.uint8).copy()
+        Pp, Pi, Pv = _csc_arrays(P_r)
+        Ap, Ai, Av = _csc_arrays(A_r)
+        vQ = np.ascontiguousarray(vQ, dtype=np.float64)
+        l_r = np.ascontiguousarray(l_r, dtype=np.float64); u_r = np.ascontiguousarray(u_r, dtype=np.float64)
+        kw.setdefault("device", torch.cuda.current_device() if torch.cuda.is_available() else -1)
+        self.settings = make_settings(**kw)
+        self._h = C.c_void_p()
+        _lib.check(lib.qpb200_dist_create(C.byref(self._h), self.rank, self.nranks, idbuf.ctypes.data_as(C.c_void_p),
+                                          self.n, self.m_local, _p64(Pp), _p64(Pi), _pd(Pv), _p64(Ap), _p64(Ai), _pd(Av),
+                                          _pd(vQ), _pd(l_r), _pd(u_r), C.byref(self.settings), 0))
+        self.info = None
+
+    def solve(self, vX, want_zy: bool = False):
+        """Collective.  ``vX`` (replicated start point) is overwritten with the solution on every rank."""
+        info = Info()
+        z = np.empty(self.m_local) if want_zy else None
+        y = np.empty(self.m_local) if want_zy else None
+        _lib.check(_lib.load().qpb200_dist_solve(self._h, _pd(vX), _pd(z) if want_zy else None,
+                                                 _pd(y) if want_zy else None, C.byref(info)))
+        self.info = info.as_dict()
+        if want_zy:
+            self.info["z_local"] = z
+            self.info["y_local"] = y
+        return ConvergenceFlag(info.conv_flag)
+
+    def apply_bytes(self, which: int) -> int:
+        return int(_lib.load().qpb200_apply_bytes(self._h, which))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.load().qpb200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,133 @@
+"""CPU tests of the multi-GPU host logic: the row/column partition of SURVEY.md 8(e), checked (a) in one
+process and (b) across a real 2-rank torch.distributed group on the gloo backend, where every rank applies
+its H_r = [P[:, J_r]  A_r'] slice and the n-vectors are combined by all_reduce -- the exact data flow of
+dist_kernels.cuh with numpy standing in for the kernels."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import scipy.sparse as sp
+
+from quadraticprogramsolver_b200 import partition
+from quadraticprogramsolver_b200.problems import config_sparse
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_balanced_blocks_cover_and_balance():
+    w = np.random.default_rng(0).integers(0, 50, size=10000)
+    for parts in (1, 2, 3, 8):
+        b = partition.balanced_blocks(w, parts)
+        assert b[0] == 0 and b[-1] == len(w) and np.all(np.diff(b) >= 0) and len(b) == parts + 1
+        tot = np.array([w[b[i]:b[i + 1]].sum() for i in range(parts)])
+        assert tot.max() <= tot.mean() * 1.1 + 100
+    assert list(partition.balanced_blocks(np.zeros(5), 8)) == sorted(partition.balanced_blocks(np.zeros(5), 8))
+
+
+def test_slices_reassemble_operator():
+    P, q, A, l, u = config_sparse(400, 900, 0.02, seed=3)
+    rng = np.random.default_rng(1)
+    uvec = rng.standard_normal(400)
+    yvec = rng.standard_normal(900)
+    rho, sigma = 0.7, 1e-3
+    for R in (1, 2, 4, 7):
+        Ku = np.zeros(400); Px = np.zeros(400); Aty = np.zeros(400); dP = np.zeros(400); dAA = np.zeros(400)
+        rows_seen = 0
+        for r in range(R):
+            P_r, A_r, l_r, u_r, (i0, i1), (j0, j1) = partition.slice_problem(P, A, l, u, r, R)
+            assert P_r.shape == (400, 400) and A_r.shape == (i1 - i0, 400)
+            assert np.array_equal(l_r, l[i0:i1]) and np.array_equal(u_r, u[i0:i1])
+            rows_seen += i1 - i0
+            Ku += P_r @ uvec + rho * (A_r.T @ (A_r @ uvec))
+            Px += P_r @ uvec
+            Aty += A_r.T @ yvec[i0:i1]
+            dP += P_r.diagonal()
+            dAA += np.asarray(A_r.multiply(A_r).sum(axis=0)).ravel()
+        assert rows_seen == 900
+        assert np.allclose(Ku + sigma * uvec, P @ uvec + rho * (A.T @ (A @ uvec)) + sigma * uvec, rtol=1e-12, atol=1e-12)
+        assert np.allclose(Px, P @ uvec) and np.allclose(Aty, A.T @ yvec)
+        assert np.allclose(dP, P.diagonal()) and np.allclose(dAA, np.asarray(A.multiply(A).sum(axis=0)).ravel())
+
+
+_WORKER = textwrap.dedent('''
+    import os, sys
+    import numpy as np
+    import torch, torch.distributed as dist
+    sys.path.insert(0, os.environ["QPB_ROOT"])
+    from quadraticprogramsolver_b200 import partition
+    from quadraticprogramsolver_b200.problems import config_sparse
+    from oracle import qp_oracle
+
+    dist.init_process_group("gloo")
+    rank, R = dist.get_rank(), dist.get_world_size()
+    P, q, A, l, u = config_sparse(120, 260, 0.05, seed=11)
+    n, m = 120, 260
+    P_r, A_r, l_r, u_r, (i0, i1), (j0, j1) = partition.slice_problem(P, A, l, u, rank, R)
+    A_rt = A_r.T.tocsr()
+
+    def allreduce(v, op=dist.ReduceOp.SUM):
+        t = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64).copy())
+        dist.all_reduce(t, op=op)
+        return t.numpy()
+
+    # distributed ADMM with the exact data flow of dist_kernels.cuh (numpy in place of the kernels)
+    rho, sigma, alpha = 1.0, 1e-6, 1.6
+    dinv = 1.0 / (allreduce(P_r.diagonal()) + sigma + rho * allreduce(np.asarray(A_r.multiply(A_r).sum(axis=0)).ravel()))
+    x = np.zeros(n); xt = np.zeros(n); z = np.zeros(i1 - i0); y = np.zeros(i1 - i0); g = np.zeros(i1 - i0)
+    flag, iters = 1, 0
+    for ii in range(1, 2001):
+        w = allreduce(P_r @ xt + A_rt @ g)                      # kSegBegin + all-reduce
+        r = sigma * (x - xt) - q - w                            # kSegPcgInit
+        zp = dinv * r; uvec = zp.copy()
+        res = np.sqrt(r @ r); rz = r @ zp
+        tol = max(np.sqrt(np.finfo(float).eps) * res, 1e-10)
+        k = 0
+        while k < 1000 and not res <= tol:
+            w = allreduce(P_r @ uvec + A_rt @ (rho * (A_r @ uvec)))   # S2, S3 partial + all-reduce
+            c = w + sigma * uvec                                # kSegPcgStep
+            a = rz / (uvec @ c)
+            xt += a * uvec; r -= a * c; zp = dinv * r
+            res = np.sqrt(r @ r); rz_new = r @ zp; k += 1
+            if k < 1000 and not res <= tol:
+                uvec = zp + (rz_new / rz) * uvec
+            rz = rz_new
+        zt = A_r @ xt                                           # kSegUpdate (rows I_r only)
+        x_old = x.copy(); x = alpha * xt + (1 - alpha) * x
+        z_old = z.copy(); zr = alpha * zt + (1 - alpha) * z
+        z = np.where(zr + y / rho > u_r, u_r, np.where(zr + y / rho < l_r, l_r, zr + y / rho))
+        y = y + rho * (zr - z)
+        g = rho * (zt - z) + y
+        if ii % 25 == 0:
+            ax = A_r @ x
+            lmax = allreduce(np.array([np.max(np.abs(x - x_old)), np.max(np.abs(z - z_old), initial=0.0),
+                                       np.max(np.abs(ax - z), initial=0.0),
+                                       max(np.max(np.abs(ax), initial=0.0), np.max(np.abs(z), initial=0.0))]), dist.ReduceOp.MAX)
+            w2 = allreduce(np.concatenate([P_r @ x, A_rt @ y]))
+            px, aty = w2[:n], w2[n:]
+            rd = np.max(np.abs(px + q + aty)); md = max(np.max(np.abs(px)), np.max(np.abs(aty)), np.max(np.abs(q)))
+            if lmax[2] < 1e-6 + 1e-6 * lmax[3] and rd < 1e-6 + 1e-6 * md: flag = 3
+            if lmax[0] <= 1e-8 and lmax[1] <= 1e-8: flag = 2
+            if flag != 1:
+                iters = ii
+                break
+    x_ref, flag_ref, info = qp_oracle.solve(P, q, A, l, u, mode="J", epsPcg=1e-10, numIterations=2000)
+    assert flag == int(flag_ref), (flag, int(flag_ref))
+    assert iters == info["iterations"], (iters, info["iterations"])
+    assert np.max(np.abs(x - x_ref)) <= 1e-6 * (1 + np.max(np.abs(x_ref)))
+    assert np.max(np.abs(z - info["z"][i0:i1])) <= 1e-6 * (1 + np.max(np.abs(info["z"])))
+    print("rank", rank, "ok", iters, flush=True)
+    dist.destroy_process_group()
+''')
+
+
+def test_two_rank_gloo_data_flow(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, QPB_ROOT=ROOT, OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29613", str(script)],
+                         env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert out.stdout.count("ok") == 2
