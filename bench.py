@@ -190,8 +190,15 @@ def run_b200(args):
     peak, peak_src = load_peaks()
 
     # ---- device-resident arm ------------------------------------------------------------------
-    # N > 1: until the row-partitioned path is selected every rank holds a replica ("replicas only")
-    s = S.QPB200Solver(P, q, A, l, u, **kw)
+    # N = 1: the single-GPU persistent kernel.  N > 1: the SAME QP row-partitioned over the N ranks
+    # (rows of A / columns of P per rank, NCCL all-reduce of the n-vector partial sums) -> strong scaling.
+    if world == 1:
+        s = S.QPB200Solver(P, q, A, l, u, **kw)
+        presliced = None
+    else:
+        from quadraticprogramsolver_b200 import partition
+        presliced = partition.slice_problem(P, A, l, u, rank, world)
+        s = S.QPB200DistSolver(P, q, A, l, u, presliced=presliced, **kw)
     x = np.zeros(n)
     for _ in range(args.warmup):
         x[:] = 0.0
@@ -215,12 +222,15 @@ def run_b200(args):
         t = torch.tensor([dev_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms = float(t.item())
-    value = world * iters / (dev_ms * 1e-3)
-    achieved = bytes_total / 1e9 / (dev_ms * 1e-3)
+        t = torch.tensor([float(bytes_total)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        bytes_total = float(t.item())
+    value = iters / (dev_ms * 1e-3)               # one QP: iterations of the whole job per second
+    achieved = bytes_total / 1e9 / (dev_ms * 1e-3) / world   # per-GPU algorithmic GB/s
 
     # stand-alone SpMV (the operator the north_star quotes): L2 flushed between launches
     spmv = {}
-    if rank == 0:
+    if rank == 0 and world == 1:
         for which, name in ((1, "A"), (4, "H=[P A']")):
             ms = s.time_apply(which, reps=20, flush_l2=True)
             gb = s.apply_bytes(which) / 1e9
@@ -228,26 +238,40 @@ def run_b200(args):
     s.close()
 
     # ---- end-to-end arm: host buffers -> create -> solve -> results on host, every step --------
-    Pp, Pi, Pv = S._csc_arrays(P)
-    Ap, Ai, Av = S._csc_arrays(A)
-    h2d = Pp.nbytes + Pi.nbytes + Pv.nbytes + Ap.nbytes + Ai.nbytes + Av.nbytes + q.nbytes + l.nbytes + u.nbytes + 8 * n
-    d2h = 8 * (n + 2 * m)
+    if world == 1:
+        Pp, Pi, Pv = S._csc_arrays(P)
+        Ap, Ai, Av = S._csc_arrays(A)
+        m_loc = m
+    else:
+        Pp, Pi, Pv = S._csc_arrays(presliced[0])
+        Ap, Ai, Av = S._csc_arrays(presliced[1])
+        m_loc = presliced[1].shape[0]
+    h2d = Pp.nbytes + Pi.nbytes + Pv.nbytes + Ap.nbytes + Ai.nbytes + Av.nbytes + 8 * (2 * n + 2 * m_loc)
+    d2h = 8 * (n + 2 * m_loc)
+
+    def e2e_once():
+        if world == 1:
+            return S.SolveQuadraticProgram(P, q, A, l, u, **kw)[2]
+        with S.QPB200DistSolver(P, q, A, l, u, presliced=presliced, **kw) as ds:
+            xx = np.zeros(n)
+            ds.solve(xx, want_zy=True)
+            return ds.info
+
     e2e_steps = max(1, min(args.steps, 3))
-    S.SolveQuadraticProgram(P, q, A, l, u, **kw)          # warm-up
+    e2e_once()                                            # warm-up
     barrier()
     t0 = time.perf_counter()
     e2e_iters = 0
     for _ in range(e2e_steps):
-        xx, fl, info = S.SolveQuadraticProgram(P, q, A, l, u, **kw)
+        info = e2e_once()
         e2e_iters += info["iterations"]
-        launches_e2e = info["kernel_launches"]
     barrier()
     e2e_wall = time.perf_counter() - t0
     if dist is not None:
-        t = torch.tensor([e2e_wall], device="cuda", dtype=torch.float64)
+        t = torch.tensor([e2e_wall, float(h2d), float(d2h)], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_wall = float(t.item())
-    e2e_value = world * e2e_iters / e2e_wall
+        e2e_wall = float(t[0].item())
+    e2e_value = e2e_iters / e2e_wall
 
     if rank != 0:
         if dist is not None:
@@ -256,10 +280,10 @@ def run_b200(args):
     line = {
         "metric": "admm_iters_per_s", "value": value, "unit": "iter/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms / max(1, args.steps), "higher_is_better": True,
-        "scaling": "weak" if world > 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": desc, "iters_per_step": ITERS, "settings": "reference defaults (rho=1, sigma=1e-6, alpha=1.6, "
                    "eps 1e-6, check every 25), Jacobi-PCG abstol 1e-6", "parallelism": "1 GPU" if world == 1 else
-                   f"{world} replicas (one per GPU)", "l2": "matrix streams (0.55 GB per operator application) exceed the 126 MB L2; "
+                   f"one QP row-partitioned over {world} GPUs (rows of A / columns of P per rank, ncclAllReduce of n-vectors)", "l2": "matrix streams (0.55 GB per operator application) exceed the 126 MB L2; "
                    "stand-alone SpMV timings flush L2 between launches", "conv_flag": flag,
                    "pcg_iters_per_step": pcg / max(1, args.steps), "gen_s": round(gen_s, 1)},
         "clocks": clocks,
@@ -267,7 +291,8 @@ def run_b200(args):
                 "steps": e2e_steps, "ms_per_step": 1e3 * e2e_wall / e2e_steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "admm_kernel (persistent; 1 launch per step)", "peak_source": peak_src,
+                     "traffic": None, "kernel": "admm_kernel (persistent; 1 launch per step)" if world == 1 else
+                     "admm_dist_kernel segments (per-GPU GB/s)", "peak_source": peak_src,
                      "spmv": spmv, "note": "cfg5's uniformly random columns make every 8-byte gather of x move a 32-byte L2 "
                      "sector; see DESIGN.md (L2-sector bound) and profiles/"},
         "cg_iters_per_s": pcg / (dev_ms * 1e-3),

@@ -2,10 +2,38 @@
 #include "host_common.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
+#include <thread>
 
 namespace qpb {
+
+int host_threads() {
+    static int nt = [] {
+        const char *e = getenv("QPB200_HOST_THREADS");
+        int v = e ? atoi(e) : (int)std::thread::hardware_concurrency();
+        return std::max(1, std::min(v, 32));
+    }();
+    return nt;
+}
+
+// fn(t, begin, end) on contiguous chunks of [0, count) -- plain std::thread, no OpenMP dependency
+void parallel_chunks(int64_t count, const std::function<void(int, int64_t, int64_t)> &fn, int64_t min_chunk) {
+    int nt = host_threads();
+    if (count < 2 * min_chunk) nt = 1;
+    nt = (int)std::max<int64_t>(1, std::min<int64_t>(nt, count / std::max<int64_t>(1, min_chunk)));
+    if (nt <= 1) {
+        fn(0, 0, count);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t) {
+        const int64_t b = count * t / nt, e = count * (t + 1) / nt;
+        th.emplace_back([&fn, t, b, e] { fn(t, b, e); });
+    }
+    for (auto &x : th) x.join();
+}
 
 std::string &last_error() {
     static thread_local std::string msg;
@@ -32,31 +60,80 @@ int validate_csc(const char *name, int64_t nrows, int64_t ncols, const int64_t *
     const int64_t nnz = colptr[ncols] - base;
     if (nnz >= (int64_t(1) << 31) - 64) return fail(QPB200_ERR_ARG, "%s: nnz = %lld exceeds the int32 index range", name, (long long)nnz);
     if (nnz > 0 && (!rowval || !nzval)) return fail(QPB200_ERR_ARG, "%s: rowval/nzval is NULL", name);
-    for (int64_t k = 0; k < nnz; ++k) {
-        const int64_t i = rowval[k] - base;
-        if (i < 0 || i >= nrows) return fail(QPB200_ERR_ARG, "%s: row index %lld out of range at nnz %lld", name, (long long)rowval[k], (long long)k);
-        if (!std::isfinite(nzval[k])) return fail(QPB200_ERR_NONFINITE, "%s: non-finite value at nnz %lld", name, (long long)k);
+    std::atomic<int64_t> bad_idx(-1), bad_val(-1);
+    parallel_chunks(nnz, [&](int, int64_t b, int64_t e) {
+        double acc = 0.0;
+        for (int64_t k = b; k < e; ++k) {
+            const int64_t i = rowval[k] - base;
+            if (i < 0 || i >= nrows) { bad_idx = k; return; }
+            acc += nzval[k] * 0.0;
+        }
+        if (acc != 0.0) bad_val = b;
+    }, 1 << 16);
+    if (bad_idx >= 0) return fail(QPB200_ERR_ARG, "%s: row index %lld out of range at nnz %lld", name, (long long)rowval[bad_idx], (long long)bad_idx.load());
+    if (bad_val >= 0) {
+        int64_t k = bad_val;
+        while (k < nnz && std::isfinite(nzval[k])) ++k;
+        return fail(QPB200_ERR_NONFINITE, "%s: non-finite value at nnz %lld", name, (long long)k);
     }
     return QPB200_OK;
 }
 
 void csc_to_csr(int64_t nrows, int64_t ncols, const int64_t *colptr, const int64_t *rowval, const double *nzval,
                 int64_t base, HostCsr &out) {
+    // stable parallel counting sort: thread t owns a contiguous block of columns; per-thread row
+    // histograms give every (thread, row) its write offset, so each row keeps ascending column order
+    // regardless of the thread count (deterministic layout).
     const int64_t nnz = colptr[ncols] - base;
     out.rows = (int)nrows;
     out.cols = (int)ncols;
     out.ptr.assign((size_t)nrows + 1, 0);
     out.idx.resize((size_t)nnz);
     out.val.resize((size_t)nnz);
-    for (int64_t k = 0; k < nnz; ++k) out.ptr[(size_t)(rowval[k] - base) + 1]++;
-    for (int64_t i = 0; i < nrows; ++i) out.ptr[(size_t)i + 1] += out.ptr[(size_t)i];
-    std::vector<int> cur(out.ptr.begin(), out.ptr.end() - 1);
-    for (int64_t j = 0; j < ncols; ++j)
-        for (int64_t k = colptr[j] - base; k < colptr[j + 1] - base; ++k) {
-            const int p = cur[(size_t)(rowval[k] - base)]++;
-            out.idx[(size_t)p] = (int)j;       // ascending j within each row: columns stay sorted
-            out.val[(size_t)p] = nzval[k];
+    int nt = host_threads();
+    if (nnz < (1 << 18)) nt = 1;
+    // column block boundaries balanced by nnz
+    std::vector<int64_t> cb((size_t)nt + 1, ncols);
+    cb[0] = 0;
+    for (int t = 1; t < nt; ++t) {
+        const int64_t target = base + nnz * t / nt;
+        cb[(size_t)t] = std::lower_bound(colptr, colptr + ncols + 1, target) - colptr;
+        if (cb[(size_t)t] > ncols) cb[(size_t)t] = ncols;
+        if (cb[(size_t)t] < cb[(size_t)t - 1]) cb[(size_t)t] = cb[(size_t)t - 1];
+    }
+    std::vector<std::vector<int>> cnt((size_t)nt);
+    auto run = [&](const std::function<void(int)> &f) {
+        if (nt == 1) { f(0); return; }
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; ++t) th.emplace_back(f, t);
+        for (auto &x : th) x.join();
+    };
+    run([&](int t) {
+        cnt[(size_t)t].assign((size_t)nrows, 0);
+        int *c = cnt[(size_t)t].data();
+        for (int64_t k = colptr[cb[(size_t)t]] - base; k < colptr[cb[(size_t)t + 1]] - base; ++k) c[rowval[k] - base]++;
+    });
+    // per-row totals -> row pointers; per-(thread,row) offsets
+    run([&](int t) {
+        const int64_t r0 = nrows * t / nt, r1 = nrows * (t + 1) / nt;
+        for (int64_t i = r0; i < r1; ++i) {
+            int tot = 0;
+            for (int u = 0; u < nt; ++u) { const int c = cnt[(size_t)u][(size_t)i]; cnt[(size_t)u][(size_t)i] = tot; tot += c; }
+            out.ptr[(size_t)i + 1] = tot;
         }
+    });
+    for (int64_t i = 0; i < nrows; ++i) out.ptr[(size_t)i + 1] += out.ptr[(size_t)i];
+    run([&](int t) {
+        int *c = cnt[(size_t)t].data();
+        const int *ptr = out.ptr.data();
+        for (int64_t j = cb[(size_t)t]; j < cb[(size_t)t + 1]; ++j)
+            for (int64_t k = colptr[j] - base; k < colptr[j + 1] - base; ++k) {
+                const int64_t i = rowval[k] - base;
+                const int p = ptr[i] + c[i]++;
+                out.idx[(size_t)p] = (int)j;
+                out.val[(size_t)p] = nzval[k];
+            }
+    });
 }
 
 void csc_as_csr_of_transpose(int64_t nrows, int64_t ncols, const int64_t *colptr, const int64_t *rowval,
@@ -68,8 +145,10 @@ void csc_as_csr_of_transpose(int64_t nrows, int64_t ncols, const int64_t *colptr
     out.idx.resize((size_t)nnz);
     out.val.resize((size_t)nnz);
     for (int64_t j = 0; j <= ncols; ++j) out.ptr[(size_t)j] = (int)(colptr[j] - base);
-    for (int64_t k = 0; k < nnz; ++k) out.idx[(size_t)k] = (int)(rowval[k] - base);
-    if (nnz) std::memcpy(out.val.data(), nzval, (size_t)nnz * sizeof(double));
+    parallel_chunks(nnz, [&](int, int64_t b, int64_t e) {
+        for (int64_t k = b; k < e; ++k) out.idx[(size_t)k] = (int)(rowval[k] - base);
+        std::memcpy(out.val.data() + b, nzval + b, (size_t)(e - b) * sizeof(double));
+    }, 1 << 16);
 }
 
 int choose_lpr(const HostCsr &M) {
@@ -136,14 +215,18 @@ void assign_tiles(HostTiles &t, int grid) {
 }
 
 bool all_finite(const double *v, size_t count) {
-    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    size_t i = 0;
-    for (; i + 8 <= count; i += 8)
-        for (int j = 0; j < 8; ++j) acc[j] += v[i + j] * 0.0;
-    for (; i < count; ++i) acc[0] += v[i] * 0.0;
-    double s = 0.0;
-    for (int j = 0; j < 8; ++j) s += acc[j];
-    return s == 0.0;
+    std::atomic<int> bad(0);
+    parallel_chunks((int64_t)count, [&](int, int64_t b, int64_t e) {
+        double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        int64_t i = b;
+        for (; i + 8 <= e; i += 8)
+            for (int j = 0; j < 8; ++j) acc[j] += v[i + j] * 0.0;
+        for (; i < e; ++i) acc[0] += v[i] * 0.0;
+        double s = 0.0;
+        for (int j = 0; j < 8; ++j) s += acc[j];
+        if (s != 0.0) bad = 1;
+    }, 1 << 18);
+    return bad == 0;
 }
 
 int check_device(int device) {

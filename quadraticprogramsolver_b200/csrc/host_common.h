@@ -5,6 +5,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -78,6 +79,9 @@ int validate_csc(const char *name, int64_t nrows, int64_t ncols, const int64_t *
 void build_tiles(const HostCsr &M, int tile_nnz, HostTiles &out);
 void assign_tiles(HostTiles &t, int grid);
 int choose_lpr(const HostCsr &M);
+
+int host_threads();
+void parallel_chunks(int64_t count, const std::function<void(int, int64_t, int64_t)> &fn, int64_t min_chunk);
 
 // true iff every entry is finite (vectorisable: v * 0 is NaN exactly for NaN / +-Inf)
 bool all_finite(const double *v, size_t count);

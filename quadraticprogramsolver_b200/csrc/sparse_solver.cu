@@ -96,6 +96,15 @@ int SparseSolver::init(int64_t n64, int64_t m64, const int64_t *Pp, const int64_
                        const int64_t *Ap, const int64_t *Ai, const double *Av, const double *q, const double *l,
                        const double *u, const qpb200_settings &s, int32_t base) {
     const auto t0 = std::chrono::steady_clock::now();
+    std::string laps;
+    auto tlast = t0;
+    auto lap = [&](const char *name) {
+        const auto now = std::chrono::steady_clock::now();
+        char b[96];
+        snprintf(b, sizeof(b), " %s=%.1f", name, std::chrono::duration<double, std::milli>(now - tlast).count());
+        laps += b;
+        tlast = now;
+    };
     if (n64 <= 0 || m64 < 0 || n64 + m64 >= (int64_t(1) << 31) - 64)
         return fail(QPB200_ERR_ARG, "qpb200_create: need 0 < n, 0 <= m, n + m < 2^31 (got n=%lld m=%lld)", (long long)n64,
                     (long long)m64);
@@ -110,6 +119,7 @@ int SparseSolver::init(int64_t n64, int64_t m64, const int64_t *Pp, const int64_
     for (int64_t i = 0; i < m64; ++i)
         if (std::isnan(l[i]) || std::isnan(u[i]) || l[i] > u[i])
             return fail(QPB200_ERR_NONFINITE, "bounds: need l[i] <= u[i], not NaN (row %lld)", (long long)i);
+    lap("validate");
     rc = check_device(s.device);
     if (rc) return rc;
     QPB_CUDA(cudaGetDevice(&device));
@@ -123,6 +133,7 @@ int SparseSolver::init(int64_t n64, int64_t m64, const int64_t *Pp, const int64_
     csc_to_csr(n, n, Pp, Pi, Pv, base, P);
     csc_to_csr(m, n, Ap, Ai, Av, base, A);
     csc_as_csr_of_transpose(m, n, Ap, Ai, Av, base, At);
+    lap("transposes");
     nnzP = P.nnz();
     nnzA = A.nnz();
     H.rows = n;
@@ -132,29 +143,32 @@ int SparseSolver::init(int64_t n64, int64_t m64, const int64_t *Pp, const int64_
     H.idx.resize((size_t)(nnzP + nnzA));
     H.val.resize((size_t)(nnzP + nnzA));
     std::vector<double> dP((size_t)n, 0.0), dAA((size_t)n, 0.0);
-    int pos = 0;
-    for (int j = 0; j < n; ++j) {
-        H.ptr[(size_t)j] = pos;
-        for (int k = P.ptr[(size_t)j]; k < P.ptr[(size_t)j + 1]; ++k) {
-            H.idx[(size_t)pos] = P.idx[(size_t)k];
-            H.val[(size_t)pos] = P.val[(size_t)k];
-            if (P.idx[(size_t)k] == j) dP[(size_t)j] += P.val[(size_t)k];
-            ++pos;
+    for (int j = 0; j <= n; ++j) H.ptr[(size_t)j] = P.ptr[(size_t)j] + At.ptr[(size_t)j];
+    const int nloc = n;
+    parallel_chunks(n, [&](int, int64_t j0, int64_t j1) {
+        for (int64_t j = j0; j < j1; ++j) {
+            int pos = H.ptr[(size_t)j];
+            for (int k = P.ptr[(size_t)j]; k < P.ptr[(size_t)j + 1]; ++k) {
+                H.idx[(size_t)pos] = P.idx[(size_t)k];
+                H.val[(size_t)pos] = P.val[(size_t)k];
+                if (P.idx[(size_t)k] == j) dP[(size_t)j] += P.val[(size_t)k];
+                ++pos;
+            }
+            H.mid[(size_t)j] = pos;
+            for (int k = At.ptr[(size_t)j]; k < At.ptr[(size_t)j + 1]; ++k) {
+                H.idx[(size_t)pos] = At.idx[(size_t)k] + nloc;
+                H.val[(size_t)pos] = At.val[(size_t)k];
+                dAA[(size_t)j] += At.val[(size_t)k] * At.val[(size_t)k];
+                ++pos;
+            }
         }
-        H.mid[(size_t)j] = pos;
-        for (int k = At.ptr[(size_t)j]; k < At.ptr[(size_t)j + 1]; ++k) {
-            H.idx[(size_t)pos] = At.idx[(size_t)k] + n;
-            H.val[(size_t)pos] = At.val[(size_t)k];
-            dAA[(size_t)j] += At.val[(size_t)k] * At.val[(size_t)k];
-            ++pos;
-        }
-    }
-    H.ptr[(size_t)n] = pos;
+    }, 4096);
     double nq = 0.0;
     for (int j = 0; j < n; ++j) nq = std::fmax(nq, std::fabs(q[j]));
     prob.normQ = nq;
 
     // ---- grid: co-resident CTAs of the persistent kernel, shrunk for small problems
+    lap("assemble_H");
     cudaDeviceProp prop;
     QPB_CUDA(cudaGetDeviceProperties(&prop, device));
     num_sms = prop.multiProcessorCount;
@@ -173,6 +187,7 @@ int SparseSolver::init(int64_t n64, int64_t m64, const int64_t *Pp, const int64_
     per_sm = std::min(per_sm, 2);
     const int grid_max = num_sms * per_sm;
 
+    lap("kernel_prep");
     HostTiles TH, TA;
     build_tiles(H, kTileNnz, TH);
     build_tiles(A, kTileNnz, TA);
@@ -182,6 +197,7 @@ int SparseSolver::init(int64_t n64, int64_t m64, const int64_t *Pp, const int64_
     assign_tiles(TH, grid);
     assign_tiles(TA, grid);
 
+    lap("tiles");
     // ---- upload
     if ((rc = upload_tiled(arena, H, TH, prob.H))) return rc;
     if ((rc = upload_tiled(arena, A, TA, prob.A))) return rc;
@@ -223,7 +239,9 @@ int SparseSolver::init(int64_t n64, int64_t m64, const int64_t *Pp, const int64_
     QPB_CUDA(cudaEventCreate(&ev0));
     QPB_CUDA(cudaEventCreate(&ev1));
     QPB_CUDA(cudaDeviceSynchronize());
+    lap("upload+alloc");
     setup_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (getenv("QPB200_TIMING")) fprintf(stderr, "[qpb200_create] total %.1f ms:%s\n", setup_ms, laps.c_str());
     return QPB200_OK;
 }
 
