@@ -57,7 +57,7 @@ __device__ __forceinline__ double clamp_julia(double x, double lo, double hi) {
 // Stand-alone SpMV (operator unit tests, SpMV roofline measurement).
 //   mode 0: y[rows] = M x            mode 1 (split): y0 = M[:, :split] x[:split], y1 = M[:, split:] x[split:]
 // =============================================================================================
-template <bool TMA, bool SPLIT>
+template <int TMA, bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 2) spmv_kernel(CsrTiled M, const double *x, double *y0, double *y1) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SpmvSmem &sm = *reinterpret_cast<SpmvSmem *>(smem_raw);
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(kThreads, 2) spmv_kernel(CsrTiled M, const dou
 // Every scalar (rho, alpha_cg, beta, residuals, flags) is recomputed identically by every thread
 // from bit-identical all-reduced values, so control flow is uniform across the grid.
 // =============================================================================================
-template <bool TMA, bool PRE>
+template <int TMA, bool PRE>
 __global__ void __launch_bounds__(kThreads, 2) admm_kernel(SparseProblemDev p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SpmvSmem &sm = *reinterpret_cast<SpmvSmem *>(smem_raw);

@@ -35,7 +35,7 @@ struct DistBuffers {
     double *wbuf2;    // 2 n    : [P x partial ; A' y partial]
 };
 
-template <bool TMA, bool PRE>
+template <int TMA, bool PRE>
 __global__ void __launch_bounds__(kThreads, 2) admm_dist_kernel(SparseProblemDev p, DistBuffers d, int seg, int do_check) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SpmvSmem &sm = *reinterpret_cast<SpmvSmem *>(smem_raw);

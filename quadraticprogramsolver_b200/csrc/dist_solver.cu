@@ -73,8 +73,10 @@ void dist_destroy(DistContext *d) {
 
 static int launch_seg(SparseSolver &s, DistContext &d, int seg, int do_check) {
     void *args[] = {(void *)&s.prob, (void *)&d.buf, (void *)&seg, (void *)&do_check};
-    const void *fn = s.use_tma ? (s.use_pre ? (const void *)admm_dist_kernel<true, true> : (const void *)admm_dist_kernel<true, false>)
-                               : (s.use_pre ? (const void *)admm_dist_kernel<false, true> : (const void *)admm_dist_kernel<false, false>);
+    const void *fns[3][2] = {{(const void *)admm_dist_kernel<0, false>, (const void *)admm_dist_kernel<0, true>},
+                             {(const void *)admm_dist_kernel<1, false>, (const void *)admm_dist_kernel<1, true>},
+                             {(const void *)admm_dist_kernel<2, false>, (const void *)admm_dist_kernel<2, true>}};
+    const void *fn = fns[s.loader][s.use_pre ? 1 : 0];
     QPB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(s.grid), dim3(kThreads), args, sizeof(SpmvSmem), s.stream));
     ++d.launches;
     return QPB200_OK;
@@ -183,8 +185,9 @@ int dist_init(SparseSolver &s, DistContext *&out, int rank, int nranks, const vo
     QPB_CUDA(s.arena.alloc(&d->buf.wbuf, (size_t)s.n + 8, true));
     QPB_CUDA(s.arena.alloc(&d->buf.wbuf2, (size_t)2 * s.n + 8, true));
     QPB_CUDA(cudaMallocHost(&d->host_state, sizeof(DistState)));
-    for (const void *fn : {(const void *)admm_dist_kernel<true, true>, (const void *)admm_dist_kernel<true, false>,
-                           (const void *)admm_dist_kernel<false, true>, (const void *)admm_dist_kernel<false, false>}) {
+    for (const void *fn : {(const void *)admm_dist_kernel<0, false>, (const void *)admm_dist_kernel<0, true>,
+                           (const void *)admm_dist_kernel<1, false>, (const void *)admm_dist_kernel<1, true>,
+                           (const void *)admm_dist_kernel<2, false>, (const void *)admm_dist_kernel<2, true>}) {
         QPB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpmvSmem)));
         int per_sm = 0;
         QPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, sizeof(SpmvSmem)));

@@ -5,6 +5,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <functional>
 #include <string>
 #include <vector>
@@ -51,12 +52,34 @@ struct DeviceArena {
     }
 };
 
+// Uninitialised POD buffer: std::vector::resize would zero-fill (and page-fault) hundreds of MB on one
+// thread; here the first touch happens in the parallel fill loops.
+template <class T>
+struct PodBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    PodBuf() = default;
+    PodBuf(const PodBuf &) = delete;
+    PodBuf &operator=(const PodBuf &) = delete;
+    ~PodBuf() { free(p); }
+    void resize(size_t k) {
+        free(p);
+        p = static_cast<T *>(malloc((k > 0 ? k : 1) * sizeof(T)));
+        n = k;
+    }
+    T *data() { return p; }
+    const T *data() const { return p; }
+    size_t size() const { return n; }
+    T &operator[](size_t i) { return p[i]; }
+    const T &operator[](size_t i) const { return p[i]; }
+};
+
 // Host CSR with int32 indices (the device layout before tiling).
 struct HostCsr {
     int rows = 0, cols = 0;
     std::vector<int> ptr;      // rows + 1
-    std::vector<int> idx;      // nnz
-    std::vector<double> val;   // nnz
+    PodBuf<int> idx;           // nnz
+    PodBuf<double> val;        // nnz
     std::vector<int> mid;      // rows (optional)
     int64_t nnz() const { return ptr.empty() ? 0 : ptr.back(); }
 };

@@ -61,8 +61,7 @@ static int upload_tiled(DeviceArena &ar, const HostCsr &M, const HostTiles &T, C
     return QPB200_OK;
 }
 
-template <class K>
-static int prep_kernel(K kernel, int *blocks_per_sm) {
+static int prep_kernel(const void *kernel, int *blocks_per_sm) {
     QPB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpmvSmem)));
     QPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kernel, kThreads, sizeof(SpmvSmem)));
     return QPB200_OK;
@@ -87,7 +86,7 @@ int SparseSolver::settings_to_dev(const qpb200_settings &s) {
     d.pcg_eps = s.pcg_eps;
     d.pcg_rel_eps = s.pcg_rel_eps < 0.0 ? std::sqrt(2.220446049250313e-16) : s.pcg_rel_eps;
     d.adaptive_rho = s.adaptive_rho;
-    use_tma = (s.spmv_loader == 2) || (s.spmv_loader == 0);   // auto = TMA
+    loader = s.spmv_loader == 1 ? 0 : (s.spmv_loader == 2 ? 1 : 2);   // settings: 0 auto (= 3), 1 LDG, 2 TMA, 3 TMA pipelined
     use_pre = s.precond != QPB200_PRECOND_NONE;
     return QPB200_OK;
 }
@@ -172,17 +171,15 @@ int SparseSolver::init(int64_t n64, int64_t m64, const int64_t *Pp, const int64_
     cudaDeviceProp prop;
     QPB_CUDA(cudaGetDeviceProperties(&prop, device));
     num_sms = prop.multiProcessorCount;
-    int bps[4] = {0, 0, 0, 0};
-    if ((rc = prep_kernel(admm_kernel<false, false>, &bps[0]))) return rc;
-    if ((rc = prep_kernel(admm_kernel<false, true>, &bps[1]))) return rc;
-    if ((rc = prep_kernel(admm_kernel<true, false>, &bps[2]))) return rc;
-    if ((rc = prep_kernel(admm_kernel<true, true>, &bps[3]))) return rc;
-    int tmp = 0;
-    if ((rc = prep_kernel(spmv_kernel<false, false>, &tmp))) return rc;
-    if ((rc = prep_kernel(spmv_kernel<false, true>, &tmp))) return rc;
-    if ((rc = prep_kernel(spmv_kernel<true, false>, &tmp))) return rc;
-    if ((rc = prep_kernel(spmv_kernel<true, true>, &tmp))) return rc;
-    int per_sm = std::min(std::min(bps[0], bps[1]), std::min(bps[2], bps[3]));
+    int per_sm = 1 << 30, tmp = 0;
+    for (const void *fn : {(const void *)admm_kernel<0, false>, (const void *)admm_kernel<0, true>, (const void *)admm_kernel<1, false>,
+                           (const void *)admm_kernel<1, true>, (const void *)admm_kernel<2, false>, (const void *)admm_kernel<2, true>}) {
+        if ((rc = prep_kernel(fn, &tmp))) return rc;
+        per_sm = std::min(per_sm, tmp);
+    }
+    for (const void *fn : {(const void *)spmv_kernel<0, false>, (const void *)spmv_kernel<0, true>, (const void *)spmv_kernel<1, false>,
+                           (const void *)spmv_kernel<1, true>, (const void *)spmv_kernel<2, false>, (const void *)spmv_kernel<2, true>})
+        if ((rc = prep_kernel(fn, &tmp))) return rc;
     if (per_sm < 1) return fail(QPB200_ERR_CUDA, "persistent kernel does not fit on an SM");
     per_sm = std::min(per_sm, 2);
     const int grid_max = num_sms * per_sm;
@@ -272,8 +269,10 @@ int SparseSolver::reset_state(const double *x0_host) {
 
 int SparseSolver::launch_admm() {
     void *args[] = {(void *)&prob};
-    const void *fn = use_tma ? (use_pre ? (const void *)admm_kernel<true, true> : (const void *)admm_kernel<true, false>)
-                             : (use_pre ? (const void *)admm_kernel<false, true> : (const void *)admm_kernel<false, false>);
+    const void *fns[3][2] = {{(const void *)admm_kernel<0, false>, (const void *)admm_kernel<0, true>},
+                             {(const void *)admm_kernel<1, false>, (const void *)admm_kernel<1, true>},
+                             {(const void *)admm_kernel<2, false>, (const void *)admm_kernel<2, true>}};
+    const void *fn = fns[loader][use_pre ? 1 : 0];
     QPB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, sizeof(SpmvSmem), stream));
     return QPB200_OK;
 }
@@ -335,17 +334,18 @@ int64_t SparseSolver::solve_bytes() const {
 }
 
 template <bool SPLIT>
-static void launch_spmv(bool tma, const CsrTiled &M, int grid, const double *x, double *y0, double *y1, cudaStream_t st) {
-    if (tma) spmv_kernel<true, SPLIT><<<grid, kThreads, sizeof(SpmvSmem), st>>>(M, x, y0, y1);
-    else spmv_kernel<false, SPLIT><<<grid, kThreads, sizeof(SpmvSmem), st>>>(M, x, y0, y1);
+static void launch_spmv(int loader, const CsrTiled &M, int grid, const double *x, double *y0, double *y1, cudaStream_t st) {
+    if (loader == 2) spmv_kernel<2, SPLIT><<<grid, kThreads, sizeof(SpmvSmem), st>>>(M, x, y0, y1);
+    else if (loader == 1) spmv_kernel<1, SPLIT><<<grid, kThreads, sizeof(SpmvSmem), st>>>(M, x, y0, y1);
+    else spmv_kernel<0, SPLIT><<<grid, kThreads, sizeof(SpmvSmem), st>>>(M, x, y0, y1);
 }
 
 int SparseSolver::apply_device(int which, const double *x, double *y) {
     // x, y device pointers; uses scratch (n+m) as needed
     switch (which) {
-        case 1: launch_spmv<false>(use_tma, prob.A, grid, x, y, nullptr, stream); break;
-        case 4: launch_spmv<false>(use_tma, prob.H, grid, x, y, nullptr, stream); break;
-        case 5: launch_spmv<true>(use_tma, prob.H, grid, x, y, y + n, stream); break;
+        case 1: launch_spmv<false>(loader, prob.A, grid, x, y, nullptr, stream); break;
+        case 4: launch_spmv<false>(loader, prob.H, grid, x, y, nullptr, stream); break;
+        case 5: launch_spmv<true>(loader, prob.H, grid, x, y, y + n, stream); break;
         default: return fail(QPB200_ERR_ARG, "apply_device: which = %d", which);
     }
     QPB_CUDA(cudaGetLastError());

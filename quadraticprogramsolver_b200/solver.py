@@ -82,7 +82,7 @@ def make_settings(**kw) -> Settings:
     s.lin_solver = {"pcg": _lib.LINSOLVE_PCG, "cholesky": _lib.LINSOLVE_CHOLESKY}[str(opts["linSolver"]).lstrip(":")]
     s.precond = {"none": _lib.PRECOND_NONE, "jacobi": _lib.PRECOND_JACOBI}[str(opts["precond"]).lstrip(":")]
     s.device = int(opts["device"])
-    s.spmv_loader = {"auto": 0, "ldg": 1, "tma": 2}[str(opts["spmvLoader"])]
+    s.spmv_loader = {"auto": 0, "ldg": 1, "tma": 2, "tma_pipe": 3}[str(opts["spmvLoader"])]
     return s
 
 

@@ -17,7 +17,7 @@ P, q, A, l, u = config_cfg5(seed=1234, scale=scale)
 out["gen_s"] = time.time() - t0
 out["n"], out["m"], out["nnzP"], out["nnzA"] = P.shape[0], A.shape[0], int(P.nnz), int(A.nnz)
 print(out, flush=True)
-for loader in ("ldg", "tma"):
+for loader in ("ldg", "tma", "tma_pipe"):
     t0 = time.time()
     with S.QPB200Solver(P, q, A, l, u, spmvLoader=loader, numIterations=100) as s:
         out[f"{loader}_create_s"] = time.time() - t0
