@@ -249,9 +249,15 @@ def run_b200(args):
     h2d = Pp.nbytes + Pi.nbytes + Pv.nbytes + Ap.nbytes + Ai.nbytes + Av.nbytes + 8 * (2 * n + 2 * m_loc)
     d2h = 8 * (n + 2 * m_loc)
 
+    # The host buffers are what the reference caller owns: SparseMatrixCSC arrays (Int64 indices), q, l, u.
+    # (scipy stores int32 indices; the one-off widening to Julia's Int64 layout is not part of the path.)
+    Parr, Aarr = (Pp, Pi, Pv), (Ap, Ai, Av)
+    q64, l64, u64 = np.ascontiguousarray(q), np.ascontiguousarray(l), np.ascontiguousarray(u)
+
     def e2e_once():
         if world == 1:
-            return S.SolveQuadraticProgram(P, q, A, l, u, **kw)[2]
+            xx = np.zeros(n)
+            return S.solve_csc_arrays(n, m, Parr, q64, Aarr, l64, u64, xx, want_zy=True, **kw)[1]
         with S.QPB200DistSolver(P, q, A, l, u, presliced=presliced, **kw) as ds:
             xx = np.zeros(n)
             ds.solve(xx, want_zy=True)

@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqpb200.so")
+LIB_PATH = os.environ.get("QPB200_LIB", os.path.join(_HERE, "libqpb200.so"))   # QPB200_LIB: A/B builds
 
 QPB200_OK = 0
 ERR_ARG, ERR_NONFINITE, ERR_CUDA, ERR_NCCL, ERR_FACTOR, ERR_DEVICE = -1, -2, -3, -4, -5, -6

@@ -64,6 +64,8 @@ __global__ void __launch_bounds__(kThreads, 2) admm_dist_kernel(SparseProblemDev
     double res_prim = S.res_prim, res_dual = S.res_dual;
     double lmax[4] = {S.lmax[0], S.lmax[1], S.lmax[2], S.lmax[3]};
     __syncthreads();
+    // a CG step enqueued speculatively after convergence: nothing to do, nothing to write (uniform exit)
+    if (seg == kSegPcgStep && !cont) return;
     // NOTE: the control block is rewritten only at the very end, after at least one grid barrier
     // whenever any value changed (segments without a barrier write back what they read, plus counters
     // that only block 0 / thread 0 touches).

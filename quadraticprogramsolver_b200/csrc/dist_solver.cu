@@ -59,7 +59,8 @@ struct DistContext {
     int rank = 0, nranks = 1;
     ncclComm_t comm = nullptr;
     DistBuffers buf{};
-    DistState *host_state = nullptr;   // pinned mirror
+    DistState *host_state = nullptr;   // pinned mirror (2 slots: the CG loop runs one step ahead of the host)
+    cudaEvent_t ev[2] = {nullptr, nullptr};
     long long launches = 0, allreduces = 0;
 };
 
@@ -68,6 +69,7 @@ void dist_destroy(DistContext *d) {
     NcclApi *api = nccl_api();
     if (d->comm && api) api->CommDestroy(d->comm);
     if (d->host_state) cudaFreeHost(d->host_state);
+    for (auto &e : d->ev) if (e) cudaEventDestroy(e);
     delete d;
 }
 
@@ -85,6 +87,13 @@ static int launch_seg(SparseSolver &s, DistContext &d, int seg, int do_check) {
 static int read_state(SparseSolver &s, DistContext &d) {
     QPB_CUDA(cudaMemcpyAsync(d.host_state, d.buf.state, sizeof(DistState), cudaMemcpyDeviceToHost, s.stream));
     QPB_CUDA(cudaStreamSynchronize(s.stream));
+    return QPB200_OK;
+}
+
+// asynchronous variant: copy the control block into pinned slot `slot` and mark it with an event
+static int post_read(SparseSolver &s, DistContext &d, int slot) {
+    QPB_CUDA(cudaMemcpyAsync(d.host_state + slot, d.buf.state, sizeof(DistState), cudaMemcpyDeviceToHost, s.stream));
+    QPB_CUDA(cudaEventRecord(d.ev[slot], s.stream));
     return QPB200_OK;
 }
 
@@ -117,12 +126,18 @@ int dist_solve(SparseSolver &s, DistContext &d, double *x_inout, double *z_out, 
         QPB_NCCL(api->AllReduce(d.buf.wbuf, d.buf.wbuf, (size_t)n, ncclDouble, ncclSum, d.comm, s.stream));
         ++d.allreduces;
         if ((rc = launch_seg(s, d, kSegPcgInit, 0))) return rc;
-        if ((rc = read_state(s, d))) return rc;
-        while (d.host_state->cont) {
+        // CG loop, run ONE STEP AHEAD of the host: step j+1 (all-reduce + segment + read-back) is enqueued
+        // before the host has seen the `cont` flag of step j, so the host round trip never idles the GPU.
+        // A step enqueued after the solve has converged finds cont == 0 on the device and returns at once
+        // (its all-reduce ran on a dead buffer: one wasted 8 MB all-reduce per ADMM iteration).
+        if ((rc = post_read(s, d, 0))) return rc;
+        for (int j = 0;; ++j) {
             QPB_NCCL(api->AllReduce(d.buf.wbuf, d.buf.wbuf, (size_t)n, ncclDouble, ncclSum, d.comm, s.stream));
             ++d.allreduces;
             if ((rc = launch_seg(s, d, kSegPcgStep, 0))) return rc;
-            if ((rc = read_state(s, d))) return rc;
+            if ((rc = post_read(s, d, (j + 1) & 1))) return rc;
+            QPB_CUDA(cudaEventSynchronize(d.ev[j & 1]));
+            if (!d.host_state[j & 1].cont) break;     // state after step j-1 (j = 0: after the init segment)
         }
         const int do_check = (ii % check_every) == 0;
         if ((rc = launch_seg(s, d, kSegUpdate, do_check))) return rc;
@@ -184,7 +199,9 @@ int dist_init(SparseSolver &s, DistContext *&out, int rank, int nranks, const vo
     QPB_CUDA(s.arena.alloc(&d->buf.state, 1, true));
     QPB_CUDA(s.arena.alloc(&d->buf.wbuf, (size_t)s.n + 8, true));
     QPB_CUDA(s.arena.alloc(&d->buf.wbuf2, (size_t)2 * s.n + 8, true));
-    QPB_CUDA(cudaMallocHost(&d->host_state, sizeof(DistState)));
+    QPB_CUDA(cudaMallocHost(&d->host_state, 2 * sizeof(DistState)));
+    QPB_CUDA(cudaEventCreateWithFlags(&d->ev[0], cudaEventDisableTiming));
+    QPB_CUDA(cudaEventCreateWithFlags(&d->ev[1], cudaEventDisableTiming));
     for (const void *fn : {(const void *)admm_dist_kernel<0, false>, (const void *)admm_dist_kernel<0, true>,
                            (const void *)admm_dist_kernel<1, false>, (const void *)admm_dist_kernel<1, true>,
                            (const void *)admm_dist_kernel<2, false>, (const void *)admm_dist_kernel<2, true>}) {

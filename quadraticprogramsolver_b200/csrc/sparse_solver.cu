@@ -86,7 +86,7 @@ int SparseSolver::settings_to_dev(const qpb200_settings &s) {
     d.pcg_eps = s.pcg_eps;
     d.pcg_rel_eps = s.pcg_rel_eps < 0.0 ? std::sqrt(2.220446049250313e-16) : s.pcg_rel_eps;
     d.adaptive_rho = s.adaptive_rho;
-    loader = s.spmv_loader == 1 ? 0 : (s.spmv_loader == 2 ? 1 : 2);   // settings: 0 auto (= 3), 1 LDG, 2 TMA, 3 TMA pipelined
+    loader = s.spmv_loader == 1 ? 0 : (s.spmv_loader == 3 ? 2 : 1);   // settings: 0 auto (= 2, TMA), 1 LDG, 2 TMA, 3 TMA pipelined
     use_pre = s.precond != QPB200_PRECOND_NONE;
     return QPB200_OK;
 }
@@ -181,7 +181,10 @@ int SparseSolver::init(int64_t n64, int64_t m64, const int64_t *Pp, const int64_
                            (const void *)spmv_kernel<1, true>, (const void *)spmv_kernel<2, false>, (const void *)spmv_kernel<2, true>})
         if ((rc = prep_kernel(fn, &tmp))) return rc;
     if (per_sm < 1) return fail(QPB200_ERR_CUDA, "persistent kernel does not fit on an SM");
-    per_sm = std::min(per_sm, 2);
+    {
+        const char *e = getenv("QPB200_CTAS_PER_SM");   // A/B experiments only
+        per_sm = std::min(per_sm, e ? std::max(1, atoi(e)) : 2);
+    }
     const int grid_max = num_sms * per_sm;
 
     lap("kernel_prep");

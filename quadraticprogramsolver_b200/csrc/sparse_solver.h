@@ -8,7 +8,7 @@ namespace qpb {
 struct SparseSolver {
     int n = 0, m = 0, device = -1, num_sms = 0, grid = 0;
     int64_t nnzP = 0, nnzA = 0;
-    int loader = 2;          // 0 LDG, 1 TMA, 2 TMA + software-pipelined gathers
+    int loader = 1;          // 0 LDG, 1 TMA (default), 2 TMA + software-pipelined gathers
     bool use_pre = true;
     qpb200_settings settings{};
     SparseProblemDev prob{};

@@ -19,11 +19,17 @@
 
 namespace qpb {
 
-constexpr int kTileNnz = 2048;          // non-zeros per tile
+#ifndef QPB_TILE_NNZ
+#define QPB_TILE_NNZ 2048
+#endif
+#ifndef QPB_STAGES
+#define QPB_STAGES 3
+#endif
+constexpr int kTileNnz = QPB_TILE_NNZ;   // non-zeros per tile (build-time tunable for A/B runs)
 constexpr int kTilePad = 8;             // alignment slack of a TMA-staged tile
-constexpr int kStages = 3;              // TMA pipeline depth
+constexpr int kStages = QPB_STAGES;      // TMA pipeline depth
 constexpr int kTileCap = kTileNnz + kTilePad;
-constexpr int kGatherBatch = 4;        // independent x-gathers issued back to back per thread
+constexpr int kGatherBatch = kTileNnz / kThreads;   // independent x-gathers issued back to back per thread
 
 // tile descriptor: x = first row, y = #rows, z = first nnz (k0), w = #nnz | flags
 constexpr int kTileContFromPrev = 1 << 30;   // this tile continues a long row started earlier
@@ -193,18 +199,17 @@ __device__ __forceinline__ void spmv_tiles_tma(const CsrTiled &M, const double *
         const int *col = sm.col[s] + off;
         for (int kb = threadIdx.x; kb < nk; kb += kThreads * kGatherBatch) {
             int c[kGatherBatch];
-            double v[kGatherBatch], xv[kGatherBatch];
+            double xv[kGatherBatch];
 #pragma unroll
             for (int j = 0; j < kGatherBatch; ++j) {
                 const int k = kb + j * kThreads;
                 c[j] = (k < nk) ? col[k] : 0;
-                v[j] = (k < nk) ? val[k] : 0.0;
             }
 #pragma unroll
             for (int j = 0; j < kGatherBatch; ++j) xv[j] = (kb + j * kThreads < nk) ? x[c[j]] : 0.0;   // independent gathers in flight
 #pragma unroll
             for (int j = 0; j < kGatherBatch; ++j)
-                if (kb + j * kThreads < nk) val[kb + j * kThreads] = v[j] * xv[j];
+                if (kb + j * kThreads < nk) val[kb + j * kThreads] *= xv[j];
         }
         fence_proxy_async_smem();   // our generic accesses to the stages (incl. tile i-1's reads) before the refill
         __syncthreads();
@@ -224,7 +229,10 @@ template <bool SPLIT, class Epi>
 __device__ __forceinline__ void spmv_tiles_tma_pipe(const CsrTiled &M, const double *x, SpmvSmem &sm, PipeState &ps,
                                                     Epi &epi) {
     static_assert(kTileNnz == kThreads * kGatherBatch, "one gather batch must cover a tile");
-    static_assert(kStages >= 3, "the refill targets the stage of tile i-1 while tile i+1 is being read");
+    if (kStages < 3) {   // the refill targets the stage of tile i-1 while tile i+1 is being read
+        spmv_tiles_tma<SPLIT>(M, x, sm, ps, epi);
+        return;
+    }
     const int tb = M.cta_begin[blockIdx.x], te = M.cta_begin[blockIdx.x + 1];
     const int nt = te - tb;
     fence_proxy_async_smem();

@@ -290,3 +290,31 @@ def config_cfg3_batch(batch: int, n: int = 64, m: int = 96, seed: int = 1234):
     u[vI] = 1.0
     A_cm = np.ascontiguousarray(A_rm.transpose(0, 2, 1))   # [b, j, i] -> column-major m x n block
     return np.ascontiguousarray(P), q, A_cm, l, u
+
+
+def config_banded(n: int = 1_000_000, m: int = 2_000_000, nnz_row_p: int = 26, nnz_row_a: int = 5, band: int = 256,
+                  seed: int = 1234):
+    """A QP with the SAME sizes and non-zeros per row as cfg5 but with every row's columns inside a band of
+    +-``band`` around the (scaled) diagonal -- i.e. the gathers of x have locality.  Used only to separate the
+    SpMV engine's streaming ability from cfg5's uniformly random gather pattern; P is made
+    symmetric and diagonally dominant so the QP is well posed."""
+    rng = np.random.default_rng(seed)
+
+    def band_matrix(rows, cols, k):
+        r = np.repeat(np.arange(rows, dtype=np.int64), k)
+        centre = (r * cols) // max(rows, 1)
+        c = np.clip(centre + rng.integers(-band, band + 1, size=r.shape[0]), 0, cols - 1)
+        v = rng.standard_normal(r.shape[0])
+        mat = sp.csr_matrix((v, (r, c)), shape=(rows, cols))
+        mat.sum_duplicates()
+        return mat
+
+    T = band_matrix(n, n, max(1, nnz_row_p // 2))
+    P = (T + T.T) * 0.5
+    P = P + sp.diags(np.asarray(abs(P).sum(axis=1)).ravel() + 1e-2)
+    A = band_matrix(m, n, nnz_row_a)
+    q = rng.standard_normal(n)
+    centre = A @ rng.standard_normal(n)
+    l = centre - rng.random(m)
+    u = centre + rng.random(m)
+    return _finish(P, q, A, l, u)

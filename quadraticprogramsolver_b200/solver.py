@@ -334,3 +334,32 @@ class QPB200DistSolver:
             self.close()
         except Exception:
             pass
+
+
+def csc_arrays_int64(mat):
+    """``(colptr, rowval, nzval)`` of a scipy matrix as Int64/Int64/Float64, 0-based -- the three arrays a
+    Julia ``SparseMatrixCSC{Float64,Int64}`` holds (scipy keeps int32 indices, Julia does not)."""
+    return _csc_arrays(mat)
+
+
+def solve_csc_arrays(n, m, P_arrays, q, A_arrays, l, u, vX, want_zy=False, **kw):
+    """The exact call sequence of julia/QPB200.jl on raw CSC arrays: qpb200_create -> qpb200_solve ->
+    qpb200_destroy, nothing else.  ``vX`` is mutated; returns ``(flag, info)``."""
+    lib = _lib.load()
+    Pp, Pi, Pv = P_arrays
+    Ap, Ai, Av = A_arrays
+    settings = make_settings(**kw)
+    h = C.c_void_p()
+    _lib.check(lib.qpb200_create(C.byref(h), n, m, _p64(Pp), _p64(Pi), _pd(Pv), _p64(Ap), _p64(Ai), _pd(Av), _pd(q), _pd(l),
+                                 _pd(u), C.byref(settings), 0))
+    try:
+        info = Info()
+        z = np.empty(m) if want_zy else None
+        y = np.empty(m) if want_zy else None
+        _lib.check(lib.qpb200_solve(h, _pd(vX), _pd(z) if want_zy else None, _pd(y) if want_zy else None, C.byref(info)))
+    finally:
+        lib.qpb200_destroy(h)
+    d = info.as_dict()
+    if want_zy:
+        d["z"], d["y"] = z, y
+    return ConvergenceFlag(info.conv_flag), d
