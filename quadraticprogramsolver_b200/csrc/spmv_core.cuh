@@ -187,9 +187,18 @@ __device__ __forceinline__ void spmv_tiles_tma(const CsrTiled &M, const double *
         const int pre = nt < (kStages - 1) ? nt : (kStages - 1);
         for (int i = 0; i < pre; ++i) tma_issue_tile(M, __ldg(M.tiles + tb + i), sm, i % kStages);
     }
+    // Tile descriptors are fetched ONE ITERATION AHEAD: a descriptor load issued when it is needed queues
+    // behind the thousands of x-gathers the SM has in flight (L1 is thrashed by them, so it is an L2 round
+    // trip under load) and serialises the tile loop; the same holds for the descriptor thread 0 needs to
+    // issue the next TMA refill.
+    int4 td_next = nt > 0 ? __ldg(M.tiles + tb) : make_int4(0, 0, 0, 0);
+    int4 td_issue = (threadIdx.x == 0 && kStages - 1 < nt) ? __ldg(M.tiles + tb + kStages - 1) : make_int4(0, 0, 0, 0);
     for (int i = 0; i < nt; ++i) {
         const int s = i % kStages;
-        const int4 td = __ldg(M.tiles + tb + i);
+        const int4 td = td_next;
+        const int4 td_refill = td_issue;
+        if (i + 1 < nt) td_next = __ldg(M.tiles + tb + i + 1);
+        if (threadIdx.x == 0 && i + kStages < nt) td_issue = __ldg(M.tiles + tb + i + kStages);
         const int k0 = td.z, nk = td.w & kTileNkMask;
         const int off = k0 & 3;
         const RowPre pre = prefetch_rowptr<SPLIT>(M, td);
@@ -213,8 +222,7 @@ __device__ __forceinline__ void spmv_tiles_tma(const CsrTiled &M, const double *
         }
         fence_proxy_async_smem();   // our generic accesses to the stages (incl. tile i-1's reads) before the refill
         __syncthreads();
-        if (threadIdx.x == 0 && i + kStages - 1 < nt)
-            tma_issue_tile(M, __ldg(M.tiles + tb + i + kStages - 1), sm, (i + kStages - 1) % kStages);
+        if (threadIdx.x == 0 && i + kStages - 1 < nt) tma_issue_tile(M, td_refill, sm, (i + kStages - 1) % kStages);
         tile_row_sums<SPLIT>(M, td, val, sm, pre, epi);
     }
     __syncthreads();
