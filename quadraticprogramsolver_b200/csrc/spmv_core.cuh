@@ -183,8 +183,13 @@ __device__ __forceinline__ void spmv_tiles_tma(const CsrTiled &M, const double *
     // the stages were last touched through the generic proxy (previous phase's row sums)
     fence_proxy_async_smem();
     __syncthreads();
+#ifndef QPB_REFILL_AFTER_ROWSUMS
+    constexpr int kAhead = kStages - 1;     // tiles in flight ahead of the one being processed
+#else
+    constexpr int kAhead = kStages;
+#endif
     if (threadIdx.x == 0) {
-        const int pre = nt < (kStages - 1) ? nt : (kStages - 1);
+        const int pre = nt < kAhead ? nt : kAhead;
         for (int i = 0; i < pre; ++i) tma_issue_tile(M, __ldg(M.tiles + tb + i), sm, i % kStages);
     }
     // Tile descriptors are fetched ONE ITERATION AHEAD: a descriptor load issued when it is needed queues
@@ -192,13 +197,13 @@ __device__ __forceinline__ void spmv_tiles_tma(const CsrTiled &M, const double *
     // trip under load) and serialises the tile loop; the same holds for the descriptor thread 0 needs to
     // issue the next TMA refill.
     int4 td_next = nt > 0 ? __ldg(M.tiles + tb) : make_int4(0, 0, 0, 0);
-    int4 td_issue = (threadIdx.x == 0 && kStages - 1 < nt) ? __ldg(M.tiles + tb + kStages - 1) : make_int4(0, 0, 0, 0);
+    int4 td_issue = (threadIdx.x == 0 && kAhead < nt) ? __ldg(M.tiles + tb + kAhead) : make_int4(0, 0, 0, 0);
     for (int i = 0; i < nt; ++i) {
         const int s = i % kStages;
         const int4 td = td_next;
         const int4 td_refill = td_issue;
         if (i + 1 < nt) td_next = __ldg(M.tiles + tb + i + 1);
-        if (threadIdx.x == 0 && i + kStages < nt) td_issue = __ldg(M.tiles + tb + i + kStages);
+        if (threadIdx.x == 0 && i + 1 + kAhead < nt) td_issue = __ldg(M.tiles + tb + i + 1 + kAhead);
         const int k0 = td.z, nk = td.w & kTileNkMask;
         const int off = k0 & 3;
         const RowPre pre = prefetch_rowptr<SPLIT>(M, td);
@@ -220,10 +225,20 @@ __device__ __forceinline__ void spmv_tiles_tma(const CsrTiled &M, const double *
             for (int j = 0; j < kGatherBatch; ++j)
                 if (kb + j * kThreads < nk) val[kb + j * kThreads] *= xv[j];
         }
+#ifndef QPB_REFILL_AFTER_ROWSUMS
         fence_proxy_async_smem();   // our generic accesses to the stages (incl. tile i-1's reads) before the refill
         __syncthreads();
         if (threadIdx.x == 0 && i + kStages - 1 < nt) tma_issue_tile(M, td_refill, sm, (i + kStages - 1) % kStages);
         tile_row_sums<SPLIT>(M, td, val, sm, pre, epi);
+#else
+        // variant for 2 big stages: the stage of tile i is handed back right after ITS row sums (one more
+        // barrier per tile), so the refill (tile i + kStages) overlaps the whole next tile
+        __syncthreads();
+        tile_row_sums<SPLIT>(M, td, val, sm, pre, epi);
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (threadIdx.x == 0 && i + kStages < nt) tma_issue_tile(M, td_refill, sm, s);
+#endif
     }
     __syncthreads();
 }
@@ -264,8 +279,12 @@ __device__ __forceinline__ void spmv_tiles_tma_pipe(const CsrTiled &M, const dou
             c[j] = (k < nk) ? col[k] : 0;
             v[j] = (k < nk) ? val[k] : 0.0;
         }
+        // volatile: the loads must be ISSUED here (before the row sums of the previous tile), not sunk to their use
 #pragma unroll
-        for (int j = 0; j < kGatherBatch; ++j) xv[j] = (threadIdx.x + j * kThreads < nk) ? x[c[j]] : 0.0;
+        for (int j = 0; j < kGatherBatch; ++j) {
+            xv[j] = 0.0;
+            if (threadIdx.x + j * kThreads < nk) asm volatile("ld.global.f64 %0, [%1];" : "=d"(xv[j]) : "l"(x + c[j]) : "memory");
+        }
     };
     int4 td = make_int4(0, 0, 0, 0);
     if (nt > 0) {

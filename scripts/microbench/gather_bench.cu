@@ -1,0 +1,72 @@
+// gather_bench.cu -- what is the B200's ceiling for uniformly random 8-byte gathers out of an L2-resident
+// vector?  (The x-gathers of a CSR SpMV on a matrix with random columns, e.g. configs[4].)
+// Every thread streams coalesced int32 indices and gathers x[idx] with ILP independent loads in flight.
+// build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a gather_bench.cu -o gather_bench
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+template <int ILP, int MODE>
+__global__ void gather_kernel(const int *__restrict__ idx, const double *x, double *out, size_t n) {
+    double acc = 0.0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t base = (size_t)blockIdx.x * blockDim.x + threadIdx.x; base + (ILP - 1) * stride < n; base += ILP * stride) {
+        int c[ILP];
+        double v[ILP];
+#pragma unroll
+        for (int j = 0; j < ILP; ++j) c[j] = __ldg(idx + base + j * stride);
+#pragma unroll
+        for (int j = 0; j < ILP; ++j) {
+            if (MODE == 0) v[j] = x[c[j]];                     // ld.global (L1 allocate)
+            else if (MODE == 1) v[j] = __ldcg(x + c[j]);       // ld.global.cg (L2 only)
+            else if (MODE == 2) v[j] = __ldg(x + c[j]);        // ld.global.nc
+            else asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v[j]) : "l"(x + c[j]));
+        }
+#pragma unroll
+        for (int j = 0; j < ILP; ++j) acc += v[j];
+    }
+    if (acc == 1.2345e300) out[0] = acc;
+}
+
+template <int ILP, int MODE>
+float run(const int *idx, const double *x, double *out, size_t n, int blocks, int threads, int reps) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    gather_kernel<ILP, MODE><<<blocks, threads>>>(idx, x, out, n);
+    cudaEventRecord(a);
+    for (int r = 0; r < reps; ++r) gather_kernel<ILP, MODE><<<blocks, threads>>>(idx, x, out, n);
+    cudaEventRecord(b);
+    cudaEventSynchronize(b);
+    float ms; cudaEventElapsedTime(&ms, a, b);
+    return ms / reps;
+}
+
+int main(int argc, char **argv) {
+    const size_t nvec = argc > 1 ? (size_t)atoll(argv[1]) : 3000000;      // doubles in x (24 MB: L2 resident)
+    const size_t n = argc > 2 ? (size_t)atoll(argv[2]) : 36000000;        // gathers per launch
+    std::vector<int> h(n);
+    unsigned long long s = 88172645463325252ULL;
+    for (size_t i = 0; i < n; ++i) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; h[i] = (int)(s % nvec); }
+    int *idx; double *x, *out;
+    cudaMalloc(&idx, n * sizeof(int)); cudaMalloc(&x, nvec * sizeof(double)); cudaMalloc(&out, 8);
+    cudaMemcpy(idx, h.data(), n * sizeof(int), cudaMemcpyHostToDevice);
+    cudaMemset(x, 0, nvec * sizeof(double));
+    cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
+    const int sms = p.multiProcessorCount;
+    printf("device %s, %d SMs; x = %.1f MB, %zu gathers per launch (index stream %.0f MB)\n", p.name, sms, nvec * 8 / 1e6, n, n * 4 / 1e6);
+    printf("%-28s %8s %10s %12s %14s\n", "variant", "thr/SM", "ms", "Ggather/s", "gathers/clk/SM");
+    const char *modes[] = {"ld.global", "ld.global.cg", "ld.global.nc", "L1::no_allocate"};
+    for (int thr_per_sm : {512, 1024, 2048}) {
+        const int threads = 512, blocks = sms * thr_per_sm / threads;
+#define RUN(ILP, MODE)                                                                                      \
+        {                                                                                                   \
+            float ms = run<ILP, MODE>(idx, x, out, n, blocks, threads, 10);                                 \
+            char name[64]; snprintf(name, sizeof(name), "%s ILP=%d", modes[MODE], ILP);                     \
+            printf("%-28s %8d %10.4f %12.1f %14.3f\n", name, thr_per_sm, ms, n / ms / 1e6,                  \
+                   n / (ms * 1e-3) / (sms * (double)p.clockRate * 1e3));                                   \
+        }
+        RUN(4, 0) RUN(8, 0) RUN(16, 0) RUN(8, 1) RUN(8, 2) RUN(8, 3) RUN(16, 1)
+    }
+    return 0;
+}
