@@ -311,17 +311,123 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_cfg3(args):
+    """configs[2]: 65 536 small dense QPs (n = 64, m = 96), contiguous batch slices per GPU, no collective.
+    metric: QP solves/s (whole batch / slowest rank's device time)."""
+    from quadraticprogramsolver_b200 import solver as S
+    from quadraticprogramsolver_b200.problems import config_cfg3_batch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    batch = int(args.batch)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from oracle import c_oracle
+        ns = min(batch, 4096)
+        P, q, A, l, u = config_cfg3_batch(ns, 64, 96, seed=1234)
+        X, fl, it, sec, rc = c_oracle.solve_dense_batch(P, q, A, l, u)
+        v = ns / sec
+        print(json.dumps({"impl": "reference", "metric": "qp_solves_per_s", "value": v, "unit": "solves/s", "n_gpus": args.gpus,
+                          "steps": 1, "warmup": 0, "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": f"cfg3 dense QPs n=64 m=96, first {ns} problems of the batch"},
+                          "cpu_baseline": {"value": v, "unit": "solves/s", "cores": c_oracle.num_threads(), "kind": "port",
+                                           "sample": f"{ns} problems, oracle/qp_oracle.c dense Cholesky mode, OpenMP"},
+                          "e2e": {"value": v, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return
+    import torch
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = dist_mod
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    lo, hi = batch * rank // world, batch * (rank + 1) // world
+    P, q, A, l, u = config_cfg3_batch(batch, 64, 96, seed=1234)
+    P, q, A, l, u = P[lo:hi].copy(), q[lo:hi].copy(), A[lo:hi].copy(), l[lo:hi].copy(), u[lo:hi].copy()
+    kw = dict(device=local_rank)
+    b = S.QPB200Batch(P, q, A, l, u, **kw)
+    for _ in range(args.warmup):
+        b.solve()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    dev_ms, iters = 0.0, 0
+    for _ in range(args.steps):
+        X, flags, its = b.solve()
+        dev_ms += b.info["solve_ms"]; iters += int(its.sum())
+    barrier()
+    clocks = sampler.stop()
+    b.close()
+    e2e_steps = max(1, min(args.steps, 2))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        S.SolveQuadraticProgramBatch(P, q, A, l, u, **kw)
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+    tot = [dev_ms, e2e_wall, float(iters)]
+    if dist is not None:
+        t = torch.tensor(tot[:2], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t2 = torch.tensor([tot[2]], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t2, op=dist.ReduceOp.SUM)
+        tot = [float(t[0]), float(t[1]), float(t2[0])]
+    if rank == 0:
+        value = batch * args.steps / (tot[0] * 1e-3)
+        flops = 2.0 * 16448.0 * tot[2]     # FMAs per ADMM iteration: 2 * 96 * 64 (A, A') + 2 * 2080 (L^-1, L^-T)
+        line = {"metric": "qp_solves_per_s", "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": tot[0] / args.steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"cfg3: {batch} dense QPs n=64 m=96 (randomQp recipe d=1), reference defaults, Cholesky of "
+                           "P+sigma I+rho A'A per QP", "parallelism": f"batch slices over {world} GPU(s), no collective",
+                           "admm_iters_per_solve": tot[2] / (batch * args.steps)},
+                "clocks": clocks,
+                "e2e": {"value": batch * e2e_steps / tot[1], "unit": "solves/s", "h2d_bytes_per_step": int(8 * (P.size + A.size + q.size + l.size + u.size + q.size)) * world,
+                        "d2h_bytes_per_step": int(8 * q.size + 12 * len(q)) * world},
+                "gpu_launches": args.steps,
+                "roofline": {"bound": "fp64_fma", "achieved": flops / (tot[0] * 1e-3) / 1e12 / world, "peak": 40.0, "unit": "TFLOP/s",
+                             "frac": flops / (tot[0] * 1e-3) / 1e12 / world / 40.0, "traffic": None,
+                             "peak_source": "nominal B200 FP64 (no measured FP64 peak in MEASURED_PEAKS.json)",
+                             "kernel": "dense_batch_kernel (per-iteration GEMVs out of shared memory; DMMA only in the factorisation)"},
+                "admm_iters_per_s": tot[2] / (tot[0] * 1e-3)}
+        if world == 1 and not args.no_cpu:
+            from oracle import c_oracle
+            ns = 2048
+            Xr, fr, ir, sec, rc = c_oracle.solve_dense_batch(P[:ns], q[:ns], A[:ns], l[:ns], u[:ns])
+            line["cpu_baseline"] = {"value": ns / sec, "unit": "solves/s", "cores": c_oracle.num_threads(), "kind": "port",
+                                    "sample": f"first {ns} problems of the batch, oracle/qp_oracle.c, OpenMP",
+                                    "parity": {"flags_equal": bool(np.array_equal(fr, flags[:ns])),
+                                               "iters_max_diff": int(np.max(np.abs(ir - its[:ns]))),
+                                               "x_max_rel_err": float(np.max(np.abs(Xr - X[:ns]) / (1 + np.max(np.abs(Xr), axis=1, keepdims=True))))}}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg5", choices=["cfg5", "cfg2"])
+    ap.add_argument("--workload", default="cfg5", choices=["cfg5", "cfg2", "cfg3"])
+    ap.add_argument("--batch", type=int, default=65536, help="cfg3 batch size")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink cfg5 (tests only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    if args.workload == "cfg3":
+        run_cfg3(args)
+        return
     if args.impl == "reference":
         run_reference(args)
     else:

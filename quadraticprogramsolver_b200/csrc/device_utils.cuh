@@ -89,15 +89,20 @@ __device__ __forceinline__ void grid_barrier(const GridSync &gs, SyncState &st) 
     st.epoch += 1;
     __syncthreads();
     if (threadIdx.x == 0) {
+        // release: this CTA's writes (ordered before us by the bar.sync above) become visible before the arrival
         __threadfence();
         const unsigned long long old = atomicAdd(gs.count, 1ULL);
-        __threadfence();
         if (old == st.epoch * gridDim.x - 1ULL) {
+            // last arriver: it has observed every other arrival through the RMW chain; the fence makes that
+            // cumulative before the flag is published (only this one CTA pays for it)
+            __threadfence();
             st_release_gpu(gs.flag, st.epoch);
         } else {
             while (ld_acquire_gpu(gs.flag) < st.epoch) {
             }
         }
+        // acquire + L1 invalidate (MEMBAR.SC.GPU ; CCTL.IVALL): the phase that follows reads vectors other CTAs
+        // wrote with plain cached loads
         __threadfence();
     }
     __syncthreads();
