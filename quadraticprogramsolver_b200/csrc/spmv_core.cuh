@@ -52,7 +52,9 @@ struct CsrTiled {
 struct __align__(128) SpmvSmem {
     double val[kStages][kTileCap];   // TMA: staged values, overwritten in place by the products
                                      // LDG: buffers 0/1 hold the products (ping-pong)
+#ifndef QPB_COL_LDG
     int col[kStages][kTileCap];      // TMA only
+#endif
     uint64_t full[kStages];          // mbarriers
     double red[kWarps * kMaxRed];
     double bcast[kMaxRed];
@@ -170,9 +172,14 @@ __device__ __forceinline__ void tma_issue_tile(const CsrTiled &M, const int4 td,
     const int k0 = td.z, nk = td.w & kTileNkMask;
     const int k0a = k0 & ~3;                            // 16-byte aligned start for both arrays
     const int cnt = ((k0 + nk - k0a) + 3) & ~3;         // <= kTileNnz + 6
+#ifndef QPB_COL_LDG
     mbar_expect_tx(&sm.full[stage], static_cast<uint32_t>(cnt) * 12u);
     tma_load_1d(sm.val[stage], M.val + k0a, static_cast<uint32_t>(cnt) * 8u, &sm.full[stage]);
     tma_load_1d(sm.col[stage], M.col + k0a, static_cast<uint32_t>(cnt) * 4u, &sm.full[stage]);
+#else
+    mbar_expect_tx(&sm.full[stage], static_cast<uint32_t>(cnt) * 8u);
+    tma_load_1d(sm.val[stage], M.val + k0a, static_cast<uint32_t>(cnt) * 8u, &sm.full[stage]);
+#endif
 }
 
 template <bool SPLIT, class Epi>
@@ -197,6 +204,16 @@ __device__ __forceinline__ void spmv_tiles_tma(const CsrTiled &M, const double *
     // trip under load) and serialises the tile loop; the same holds for the descriptor thread 0 needs to
     // issue the next TMA refill.
     int4 td_next = nt > 0 ? __ldg(M.tiles + tb) : make_int4(0, 0, 0, 0);
+#ifdef QPB_COL_LDG
+    // column indices are NOT staged in shared memory (every KB of shared memory is a KB less L1, and L1
+    // capacity bounds the number of gathers in flight): they are read with coalesced loads one tile ahead
+    int cnext[kGatherBatch];
+#pragma unroll
+    for (int j = 0; j < kGatherBatch; ++j) {
+        const int k = threadIdx.x + j * kThreads;
+        cnext[j] = (nt > 0 && k < (td_next.w & kTileNkMask)) ? __ldg(M.col + td_next.z + k) : 0;
+    }
+#endif
     int4 td_issue = (threadIdx.x == 0 && kAhead < nt) ? __ldg(M.tiles + tb + kAhead) : make_int4(0, 0, 0, 0);
     for (int i = 0; i < nt; ++i) {
         const int s = i % kStages;
@@ -210,17 +227,32 @@ __device__ __forceinline__ void spmv_tiles_tma(const CsrTiled &M, const double *
         mbar_wait(&sm.full[s], (ps.parity >> s) & 1u);
         ps.parity ^= (1u << s);
         double *val = sm.val[s] + off;
+#ifndef QPB_COL_LDG
         const int *col = sm.col[s] + off;
+#endif
         for (int kb = threadIdx.x; kb < nk; kb += kThreads * kGatherBatch) {
             int c[kGatherBatch];
             double xv[kGatherBatch];
 #pragma unroll
             for (int j = 0; j < kGatherBatch; ++j) {
+#ifndef QPB_COL_LDG
                 const int k = kb + j * kThreads;
                 c[j] = (k < nk) ? col[k] : 0;
+#else
+                c[j] = cnext[j];
+#endif
             }
 #pragma unroll
             for (int j = 0; j < kGatherBatch; ++j) xv[j] = (kb + j * kThreads < nk) ? x[c[j]] : 0.0;   // independent gathers in flight
+#ifdef QPB_COL_LDG
+            if (i + 1 < nt) {
+#pragma unroll
+                for (int j = 0; j < kGatherBatch; ++j) {
+                    const int k = threadIdx.x + j * kThreads;
+                    cnext[j] = (k < (td_next.w & kTileNkMask)) ? __ldg(M.col + td_next.z + k) : 0;
+                }
+            }
+#endif
 #pragma unroll
             for (int j = 0; j < kGatherBatch; ++j)
                 if (kb + j * kThreads < nk) val[kb + j * kThreads] *= xv[j];
@@ -252,6 +284,9 @@ template <bool SPLIT, class Epi>
 __device__ __forceinline__ void spmv_tiles_tma_pipe(const CsrTiled &M, const double *x, SpmvSmem &sm, PipeState &ps,
                                                     Epi &epi) {
     static_assert(kTileNnz == kThreads * kGatherBatch, "one gather batch must cover a tile");
+#ifdef QPB_COL_LDG
+    spmv_tiles_tma<SPLIT>(M, x, sm, ps, epi);
+#else
     if (kStages < 3) {   // the refill targets the stage of tile i-1 while tile i+1 is being read
         spmv_tiles_tma<SPLIT>(M, x, sm, ps, epi);
         return;
@@ -314,6 +349,7 @@ __device__ __forceinline__ void spmv_tiles_tma_pipe(const CsrTiled &M, const dou
         td = tdn;
     }
     __syncthreads();
+#endif
 }
 
 // LOADER: 0 = coalesced LDG, 1 = TMA staged, 2 = TMA staged + software pipelined gathers

@@ -9,7 +9,7 @@ tag = sys.argv[1]
 scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 P, q, A, l, u = config_cfg5(seed=1234, scale=scale)
 out = {"tag": tag}
-for loader in ("tma", "tma_pipe"):
+for loader in ("tma",):
     with S.QPB200Solver(P, q, A, l, u, spmvLoader=loader, numIterations=100) as s:
         for which, name in ((1, "A"), (4, "H")):
             ms = min(s.time_apply(which, reps=20, flush_l2=True) for _ in range(2))
