@@ -1,0 +1,164 @@
+// dense_host.cu -- host side of the batched dense path (qpb200_batch_*); the kernel is in dense_kernel.cuh.
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "dense_kernel.cuh"
+#include "host_common.h"
+
+namespace qpb {
+
+struct DenseBatch {
+    int64_t batch = 0;
+    int n = 0, m = 0, mp = 0, device = -1, grid = 0;
+    qpb200_settings settings{};
+    DenseBatchParams prm{};
+    DeviceArena arena;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double setup_ms = 0.0;
+    size_t smem = 0;
+    ~DenseBatch() {
+        if (device >= 0) cudaSetDevice(device);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (stream) cudaStreamDestroy(stream);
+        arena.release();
+    }
+};
+
+}  // namespace qpb
+
+struct qpb200_batch {
+    qpb::DenseBatch b;
+};
+
+using namespace qpb;
+
+extern "C" {
+
+int qpb200_batch_create(qpb200_batch **out, int64_t batch, int64_t n, int64_t m, const double *P, const double *A,
+                        const double *q, const double *l, const double *u, const qpb200_settings *settings) {
+    if (!out) return fail(QPB200_ERR_ARG, "qpb200_batch_create: out is NULL");
+    *out = nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    if (batch <= 0 || n <= 0 || n > kDN || m <= 0 || m > 128)
+        return fail(QPB200_ERR_ARG, "qpb200_batch_create: need batch > 0, 0 < n <= 64, 0 < m <= 128 (got %lld, %lld, %lld)",
+                    (long long)batch, (long long)n, (long long)m);
+    if (batch >= (int64_t(1) << 31)) return fail(QPB200_ERR_ARG, "qpb200_batch_create: batch too large");
+    if (!P || !A || !q || !l || !u) return fail(QPB200_ERR_ARG, "qpb200_batch_create: NULL array");
+    qpb200_settings s;
+    if (settings) s = *settings;
+    else { qpb200_default_settings(&s); s.lin_solver = QPB200_LINSOLVE_CHOLESKY; }
+    if (!(s.rho > 0.0) || !(s.sigma >= 0.0) || s.max_iter < 0 || s.check_every <= 0)
+        return fail(QPB200_ERR_ARG, "settings: need rho > 0, sigma >= 0, max_iter >= 0, check_every > 0");
+    if (s.lin_solver != QPB200_LINSOLVE_CHOLESKY)
+        return fail(QPB200_ERR_ARG, "qpb200_batch_create: the dense batch path implements lin_solver = QPB200_LINSOLVE_CHOLESKY only");
+    // value checks on a strided sample would miss entries: scan everything (memory-bound, ~GB/s)
+    const size_t nP = (size_t)batch * n * n, nA = (size_t)batch * m * n;
+    if (!all_finite(P, nP)) return fail(QPB200_ERR_NONFINITE, "P has a non-finite entry");
+    if (!all_finite(A, nA)) return fail(QPB200_ERR_NONFINITE, "A has a non-finite entry");
+    if (!all_finite(q, (size_t)batch * n)) return fail(QPB200_ERR_NONFINITE, "q has a non-finite entry");
+    for (size_t i = 0; i < (size_t)batch * m; ++i)
+        if (std::isnan(l[i]) || std::isnan(u[i]) || l[i] > u[i]) return fail(QPB200_ERR_NONFINITE, "bounds: need l <= u, not NaN (entry %zu)", i);
+    int rc = check_device(s.device);
+    if (rc) return rc;
+    qpb200_batch *h = new (std::nothrow) qpb200_batch();
+    if (!h) return fail(QPB200_ERR_ARG, "out of host memory");
+    DenseBatch &B = h->b;
+#define QPB_CUDA_H(call)                                                                                     \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess) {                                                                             \
+            delete h;                                                                                        \
+            return fail(QPB200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+        }                                                                                                    \
+    } while (0)
+    QPB_CUDA_H(cudaGetDevice(&B.device));
+    B.batch = batch; B.n = (int)n; B.m = (int)m; B.mp = ((int)m + 3) & ~3;
+    B.settings = s;
+    double *dP, *dA, *dq, *dl, *du;
+    QPB_CUDA_H(B.arena.alloc(&dP, nP));
+    QPB_CUDA_H(B.arena.alloc(&dA, nA));
+    QPB_CUDA_H(B.arena.alloc(&dq, (size_t)batch * n));
+    QPB_CUDA_H(B.arena.alloc(&dl, (size_t)batch * m));
+    QPB_CUDA_H(B.arena.alloc(&du, (size_t)batch * m));
+    QPB_CUDA_H(B.arena.alloc(&B.prm.X, (size_t)batch * n));
+    QPB_CUDA_H(B.arena.alloc(&B.prm.flags, (size_t)batch));
+    QPB_CUDA_H(B.arena.alloc(&B.prm.iters, (size_t)batch));
+    QPB_CUDA_H(B.arena.alloc(&B.prm.factor_fail, 1, true));
+    QPB_CUDA_H(B.arena.alloc(&B.prm.totals, 4, true));
+    QPB_CUDA_H(B.arena.alloc(&B.prm.queue, 4, true));
+    QPB_CUDA_H(cudaStreamCreateWithFlags(&B.stream, cudaStreamNonBlocking));
+    QPB_CUDA_H(cudaEventCreate(&B.ev0));
+    QPB_CUDA_H(cudaEventCreate(&B.ev1));
+    QPB_CUDA_H(cudaMemcpyAsync(dP, P, nP * sizeof(double), cudaMemcpyHostToDevice, B.stream));
+    QPB_CUDA_H(cudaMemcpyAsync(dA, A, nA * sizeof(double), cudaMemcpyHostToDevice, B.stream));
+    QPB_CUDA_H(cudaMemcpyAsync(dq, q, (size_t)batch * n * sizeof(double), cudaMemcpyHostToDevice, B.stream));
+    QPB_CUDA_H(cudaMemcpyAsync(dl, l, (size_t)batch * m * sizeof(double), cudaMemcpyHostToDevice, B.stream));
+    QPB_CUDA_H(cudaMemcpyAsync(du, u, (size_t)batch * m * sizeof(double), cudaMemcpyHostToDevice, B.stream));
+    B.prm.batch = (int)batch; B.prm.n = B.n; B.prm.m = B.m; B.prm.mp = B.mp;
+    B.prm.P = dP; B.prm.A = dA; B.prm.q = dq; B.prm.l = dl; B.prm.u = du;
+    B.prm.blocked_chol = s.reserved_i[0] == 1 ? 0 : 1;     // reserved_i[0] = 1 selects the unblocked factor (A/B testing)
+    AdmmSettingsDev &d = B.prm.s;
+    d.max_iter = s.max_iter; d.check_every = s.check_every; d.pcg_max_iter = 0;
+    d.eps_abs = s.eps_abs; d.eps_rel = s.eps_rel; d.rho = s.rho; d.sigma = s.sigma; d.alpha = s.alpha;
+    d.rho_factor = s.rho_factor; d.pcg_eps = 0; d.pcg_rel_eps = 0; d.adaptive_rho = s.adaptive_rho;
+    B.smem = dense_smem_bytes(B.mp);
+    QPB_CUDA_H(cudaFuncSetAttribute(dense_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.smem));
+    int per_sm = 0;
+    QPB_CUDA_H(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dense_batch_kernel, kDThreads, B.smem));
+    if (per_sm < 1) { delete h; return fail(QPB200_ERR_CUDA, "dense batch kernel does not fit on an SM (smem %zu)", B.smem); }
+    cudaDeviceProp prop;
+    QPB_CUDA_H(cudaGetDeviceProperties(&prop, B.device));
+    B.grid = (int)std::min<int64_t>(batch, (int64_t)prop.multiProcessorCount * per_sm);
+    QPB_CUDA_H(cudaStreamSynchronize(B.stream));
+    B.setup_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    *out = h;
+    return QPB200_OK;
+#undef QPB_CUDA_H
+}
+
+int qpb200_batch_solve(qpb200_batch *h, double *X_inout, int32_t *flags, int64_t *iters, qpb200_info *info) {
+    if (!h || !X_inout) return fail(QPB200_ERR_ARG, "qpb200_batch_solve: NULL argument");
+    DenseBatch &B = h->b;
+    QPB_CUDA(cudaSetDevice(B.device));
+    const size_t nx = (size_t)B.batch * B.n;
+    QPB_CUDA(cudaMemcpyAsync(B.prm.X, X_inout, nx * sizeof(double), cudaMemcpyHostToDevice, B.stream));
+    QPB_CUDA(cudaMemsetAsync(B.prm.totals, 0, 4 * sizeof(unsigned long long), B.stream));
+    QPB_CUDA(cudaMemsetAsync(B.prm.factor_fail, 0, sizeof(int), B.stream));
+    QPB_CUDA(cudaMemsetAsync(B.prm.queue, 0, 4 * sizeof(unsigned int), B.stream));
+    QPB_CUDA(cudaEventRecord(B.ev0, B.stream));
+    dense_batch_kernel<<<B.grid, kDThreads, B.smem, B.stream>>>(B.prm);
+    QPB_CUDA(cudaGetLastError());
+    QPB_CUDA(cudaEventRecord(B.ev1, B.stream));
+    QPB_CUDA(cudaMemcpyAsync(X_inout, B.prm.X, nx * sizeof(double), cudaMemcpyDeviceToHost, B.stream));
+    if (flags) QPB_CUDA(cudaMemcpyAsync(flags, B.prm.flags, (size_t)B.batch * sizeof(int), cudaMemcpyDeviceToHost, B.stream));
+    if (iters) QPB_CUDA(cudaMemcpyAsync(iters, B.prm.iters, (size_t)B.batch * sizeof(long long), cudaMemcpyDeviceToHost, B.stream));
+    unsigned long long tot[4];
+    int ffail = 0;
+    QPB_CUDA(cudaMemcpyAsync(tot, B.prm.totals, sizeof(tot), cudaMemcpyDeviceToHost, B.stream));
+    QPB_CUDA(cudaMemcpyAsync(&ffail, B.prm.factor_fail, sizeof(int), cudaMemcpyDeviceToHost, B.stream));
+    QPB_CUDA(cudaStreamSynchronize(B.stream));
+    float ms = 0.f;
+    QPB_CUDA(cudaEventElapsedTime(&ms, B.ev0, B.ev1));
+    if (info) {
+        std::memset(info, 0, sizeof(*info));
+        info->conv_flag = 0;
+        info->iterations = (int64_t)tot[0];
+        info->rho_updates = (int64_t)tot[1];
+        info->rho_final = B.settings.rho;
+        info->res_prim = NAN;
+        info->res_dual = NAN;
+        info->solve_ms = ms;
+        info->setup_ms = B.setup_ms;
+        info->kernel_launches = 1;
+    }
+    if (ffail) return fail(QPB200_ERR_FACTOR, "Cholesky breakdown: a pivot of P + sigma I + rho A'A was not positive");
+    return QPB200_OK;
+}
+
+void qpb200_batch_destroy(qpb200_batch *h) { delete h; }
+
+}  // extern "C"

@@ -30,12 +30,14 @@ __global__ void gather_kernel(const int *__restrict__ idx, const double *x, doub
 }
 
 template <int ILP, int MODE>
-float run(const int *idx, const double *x, double *out, size_t n, int blocks, int threads, int reps) {
+float run(const int *idx, const double *x, double *out, size_t n, int blocks, int threads, int reps, size_t smem = 0) {
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);
-    gather_kernel<ILP, MODE><<<blocks, threads>>>(idx, x, out, n);
+    // smem > 0: an (unused) dynamic shared-memory allocation per CTA -- it shrinks the L1 data cache
+    cudaFuncSetAttribute(gather_kernel<ILP, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    gather_kernel<ILP, MODE><<<blocks, threads, smem>>>(idx, x, out, n);
     cudaEventRecord(a);
-    for (int r = 0; r < reps; ++r) gather_kernel<ILP, MODE><<<blocks, threads>>>(idx, x, out, n);
+    for (int r = 0; r < reps; ++r) gather_kernel<ILP, MODE><<<blocks, threads, smem>>>(idx, x, out, n);
     cudaEventRecord(b);
     cudaEventSynchronize(b);
     float ms; cudaEventElapsedTime(&ms, a, b);
@@ -67,6 +69,16 @@ int main(int argc, char **argv) {
                    n / (ms * 1e-3) / (sms * (double)p.clockRate * 1e3));                                   \
         }
         RUN(4, 0) RUN(8, 0) RUN(16, 0) RUN(8, 1) RUN(8, 2) RUN(8, 3) RUN(16, 1)
+    }
+    // L1 capacity vs gathers in flight: 2 CTAs x 512 threads per SM, ILP 4 / 8, with a shared-memory
+    // allocation per CTA like the SpMV kernel's (every KB of shared memory is a KB less L1)
+    printf("\n%-28s %8s %10s %12s %14s\n", "1024 thr/SM, smem/CTA", "KB", "ms", "Ggather/s", "gathers/clk/SM");
+    for (int kb : {0, 16, 33, 50, 75, 100}) {
+        const int threads = 512, blocks = sms * 2;
+        float m4 = run<4, 0>(idx, x, out, n, blocks, threads, 10, (size_t)kb * 1024);
+        float m8 = run<8, 0>(idx, x, out, n, blocks, threads, 10, (size_t)kb * 1024);
+        printf("%-28s %8d %10.4f %12.1f %14.3f\n", "ld.global ILP=4", kb, m4, n / m4 / 1e6, n / (m4 * 1e-3) / (sms * (double)p.clockRate * 1e3));
+        printf("%-28s %8d %10.4f %12.1f %14.3f\n", "ld.global ILP=8", kb, m8, n / m8 / 1e6, n / (m8 * 1e-3) / (sms * (double)p.clockRate * 1e3));
     }
     return 0;
 }
