@@ -50,9 +50,13 @@ struct CsrTiled {
 
 // Shared memory of one CTA.
 struct __align__(128) SpmvSmem {
+#ifdef QPB_SMEM_LEAN
+    double val[2][kTileCap];         // lean variant: only the two product buffers live in shared memory
+#else
     double val[kStages][kTileCap];   // TMA: staged values, overwritten in place by the products
+#endif
                                      // LDG: buffers 0/1 hold the products (ping-pong)
-#ifndef QPB_COL_LDG
+#if !defined(QPB_COL_LDG) && !defined(QPB_SMEM_LEAN)
     int col[kStages][kTileCap];      // TMA only
 #endif
     uint64_t full[kStages];          // mbarriers
@@ -167,12 +171,70 @@ __device__ __forceinline__ void spmv_tiles_ldg(const CsrTiled &M, const double *
     __syncthreads();
 }
 
+// ---- loader 1b (build variant QPB_SMEM_LEAN): register-prefetched stream, shared memory only for products ---
+// Every KB of shared memory is a KB less L1, and on B200 the random x-gathers collapse once the sectors
+// in flight exceed the L1 capacity (profiles/r1_gather_ceiling_smem_sweep.txt).  This loader keeps just two
+// product buffers in shared memory; the (col, val) stream of tile i+1 is fetched into registers (no L1
+// allocation) while the gathers of tile i are in flight.
+__device__ __forceinline__ int ldg_stream_i32(const int *p) {
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double ldg_stream_f64(const double *p) {
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
+template <bool SPLIT, class Epi>
+__device__ __forceinline__ void spmv_tiles_ldg_pf(const CsrTiled &M, const double *x, SpmvSmem &sm, Epi &epi) {
+    static_assert(kTileNnz == kThreads * kGatherBatch, "one gather batch must cover a tile");
+    const int tb = M.cta_begin[blockIdx.x], te = M.cta_begin[blockIdx.x + 1];
+    const int nt = te - tb;
+    int4 td_next = nt > 0 ? __ldg(M.tiles + tb) : make_int4(0, 0, 0, 0);
+    int cn[kGatherBatch];
+    double vn[kGatherBatch];
+    auto fetch = [&](const int4 &tdi) {
+        const int nk = tdi.w & kTileNkMask;
+#pragma unroll
+        for (int j = 0; j < kGatherBatch; ++j) {
+            const int k = threadIdx.x + j * kThreads;
+            cn[j] = (k < nk) ? ldg_stream_i32(M.col + tdi.z + k) : 0;
+            vn[j] = (k < nk) ? ldg_stream_f64(M.val + tdi.z + k) : 0.0;
+        }
+    };
+    if (nt > 0) fetch(td_next);
+    for (int i = 0; i < nt; ++i) {
+        const int4 td = td_next;
+        if (i + 1 < nt) td_next = __ldg(M.tiles + tb + i + 1);
+        const int nk = td.w & kTileNkMask;
+        double *prod = sm.val[i & 1];
+        const RowPre pre = prefetch_rowptr<SPLIT>(M, td);
+        double v[kGatherBatch], xv[kGatherBatch];
+#pragma unroll
+        for (int j = 0; j < kGatherBatch; ++j) {
+            v[j] = vn[j];
+            xv[j] = (threadIdx.x + j * kThreads < nk) ? x[cn[j]] : 0.0;   // independent gathers in flight
+        }
+        if (i + 1 < nt) fetch(td_next);                                    // stream of the next tile, behind the gathers
+#pragma unroll
+        for (int j = 0; j < kGatherBatch; ++j) {
+            const int k = threadIdx.x + j * kThreads;
+            if (k < nk) prod[k] = v[j] * xv[j];
+        }
+        __syncthreads();
+        tile_row_sums<SPLIT>(M, td, prod, sm, pre, epi);
+    }
+    __syncthreads();
+}
+
 // ---- loader 2: TMA bulk-copy staged tiles ------------------------------------------------------
 __device__ __forceinline__ void tma_issue_tile(const CsrTiled &M, const int4 td, SpmvSmem &sm, int stage) {
     const int k0 = td.z, nk = td.w & kTileNkMask;
     const int k0a = k0 & ~3;                            // 16-byte aligned start for both arrays
     const int cnt = ((k0 + nk - k0a) + 3) & ~3;         // <= kTileNnz + 6
-#ifndef QPB_COL_LDG
+#if !defined(QPB_COL_LDG) && !defined(QPB_SMEM_LEAN)
     mbar_expect_tx(&sm.full[stage], static_cast<uint32_t>(cnt) * 12u);
     tma_load_1d(sm.val[stage], M.val + k0a, static_cast<uint32_t>(cnt) * 8u, &sm.full[stage]);
     tma_load_1d(sm.col[stage], M.col + k0a, static_cast<uint32_t>(cnt) * 4u, &sm.full[stage]);
@@ -355,9 +417,13 @@ __device__ __forceinline__ void spmv_tiles_tma_pipe(const CsrTiled &M, const dou
 // LOADER: 0 = coalesced LDG, 1 = TMA staged, 2 = TMA staged + software pipelined gathers
 template <int LOADER, bool SPLIT, class Epi>
 __device__ __forceinline__ void spmv_tiles(const CsrTiled &M, const double *x, SpmvSmem &sm, PipeState &ps, Epi &epi) {
+#ifdef QPB_SMEM_LEAN
+    spmv_tiles_ldg_pf<SPLIT>(M, x, sm, epi);
+#else
     if (LOADER == 2) spmv_tiles_tma_pipe<SPLIT>(M, x, sm, ps, epi);
     else if (LOADER == 1) spmv_tiles_tma<SPLIT>(M, x, sm, ps, epi);
     else spmv_tiles_ldg<SPLIT>(M, x, sm, epi);
+#endif
 }
 
 __device__ __forceinline__ void spmv_smem_init(SpmvSmem &sm, PipeState &ps) {
