@@ -58,7 +58,7 @@ __device__ __forceinline__ double clamp_julia(double x, double lo, double hi) {
 //   mode 0: y[rows] = M x            mode 1 (split): y0 = M[:, :split] x[:split], y1 = M[:, split:] x[split:]
 // =============================================================================================
 template <int TMA, bool SPLIT>
-__global__ void __launch_bounds__(kThreads, 2) spmv_kernel(CsrTiled M, const double *x, double *y0, double *y1) {
+__global__ void __launch_bounds__(kThreads, kMinCtas) spmv_kernel(CsrTiled M, const double *x, double *y0, double *y1) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SpmvSmem &sm = *reinterpret_cast<SpmvSmem *>(smem_raw);
     PipeState ps;
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(kThreads, 2) spmv_kernel(CsrTiled M, const dou
 // from bit-identical all-reduced values, so control flow is uniform across the grid.
 // =============================================================================================
 template <int TMA, bool PRE>
-__global__ void __launch_bounds__(kThreads, 2) admm_kernel(SparseProblemDev p) {
+__global__ void __launch_bounds__(kThreads, kMinCtas) admm_kernel(SparseProblemDev p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SpmvSmem &sm = *reinterpret_cast<SpmvSmem *>(smem_raw);
     PipeState ps;

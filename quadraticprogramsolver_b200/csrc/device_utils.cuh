@@ -6,7 +6,14 @@
 
 namespace qpb {
 
-constexpr int kThreads = 512;   // threads per CTA of every sparse-path kernel
+#ifndef QPB_THREADS
+#define QPB_THREADS 512
+#endif
+#ifndef QPB_MIN_CTAS
+#define QPB_MIN_CTAS 2
+#endif
+constexpr int kThreads = QPB_THREADS;   // threads per CTA of every sparse-path kernel (build-time tunable)
+constexpr int kMinCtas = QPB_MIN_CTAS;  // __launch_bounds__ minimum resident CTAs per SM
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxRed = 8;      // widest fused reduction (values per barrier)
 

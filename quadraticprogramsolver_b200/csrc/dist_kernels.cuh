@@ -36,7 +36,7 @@ struct DistBuffers {
 };
 
 template <int TMA, bool PRE>
-__global__ void __launch_bounds__(kThreads, 2) admm_dist_kernel(SparseProblemDev p, DistBuffers d, int seg, int do_check) {
+__global__ void __launch_bounds__(kThreads, kMinCtas) admm_dist_kernel(SparseProblemDev p, DistBuffers d, int seg, int do_check) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SpmvSmem &sm = *reinterpret_cast<SpmvSmem *>(smem_raw);
     PipeState ps;
