@@ -7,10 +7,10 @@
 namespace qpb {
 
 #ifndef QPB_THREADS
-#define QPB_THREADS 512
+#define QPB_THREADS 256
 #endif
 #ifndef QPB_MIN_CTAS
-#define QPB_MIN_CTAS 2
+#define QPB_MIN_CTAS 4
 #endif
 constexpr int kThreads = QPB_THREADS;   // threads per CTA of every sparse-path kernel (build-time tunable)
 constexpr int kMinCtas = QPB_MIN_CTAS;  // __launch_bounds__ minimum resident CTAs per SM

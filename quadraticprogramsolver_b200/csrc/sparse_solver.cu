@@ -183,7 +183,7 @@ int SparseSolver::init(int64_t n64, int64_t m64, const int64_t *Pp, const int64_
     if (per_sm < 1) return fail(QPB200_ERR_CUDA, "persistent kernel does not fit on an SM");
     {
         const char *e = getenv("QPB200_CTAS_PER_SM");   // A/B experiments only
-        per_sm = std::min(per_sm, e ? std::max(1, atoi(e)) : 2);
+        per_sm = std::min(per_sm, e ? std::max(1, atoi(e)) : kMinCtas);
     }
     const int grid_max = num_sms * per_sm;
 

@@ -20,7 +20,7 @@
 namespace qpb {
 
 #ifndef QPB_TILE_NNZ
-#define QPB_TILE_NNZ 2048
+#define QPB_TILE_NNZ 1024
 #endif
 #ifndef QPB_STAGES
 #define QPB_STAGES 3
