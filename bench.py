@@ -104,6 +104,10 @@ def make_workload(name, scale):
     if name == "cfg5":
         P, q, A, l, u = problems.config_cfg5(seed=1234, scale=scale)
         desc = f"cfg5 sparse QP n={P.shape[0]} m={A.shape[0]} nnz(P)={P.nnz} nnz(A)={A.nnz} (randomQp recipe, d=5/n, feasible bounds)"
+    elif name == "cfg4":
+        P, q, A, l, u = problems.config_cfg4(seed=1234, scale=scale)
+        desc = (f"cfg4 constrained least squares (README form) as QP: n={P.shape[0]} m={A.shape[0]} nnz(P=A'A)={P.nnz} "
+                f"nnz([B;D])={A.nnz}; A_ls {4 * P.shape[0]}x{P.shape[0]}, B {P.shape[0] // 2} rows (<= c), D {P.shape[0] // 10} rows (= e), 5 nnz/row")
     elif name == "cfg2":
         P, q, A, l, u = problems.config_cfg2(seed=1234)
         desc = f"cfg2 sparse QP n={P.shape[0]} m={A.shape[0]} nnz(P)={P.nnz} nnz(A)={A.nnz} (d=1e-3, feasible bounds)"
@@ -419,7 +423,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg5", choices=["cfg5", "cfg2", "cfg3"])
+    ap.add_argument("--workload", default="cfg5", choices=["cfg5", "cfg2", "cfg3", "cfg4"])
     ap.add_argument("--batch", type=int, default=65536, help="cfg3 batch size")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink cfg5 (tests only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")

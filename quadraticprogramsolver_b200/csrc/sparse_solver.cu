@@ -194,6 +194,7 @@ int SparseSolver::init(int64_t n64, int64_t m64, const int64_t *Pp, const int64_
     int64_t want = std::max<int64_t>((int64_t)std::max(TH.tiles.size(), TA.tiles.size()),
                                      ((int64_t)std::max(n, m) + kThreads * 4 - 1) / (kThreads * 4));
     grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid_max, want));
+    if (const char *e = getenv("QPB200_GRID")) grid = std::max(1, std::min(grid_max, atoi(e)));   // A/B experiments only
     assign_tiles(TH, grid);
     assign_tiles(TA, grid);
 
