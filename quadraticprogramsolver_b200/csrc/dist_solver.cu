@@ -8,8 +8,9 @@
 #include <cmath>
 #include <cstring>
 #include <new>
+#include <vector>
 
-#include "dist_kernels.cuh"
+#include "peer_kernels.cuh"
 #include "host_common.h"
 #include "sparse_solver.h"
 
@@ -21,6 +22,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
 
@@ -40,7 +42,8 @@ static NcclApi *nccl_api() {
     api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.lib, "ncclCommDestroy");
     api.AllReduce = (decltype(api.AllReduce))dlsym(api.lib, "ncclAllReduce");
     api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.lib, "ncclGetErrorString");
-    if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllReduce || !api.GetErrorString) {
+    api.AllGather = (decltype(api.AllGather))dlsym(api.lib, "ncclAllGather");
+    if (!api.AllGather || !api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllReduce || !api.GetErrorString) {
         dlclose(api.lib);
         api.lib = nullptr;
         return nullptr;
@@ -62,6 +65,13 @@ struct DistContext {
     DistState *host_state = nullptr;   // pinned mirror (2 slots: the CG loop runs one step ahead of the host)
     cudaEvent_t ev[2] = {nullptr, nullptr};
     long long launches = 0, allreduces = 0;
+    // in-kernel peer-memory path (peer_kernels.cuh)
+    bool peer_ok = false;
+    PeerDev peer{};
+    double *region = nullptr;              // this rank's peer-visible allocation (not in the arena: IPC-exported)
+    void *opened[kMaxPeers] = {nullptr};   // cudaIpcOpenMemHandle results
+    size_t region_doubles = 0;
+    double *tiny = nullptr;                // 1 double for the host-level rendezvous all-reduce
 };
 
 void dist_destroy(DistContext *d) {
@@ -70,6 +80,8 @@ void dist_destroy(DistContext *d) {
     if (d->comm && api) api->CommDestroy(d->comm);
     if (d->host_state) cudaFreeHost(d->host_state);
     for (auto &e : d->ev) if (e) cudaEventDestroy(e);
+    for (void *o : d->opened) if (o) cudaIpcCloseMemHandle(o);
+    if (d->region) cudaFree(d->region);
     delete d;
 }
 
@@ -182,6 +194,8 @@ int dist_solve(SparseSolver &s, DistContext &d, double *x_inout, double *z_out, 
     return QPB200_OK;
 }
 
+static int peer_init(SparseSolver &s, DistContext &d);
+
 int dist_init(SparseSolver &s, DistContext *&out, int rank, int nranks, const void *unique_id) {
     NcclApi *api = nccl_api();
     if (!api) return fail(QPB200_ERR_NCCL, "libnccl.so.2 could not be loaded (dlopen)");
@@ -215,6 +229,132 @@ int dist_init(SparseSolver &s, DistContext *&out, int rank, int nranks, const vo
     QPB_NCCL(api->AllReduce(s.prob.dP, const_cast<double *>(s.prob.dP), (size_t)s.n, ncclDouble, ncclSum, d->comm, s.stream));
     QPB_NCCL(api->AllReduce(s.prob.dAA, const_cast<double *>(s.prob.dAA), (size_t)s.n, ncclDouble, ncclSum, d->comm, s.stream));
     QPB_CUDA(cudaStreamSynchronize(s.stream));
+    // collective choice (settings.reserved_i[1]): 0 = in-kernel peer-memory all-reduce when the GPUs can map each
+    // other's memory, else NCCL; 1 = NCCL + host-driven segments; 2 = peer path required
+    const int mode = s.settings.reserved_i[1];
+    if (mode != 1) {
+        const int prc = peer_init(s, *d);
+        if (prc != QPB200_OK && mode == 2) return prc;
+        // all ranks must agree: use the peer path only if every rank could map every peer
+        double ok = d->peer_ok ? 1.0 : 0.0, *dok = nullptr;
+        QPB_CUDA(s.arena.alloc(&dok, 2, true));
+        QPB_CUDA(cudaMemcpyAsync(dok, &ok, sizeof(double), cudaMemcpyHostToDevice, s.stream));
+        QPB_NCCL(api->AllReduce(dok, dok, 1, ncclDouble, ncclMin, d->comm, s.stream));
+        QPB_CUDA(cudaMemcpyAsync(&ok, dok, sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+        QPB_CUDA(cudaStreamSynchronize(s.stream));
+        d->peer_ok = ok > 0.5;
+        if (!d->peer_ok && mode == 2) return fail(QPB200_ERR_CUDA, "peer-memory path requested but not available on every rank");
+    }
+    return QPB200_OK;
+}
+
+
+// ---- in-kernel peer-memory path --------------------------------------------------------------------
+static int peer_init(SparseSolver &s, DistContext &d) {
+    NcclApi *api = nccl_api();
+    if (d.nranks > kMaxPeers) return QPB200_OK;      // stays on the NCCL path
+    const size_t n = (size_t)s.n;
+    auto up = [](size_t v) { return (v + 15) & ~size_t(15); };
+    PeerDev &pd = d.peer;
+    pd.rank = d.rank;
+    pd.nranks = d.nranks;
+    size_t off = 0;
+    pd.off_flags = (long long)off; off += 16;
+    pd.off_lmax = (long long)off; off += up(4 * (size_t)kMaxPeers);
+    pd.off_wpart = (long long)off; off += up(n);
+    pd.off_wred = (long long)off; off += up(n);
+    pd.off_w2part = (long long)off; off += up(2 * n);
+    pd.off_w2red = (long long)off; off += up(2 * n);
+    d.region_doubles = off;
+    QPB_CUDA(cudaMalloc(&d.region, off * sizeof(double)));
+    QPB_CUDA(cudaMemset(d.region, 0, off * sizeof(double)));
+    // exchange the IPC handles through the NCCL communicator we already have
+    cudaIpcMemHandle_t mine;
+    QPB_CUDA(cudaIpcGetMemHandle(&mine, d.region));
+    unsigned char *hbuf = nullptr;
+    const size_t hsz = sizeof(cudaIpcMemHandle_t);
+    QPB_CUDA(s.arena.alloc(&hbuf, hsz * d.nranks, true));
+    QPB_CUDA(cudaMemcpyAsync(hbuf + hsz * d.rank, &mine, hsz, cudaMemcpyHostToDevice, s.stream));
+    QPB_NCCL(api->AllGather(hbuf + hsz * d.rank, hbuf, hsz, ncclChar, d.comm, s.stream));
+    std::vector<cudaIpcMemHandle_t> all((size_t)d.nranks);
+    QPB_CUDA(cudaMemcpyAsync(all.data(), hbuf, hsz * d.nranks, cudaMemcpyDeviceToHost, s.stream));
+    QPB_CUDA(cudaStreamSynchronize(s.stream));
+    for (int q = 0; q < d.nranks; ++q) {
+        if (q == d.rank) {
+            pd.region[q] = d.region;
+            continue;
+        }
+        void *ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, all[(size_t)q], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(QPB200_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s -- peer path unavailable", q, cudaGetErrorString(e));
+        }
+        d.opened[q] = ptr;
+        pd.region[q] = static_cast<double *>(ptr);
+    }
+    pd.info = s.prob.info;
+    QPB_CUDA(s.arena.alloc(&d.tiny, 2, true));
+    for (const void *fn : {(const void *)admm_peer_kernel<0, false>, (const void *)admm_peer_kernel<0, true>,
+                           (const void *)admm_peer_kernel<1, false>, (const void *)admm_peer_kernel<1, true>,
+                           (const void *)admm_peer_kernel<2, false>, (const void *)admm_peer_kernel<2, true>}) {
+        QPB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpmvSmem)));
+        int per_sm = 0;
+        QPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, sizeof(SpmvSmem)));
+        if (per_sm * s.num_sms < s.grid)
+            return fail(QPB200_ERR_CUDA, "peer kernel cannot be co-resident at grid %d (%d per SM)", s.grid, per_sm);
+    }
+    d.peer_ok = true;
+    return QPB200_OK;
+}
+
+int peer_solve(SparseSolver &s, DistContext &d, double *x_inout, double *z_out, double *y_out, qpb200_info *info) {
+    NcclApi *api = nccl_api();
+    if (!x_inout) return fail(QPB200_ERR_ARG, "qpb200_dist_solve: x_inout is NULL");
+    QPB_CUDA(cudaSetDevice(s.device));
+    const int n = s.n, m = s.m;
+    int rc = s.reset_state(x_inout);
+    if (rc) return rc;
+    // epoch flags back to zero, then a host-level rendezvous: nobody launches before everybody has reset
+    QPB_CUDA(cudaMemsetAsync(d.region, 0, (size_t)(d.peer.off_wpart) * sizeof(double), s.stream));
+    QPB_NCCL(api->AllReduce(d.tiny, d.tiny, 1, ncclDouble, ncclSum, d.comm, s.stream));
+    QPB_CUDA(cudaStreamSynchronize(s.stream));
+    QPB_CUDA(cudaEventRecord(s.ev0, s.stream));
+    {
+        void *args[] = {(void *)&s.prob, (void *)&d.peer};
+        const void *fns[3][2] = {{(const void *)admm_peer_kernel<0, false>, (const void *)admm_peer_kernel<0, true>},
+                                 {(const void *)admm_peer_kernel<1, false>, (const void *)admm_peer_kernel<1, true>},
+                                 {(const void *)admm_peer_kernel<2, false>, (const void *)admm_peer_kernel<2, true>}};
+        QPB_CUDA(cudaLaunchCooperativeKernel(fns[s.loader][s.use_pre ? 1 : 0], dim3(s.grid), dim3(kThreads), args,
+                                             sizeof(SpmvSmem), s.stream));
+    }
+    QPB_CUDA(cudaEventRecord(s.ev1, s.stream));
+    QPB_CUDA(cudaMemcpyAsync(x_inout, s.prob.XY, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    if (z_out && m) QPB_CUDA(cudaMemcpyAsync(z_out, s.prob.z, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    if (y_out && m) QPB_CUDA(cudaMemcpyAsync(y_out, s.prob.XY + n, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    AdmmInfoDev hi;
+    QPB_CUDA(cudaMemcpyAsync(&hi, s.prob.info, sizeof(hi), cudaMemcpyDeviceToHost, s.stream));
+    QPB_CUDA(cudaStreamSynchronize(s.stream));
+    // nobody tears its buffers down (or starts the next solve) while a peer may still be reading them
+    QPB_NCCL(api->AllReduce(d.tiny, d.tiny, 1, ncclDouble, ncclSum, d.comm, s.stream));
+    QPB_CUDA(cudaStreamSynchronize(s.stream));
+    float ms = 0.f;
+    QPB_CUDA(cudaEventElapsedTime(&ms, s.ev0, s.ev1));
+    s.last_info = hi;
+    if (info) {
+        std::memset(info, 0, sizeof(*info));
+        info->conv_flag = hi.conv_flag;
+        info->iterations = hi.iterations;
+        info->rho_final = hi.rho_final;
+        info->res_prim = hi.res_prim;
+        info->res_dual = hi.res_dual;
+        info->rho_updates = hi.rho_updates;
+        info->pcg_iters_total = hi.pcg_iters_total;
+        info->pcg_maxed = hi.pcg_maxed;
+        info->solve_ms = ms;
+        info->setup_ms = s.setup_ms;
+        info->kernel_launches = 1;
+    }
     return QPB200_OK;
 }
 
@@ -257,6 +397,7 @@ int qpb200_dist_create(qpb200_handle **out, int32_t rank, int32_t nranks, const 
 
 int qpb200_dist_solve(qpb200_handle *h, double *x_inout, double *z_out, double *y_out, qpb200_info *info) {
     if (!h || !h->dist) return fail(QPB200_ERR_ARG, "qpb200_dist_solve: not a distributed handle");
+    if (h->dist->peer_ok) return peer_solve(h->solver, *h->dist, x_inout, z_out, y_out, info);
     return dist_solve(h->solver, *h->dist, x_inout, z_out, y_out, info);
 }
 

@@ -1,0 +1,313 @@
+// peer_kernels.cuh -- ONE persistent kernel per GPU for a QP row-partitioned over R GPUs: the SpMV passes,
+// the vector updates AND the all-reduces run inside the same cooperative launch; the collectives are
+// plain loads/stores on NVLink peer memory (cudaIpc-mapped), with no NCCL call and no host round trip in
+// the loop.  (dist_kernels.cuh + ncclAllReduce is the baseline this replaces.)
+//
+// Operator split (same as dist_kernels.cuh): rank r owns rows I_r of A and columns J_r of P,
+//     K u = sum_r H_r [u ; rho A_r u] + sigma u,   H_r = [P[:, J_r]  A_r'].
+// In-kernel all-reduce of an n-vector ("two-shot", deterministic):
+//   1. every rank writes its partial H_r v into its own peer-visible buffer      -> system barrier
+//   2. rank r sums slice r of all R partials in rank order (remote reads over NVLink) and PUSHES the sums
+//      into every rank's result buffer (remote writes)                                 -> system barrier
+// Every element is reduced by exactly one rank, so all ranks receive bit-identical vectors and branch
+// identically.  The system barrier is the grid barrier whose last-arriving CTA exchanges an epoch flag with
+// the peers (st.release.sys / ld.acquire.sys on peer memory) before releasing the local CTAs.
+// One process per GPU launches its kernel at the same time; kernels on DIFFERENT GPUs spin on each other,
+// never kernels sharing a GPU.
+#pragma once
+#include "dist_kernels.cuh"
+
+namespace qpb {
+
+constexpr int kMaxPeers = 8;
+
+struct PeerDev {
+    int rank, nranks;
+    double *region[kMaxPeers];       // peer-visible region of every rank (own entry = local pointer)
+    // offsets in doubles inside a region
+    long long off_wpart, off_wred;   // n each
+    long long off_w2part, off_w2red; // 2n each
+    long long off_lmax;              // nranks * 4
+    long long off_flags;             // kMaxPeers unsigned long long
+    AdmmInfoDev *info;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+struct XState {
+    unsigned long long xepoch;
+};
+
+// grid barrier + cross-GPU barrier in one: only the last-arriving CTA talks to the peers
+__device__ __forceinline__ void sys_barrier(const GridSync &gs, SyncState &st, const PeerDev &pd, XState &xs) {
+    st.epoch += 1;
+    xs.xepoch += 1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();   // this CTA's writes, including stores to peer memory
+        const unsigned long long old = atomicAdd(gs.count, 1ULL);
+        if (old == st.epoch * gridDim.x - 1ULL) {
+            __threadfence_system();
+            for (int q = 0; q < pd.nranks; ++q)
+                if (q != pd.rank)
+                    st_release_sys(reinterpret_cast<unsigned long long *>(pd.region[q] + pd.off_flags) + pd.rank, xs.xepoch);
+            const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(pd.region[pd.rank] + pd.off_flags);
+            const long long t0 = clock64();
+            for (int q = 0; q < pd.nranks; ++q) {
+                if (q == pd.rank) continue;
+                while (ld_acquire_sys(mine + q) < xs.xepoch) {
+                    if (clock64() - t0 > 60000000000LL) __trap();   // ~30 s: a peer is gone; fail loudly, do not hang
+                }
+            }
+            __threadfence_system();
+            st_release_gpu(gs.flag, st.epoch);
+        } else {
+            while (ld_acquire_gpu(gs.flag) < st.epoch) {
+            }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// all-reduce(sum) of `len` doubles: partial at off_part in every region -> result at off_red in every region
+__device__ __forceinline__ void peer_allreduce(const GridSync &gs, SyncState &st, const PeerDev &pd, XState &xs,
+                                               long long off_part, long long off_red, int len) {
+    sys_barrier(gs, st, pd, xs);                      // all partials written and visible
+    const int R = pd.nranks;
+    const int j0 = (int)((long long)len * pd.rank / R), j1 = (int)((long long)len * (pd.rank + 1) / R);
+    for (int j = j0 + blockIdx.x * kThreads + threadIdx.x; j < j1; j += gridDim.x * kThreads) {
+        double s = 0.0;
+        for (int q = 0; q < R; ++q) s += pd.region[q][off_part + j];    // rank order: deterministic
+        for (int q = 0; q < R; ++q) pd.region[q][off_red + j] = s;       // push to everyone (incl. self)
+    }
+    sys_barrier(gs, st, pd, xs);                      // all slices delivered everywhere
+}
+
+// all-reduce(max) of 4 doubles per rank: every rank pushes its 4 values into slot `rank` of every region
+__device__ __forceinline__ void peer_allmax4(const GridSync &gs, SyncState &st, const PeerDev &pd, XState &xs, double (&v)[4]) {
+    if (blockIdx.x == 0 && threadIdx.x < 4)
+        for (int q = 0; q < pd.nranks; ++q) pd.region[q][pd.off_lmax + 4 * pd.rank + threadIdx.x] = v[threadIdx.x];
+    sys_barrier(gs, st, pd, xs);
+    const double *slots = pd.region[pd.rank] + pd.off_lmax;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        double x = 0.0;
+        for (int q = 0; q < pd.nranks; ++q) x = nanmax(x, __ldcg(slots + 4 * q + i));
+        v[i] = x;
+    }
+}
+
+template <int TMA, bool PRE>
+__global__ void __launch_bounds__(kThreads, kMinCtas) admm_peer_kernel(SparseProblemDev p, PeerDev pd) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SpmvSmem &sm = *reinterpret_cast<SpmvSmem *>(smem_raw);
+    PipeState ps;
+    spmv_smem_init(sm, ps);
+    SyncState st;
+    st.epoch = 0;
+    XState xs;
+    xs.xepoch = 0;
+
+    const int n = p.n, m = p.m;
+    const int gtid = blockIdx.x * kThreads + threadIdx.x;
+    const int gstride = gridDim.x * kThreads;
+    double *const x = p.XY, *const y = p.XY + n;
+    double *const xt = p.XG, *const g = p.XG + n;
+    double *const u = p.UT, *const t = p.UT + n;
+    double *const zpv = PRE ? p.zp : p.r;
+    double *const wpart = pd.region[pd.rank] + pd.off_wpart;
+    const double *const wred = pd.region[pd.rank] + pd.off_wred;
+    double *const w2part = pd.region[pd.rank] + pd.off_w2part;
+    const double *const w2red = pd.region[pd.rank] + pd.off_w2red;
+
+    double rho = p.s.rho, rho1 = 1.0 / rho;
+    const double alpha = p.s.alpha, alpha1 = 1.0 - alpha;
+    const double sigma = p.s.sigma;
+    const double eps_admm = fmin(p.s.eps_abs, p.s.eps_rel) * 1e-2;
+    double rhorho = rho;
+    int conv_flag = 1;
+    long long rho_updates = 0, pcg_total = 0, pcg_maxed = 0, n_h = 0, n_a = 0;
+    double res_prim = nan(""), res_dual = nan("");
+    bool dinv_ready = false;
+
+    auto spmv_A_t = [&]() {      // t = rho * A_r u
+        auto epi = [&](int i, double s0, double) { t[i] = rho * s0; };
+        spmv_tiles<TMA, false>(p.A, u, sm, ps, epi);
+        ++n_a;
+    };
+    auto spmv_H_partial = [&](const double *pair) {   // wpart = H_r * pair
+        auto epi = [&](int j, double s0, double) { wpart[j] = s0; };
+        spmv_tiles<TMA, false>(p.H, pair, sm, ps, epi);
+        ++n_h;
+    };
+
+    long long ii = 0;
+    for (ii = 1; ii <= p.s.max_iter; ++ii) {
+        bool changed = false;
+        if (p.s.adaptive_rho && ((rhorho * p.s.rho_factor < rho) || (rhorho > p.s.rho_factor * rho))) {
+            rho = rhorho;
+            rho1 = 1.0 / rho;
+            changed = true;
+            ++rho_updates;
+        }
+        if (changed || !dinv_ready) {
+            if (PRE)
+                for (int j = gtid; j < n; j += gstride) p.dinv[j] = 1.0 / (p.dP[j] + sigma + rho * p.dAA[j]);
+            if (changed)
+                for (int i = gtid; i < m; i += gstride) g[i] = rho * (p.zt[i] - p.z[i]) + y[i];
+            dinv_ready = true;
+            grid_barrier(p.gs, st);
+        }
+        // ---- r0 = sigma (x - x~) - q - sum_r H_r [x~ ; g_r]
+        spmv_H_partial(p.XG);
+        peer_allreduce(p.gs, st, pd, xs, pd.off_wpart, pd.off_wred, n);
+        double acc[2] = {0.0, 0.0};
+        for (int j = gtid; j < n; j += gstride) {
+            const double rj = sigma * (x[j] - xt[j]) - p.q[j] - wred[j];
+            p.r[j] = rj;
+            const double zj = PRE ? p.dinv[j] * rj : rj;
+            if (PRE) p.zp[j] = zj;
+            u[j] = zj;
+            acc[0] += rj * rj;
+            acc[1] += rj * zj;
+        }
+        grid_barrier_reduce<2, false>(p.gs, st, acc, sm.red, sm.bcast);
+        double residual = sqrt(acc[0]);
+        double rz = acc[1];
+        const double tol = fmax(p.s.pcg_rel_eps * residual, p.s.pcg_eps);
+        long long k = 0;
+        while (k < p.s.pcg_max_iter && !(residual <= tol)) {
+            spmv_A_t();
+            grid_barrier(p.gs, st);
+            spmv_H_partial(p.UT);
+            peer_allreduce(p.gs, st, pd, xs, pd.off_wpart, pd.off_wred, n);
+            double uc[1] = {0.0};
+            for (int j = gtid; j < n; j += gstride) {
+                const double uj = u[j];
+                const double cj = wred[j] + sigma * uj;
+                p.c[j] = cj;
+                uc[0] += uj * cj;
+            }
+            grid_barrier_reduce<1, false>(p.gs, st, uc, sm.red, sm.bcast);
+            if (!(uc[0] > 0.0)) break;
+            const double a_cg = rz / uc[0];
+            double acc2[2] = {0.0, 0.0};
+            for (int j = gtid; j < n; j += gstride) {
+                xt[j] += a_cg * u[j];
+                const double rj = p.r[j] - a_cg * p.c[j];
+                p.r[j] = rj;
+                const double zj = PRE ? p.dinv[j] * rj : rj;
+                if (PRE) p.zp[j] = zj;
+                acc2[0] += rj * rj;
+                acc2[1] += rj * zj;
+            }
+            grid_barrier_reduce<2, false>(p.gs, st, acc2, sm.red, sm.bcast);
+            residual = sqrt(acc2[0]);
+            const double rz_new = acc2[1];
+            ++k;
+            if (k < p.s.pcg_max_iter && !(residual <= tol)) {
+                const double beta = rz_new / rz;
+                for (int j = gtid; j < n; j += gstride) u[j] = zpv[j] + beta * u[j];
+                grid_barrier(p.gs, st);
+            }
+            rz = rz_new;
+        }
+        pcg_total += k;
+        if (k >= p.s.pcg_max_iter && !(residual <= tol)) ++pcg_maxed;
+
+        // ---- z~ = A_r x~ with relaxation / clip / dual update on the local rows; x update (replicated)
+        const bool do_check = (ii % p.s.check_every) == 0;
+        double nrm[4] = {0.0, 0.0, 0.0, 0.0};     // dx, dz, |Ax - z|, max(|Ax|, |z|)
+        {
+            auto epi = [&](int i, double s0, double) {
+                const double zt_i = s0;
+                const double z_old = p.z[i], y_old = y[i];
+                const double zr = alpha * zt_i + alpha1 * z_old;
+                const double z_new = clamp_julia(zr + rho1 * y_old, p.l[i], p.u[i]);
+                const double y_new = y_old + rho * (zr - z_new);
+                p.z[i] = z_new;
+                y[i] = y_new;
+                p.zt[i] = zt_i;
+                g[i] = rho * (zt_i - z_new) + y_new;
+                nrm[1] = nanmax(nrm[1], fabs(z_new - z_old));
+            };
+            spmv_tiles<TMA, false>(p.A, xt, sm, ps, epi);
+            ++n_a;
+        }
+        for (int j = gtid; j < n; j += gstride) {
+            const double x_old = x[j];
+            const double x_new = alpha * xt[j] + alpha1 * x_old;
+            x[j] = x_new;
+            nrm[0] = nanmax(nrm[0], fabs(x_new - x_old));
+        }
+        grid_barrier(p.gs, st);
+        if (do_check) {
+            {
+                auto epi = [&](int i, double s0, double) {
+                    const double zi = p.z[i];
+                    nrm[2] = nanmax(nrm[2], fabs(s0 - zi));
+                    nrm[3] = nanmax(nrm[3], fabs(s0));
+                    nrm[3] = nanmax(nrm[3], fabs(zi));
+                };
+                spmv_tiles<TMA, false>(p.A, x, sm, ps, epi);
+                ++n_a;
+            }
+            {
+                auto epi = [&](int j, double s0, double s1) {
+                    w2part[j] = s0;
+                    w2part[n + j] = s1;
+                };
+                spmv_tiles<TMA, true>(p.H, p.XY, sm, ps, epi);
+                ++n_h;
+            }
+            grid_barrier_reduce<4, true>(p.gs, st, nrm, sm.red, sm.bcast);   // local maxima (identical in all CTAs)
+            peer_allmax4(p.gs, st, pd, xs, nrm);
+            peer_allreduce(p.gs, st, pd, xs, pd.off_w2part, pd.off_w2red, 2 * n);
+            double nd[2] = {0.0, 0.0};
+            for (int j = gtid; j < n; j += gstride) {
+                const double px = w2red[j], aty = w2red[n + j];
+                nd[0] = nanmax(nd[0], fabs(px + p.q[j] + aty));
+                nd[1] = nanmax(nd[1], fabs(px));
+                nd[1] = nanmax(nd[1], fabs(aty));
+            }
+            grid_barrier_reduce<2, true>(p.gs, st, nd, sm.red, sm.bcast);
+            const double dx = nrm[0], dz = nrm[1];
+            res_prim = nrm[2];
+            res_dual = nd[0];
+            const double max_prim = nrm[3];
+            const double max_dual = nanmax(nd[1], p.normQ);
+            if (p.s.adaptive_rho) {
+                const double num = res_prim * max_dual, den = res_dual * max_prim;
+                rhorho = clamp_julia(rho * sqrt(num / den), 1e-3, 1e6);
+            }
+            if ((res_prim < p.s.eps_abs + p.s.eps_rel * max_prim) && (res_dual < p.s.eps_abs + p.s.eps_rel * max_dual)) conv_flag = 3;
+            if ((dx <= eps_admm) && (dz <= eps_admm)) conv_flag = 2;
+            if (conv_flag != 1) break;
+        }
+    }
+    if (ii > p.s.max_iter) ii = p.s.max_iter;
+
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        AdmmInfoDev &o = *pd.info;
+        o.conv_flag = conv_flag;
+        o.iterations = ii;
+        o.rho_final = rho;
+        o.res_prim = res_prim;
+        o.res_dual = res_dual;
+        o.rho_updates = rho_updates;
+        o.pcg_iters_total = pcg_total;
+        o.pcg_maxed = pcg_maxed;
+        o.n_h_passes = n_h;
+        o.n_a_passes = n_a;
+    }
+}
+
+}  // namespace qpb

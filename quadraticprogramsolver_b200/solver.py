@@ -295,7 +295,11 @@ class QPB200DistSolver:
         vQ = np.ascontiguousarray(vQ, dtype=np.float64)
         l_r = np.ascontiguousarray(l_r, dtype=np.float64); u_r = np.ascontiguousarray(u_r, dtype=np.float64)
         kw.setdefault("device", torch.cuda.current_device() if torch.cuda.is_available() else -1)
+        # collective: "auto" = in-kernel all-reduce over NVLink peer memory when available, else NCCL;
+        # "nccl" = host-driven segments + ncclAllReduce; "peer" = peer path required
+        dist_mode = {"auto": 0, "nccl": 1, "peer": 2}[kw.pop("distMode", "auto")]
         self.settings = make_settings(**kw)
+        self.settings.reserved_i[1] = dist_mode
         self._h = C.c_void_p()
         _lib.check(lib.qpb200_dist_create(C.byref(self._h), self.rank, self.nranks, idbuf.ctypes.data_as(C.c_void_p),
                                           self.n, self.m_local, _p64(Pp), _p64(Pi), _pd(Pv), _p64(Ap), _p64(Ai), _pd(Av),

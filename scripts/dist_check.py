@@ -25,9 +25,10 @@ rank, world = dist.get_rank(), dist.get_world_size()
 out = {}
 P, q, A, l, u = config_cfg5(seed=1234, scale=pscale)
 n, m = P.shape[0], A.shape[0]
-for precond, adapt in (("jacobi", False), ("none", False), ("jacobi", True)):
+modes = os.environ.get("QPB_DIST_MODES", "peer,nccl").split(",")
+for mode, precond, adapt in [(mo, pc, ad) for mo in modes for pc, ad in (("jacobi", False), ("none", False), ("jacobi", True))]:
     kw = dict(numIterations=400, epsPcg=1e-10, precond=precond, adptRho=adapt, rho=0.1 if adapt else 1.0)
-    with S.QPB200DistSolver(P, q, A, l, u, **kw) as ds:
+    with S.QPB200DistSolver(P, q, A, l, u, distMode=mode, **kw) as ds:
         x = np.zeros(n)
         flag = ds.solve(x, want_zy=True)
         info = dict(ds.info)
@@ -42,35 +43,37 @@ for precond, adapt in (("jacobi", False), ("none", False), ("jacobi", True)):
     res = dict(ok=bool(ok), flag=int(flag), flag1=int(flag1), it=info["iterations"], it1=info1["iterations"], err=err, zerr=zerr,
                pcg=info["pcg_iters_total"], pcg1=info1["pcg_iters_total"], rho_updates=info["rho_updates"],
                ms=info["solve_ms"], ms1=info1["solve_ms"], launches=info["kernel_launches"])
-    out[f"parity_{precond}_{'adapt' if adapt else 'fixed'}"] = res
+    out[f"parity_{mode}_{precond}_{'adapt' if adapt else 'fixed'}"] = res
     t = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(json.dumps({f"parity_{precond}_{adapt}": res, "all_ranks_ok": bool(t.item() == 1.0)}), flush=True)
+        print(json.dumps({f"parity_{mode}_{precond}_{adapt}": res, "all_ranks_ok": bool(t.item() == 1.0)}), flush=True)
     assert t.item() == 1.0, res
 
 if tscale > 0:
     P, q, A, l, u = config_cfg5(seed=1234, scale=tscale)
     n = P.shape[0]
-    kw = dict(numIterations=iters)
-    t0 = time.time()
-    with S.QPB200DistSolver(P, q, A, l, u, **kw) as ds:
-        create_s = time.time() - t0
-        for rep in range(3):
-            x = np.zeros(n)
-            dist.barrier(); torch.cuda.synchronize()
-            t0 = time.time()
-            ds.solve(x)
-            torch.cuda.synchronize()
-            wall = time.time() - t0
-        info = dict(ds.info)
-    t = torch.tensor([info["solve_ms"]], device="cuda", dtype=torch.float64)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        res = dict(world=world, n=n, create_s=create_s, wall_s=wall, solve_ms_max=float(t.item()), iters=info["iterations"],
-                   pcg=info["pcg_iters_total"], it_per_s=info["iterations"] / (float(t.item()) * 1e-3), launches=info["kernel_launches"])
-        print(json.dumps({"timing": res}), flush=True)
-        out["timing"] = res
+    for mode in modes:
+        kw = dict(numIterations=iters)
+        t0 = time.time()
+        with S.QPB200DistSolver(P, q, A, l, u, distMode=mode, **kw) as ds:
+            create_s = time.time() - t0
+            for rep in range(3):
+                x = np.zeros(n)
+                dist.barrier(); torch.cuda.synchronize()
+                t0 = time.time()
+                ds.solve(x)
+                torch.cuda.synchronize()
+                wall = time.time() - t0
+            info = dict(ds.info)
+        t = torch.tensor([info["solve_ms"]], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            res = dict(mode=mode, world=world, n=n, create_s=create_s, wall_s=wall, solve_ms_max=float(t.item()),
+                       iters=info["iterations"], pcg=info["pcg_iters_total"],
+                       it_per_s=info["iterations"] / (float(t.item()) * 1e-3), launches=info["kernel_launches"])
+            print(json.dumps({"timing_" + mode: res}), flush=True)
+            out["timing_" + mode] = res
 if rank == 0:
     json.dump(out, open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", f"dist_check_{world}.json"), "w"), indent=1)
 dist.destroy_process_group()
