@@ -294,6 +294,8 @@ static int peer_init(SparseSolver &s, DistContext &d) {
         pd.region[q] = static_cast<double *>(ptr);
     }
     pd.info = s.prob.info;
+    pd.dbg = nullptr;
+    if (getenv("QPB200_TIMING")) QPB_CUDA(s.arena.alloc(&pd.dbg, 16, true));
     QPB_CUDA(s.arena.alloc(&d.tiny, 2, true));
     for (const void *fn : {(const void *)admm_peer_kernel<0, false>, (const void *)admm_peer_kernel<0, true>,
                            (const void *)admm_peer_kernel<1, false>, (const void *)admm_peer_kernel<1, true>,
@@ -341,6 +343,14 @@ int peer_solve(SparseSolver &s, DistContext &d, double *x_inout, double *z_out, 
     float ms = 0.f;
     QPB_CUDA(cudaEventElapsedTime(&ms, s.ev0, s.ev1));
     s.last_info = hi;
+    if (d.peer.dbg) {
+        unsigned long long t[16];
+        QPB_CUDA(cudaMemcpy(t, d.peer.dbg, sizeof(t), cudaMemcpyDeviceToHost));
+        QPB_CUDA(cudaMemset(d.peer.dbg, 0, sizeof(t)));
+        const double k = hi.pcg_iters_total > 0 ? 1e-3 / (double)hi.pcg_iters_total : 0.0;
+        fprintf(stderr, "[qpb200 peer rank %d] us per CG iteration: A pass %.1f, H pass %.1f, all-reduce %.1f, c+u.c %.1f, x~/r %.1f, u %.1f, other %.1f (solve %.1f ms, %lld CG its)\n",
+                d.rank, t[0] * k, t[1] * k, t[2] * k, t[3] * k, t[4] * k, t[5] * k, t[6] * k, ms, (long long)hi.pcg_iters_total);
+    }
     if (info) {
         std::memset(info, 0, sizeof(*info));
         info->conv_flag = hi.conv_flag;

@@ -30,6 +30,7 @@ struct PeerDev {
     long long off_lmax;              // nranks * 4
     long long off_flags;             // kMaxPeers unsigned long long
     AdmmInfoDev *info;
+    unsigned long long *dbg;         // 16 phase timers in ns (block 0 / thread 0), printed with QPB200_TIMING
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
@@ -39,6 +40,12 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 }
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
 }
 
 struct XState {
@@ -83,10 +90,37 @@ __device__ __forceinline__ void peer_allreduce(const GridSync &gs, SyncState &st
     sys_barrier(gs, st, pd, xs);                      // all partials written and visible
     const int R = pd.nranks;
     const int j0 = (int)((long long)len * pd.rank / R), j1 = (int)((long long)len * (pd.rank + 1) / R);
-    for (int j = j0 + blockIdx.x * kThreads + threadIdx.x; j < j1; j += gridDim.x * kThreads) {
-        double s = 0.0;
-        for (int q = 0; q < R; ++q) s += pd.region[q][off_part + j];    // rank order: deterministic
-        for (int q = 0; q < R; ++q) pd.region[q][off_red + j] = s;       // push to everyone (incl. self)
+    const double *src[kMaxPeers];
+    double *dst[kMaxPeers];
+#pragma unroll
+    for (int q = 0; q < kMaxPeers; ++q) {
+        src[q] = pd.region[q < R ? q : 0] + off_part;
+        dst[q] = pd.region[q < R ? q : 0] + off_red;
+    }
+    constexpr int U = 4;     // independent remote loads in flight per thread
+    const int stride = gridDim.x * kThreads;
+    for (int jb = j0 + blockIdx.x * kThreads + threadIdx.x; jb < j1; jb += U * stride) {
+        double s[U];
+#pragma unroll
+        for (int e = 0; e < U; ++e) s[e] = 0.0;
+#pragma unroll
+        for (int q = 0; q < kMaxPeers; ++q)          // rank order: deterministic
+            if (q < R) {
+#pragma unroll
+                for (int e = 0; e < U; ++e) {
+                    const int j = jb + e * stride;
+                    if (j < j1) s[e] += __ldcg(src[q] + j);
+                }
+            }
+#pragma unroll
+        for (int q = 0; q < kMaxPeers; ++q)          // push to everyone (incl. self)
+            if (q < R) {
+#pragma unroll
+                for (int e = 0; e < U; ++e) {
+                    const int j = jb + e * stride;
+                    if (j < j1) dst[q][j] = s[e];
+                }
+            }
     }
     sys_barrier(gs, st, pd, xs);                      // all slices delivered everywhere
 }
@@ -149,6 +183,16 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) admm_peer_kernel(SparsePro
         ++n_h;
     };
 
+    // optional phase timers (ns, block 0 / thread 0 only): 0 A pass, 1 H pass, 2 all-reduce, 3 c + u.c, 4 x~/r update, 5 u update
+    unsigned long long t_last = gtimer();
+    auto tick = [&](int slot) {
+        if (pd.dbg && blockIdx.x == 0 && threadIdx.x == 0) {
+            const unsigned long long now = gtimer();
+            pd.dbg[slot] += now - t_last;
+            t_last = now;
+        }
+    };
+
     long long ii = 0;
     for (ii = 1; ii <= p.s.max_iter; ++ii) {
         bool changed = false;
@@ -185,10 +229,14 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) admm_peer_kernel(SparsePro
         const double tol = fmax(p.s.pcg_rel_eps * residual, p.s.pcg_eps);
         long long k = 0;
         while (k < p.s.pcg_max_iter && !(residual <= tol)) {
+            tick(6);
             spmv_A_t();
             grid_barrier(p.gs, st);
+            tick(0);
             spmv_H_partial(p.UT);
+            tick(1);
             peer_allreduce(p.gs, st, pd, xs, pd.off_wpart, pd.off_wred, n);
+            tick(2);
             double uc[1] = {0.0};
             for (int j = gtid; j < n; j += gstride) {
                 const double uj = u[j];
@@ -197,6 +245,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) admm_peer_kernel(SparsePro
                 uc[0] += uj * cj;
             }
             grid_barrier_reduce<1, false>(p.gs, st, uc, sm.red, sm.bcast);
+            tick(3);
             if (!(uc[0] > 0.0)) break;
             const double a_cg = rz / uc[0];
             double acc2[2] = {0.0, 0.0};
@@ -213,12 +262,14 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) admm_peer_kernel(SparsePro
             residual = sqrt(acc2[0]);
             const double rz_new = acc2[1];
             ++k;
+            tick(4);
             if (k < p.s.pcg_max_iter && !(residual <= tol)) {
                 const double beta = rz_new / rz;
                 for (int j = gtid; j < n; j += gstride) u[j] = zpv[j] + beta * u[j];
                 grid_barrier(p.gs, st);
             }
             rz = rz_new;
+            tick(5);
         }
         pcg_total += k;
         if (k >= p.s.pcg_max_iter && !(residual <= tol)) ++pcg_maxed;
