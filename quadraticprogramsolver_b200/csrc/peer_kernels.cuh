@@ -52,16 +52,21 @@ struct XState {
     unsigned long long xepoch;
 };
 
-// grid barrier + cross-GPU barrier in one: only the last-arriving CTA talks to the peers
+// grid barrier + cross-GPU barrier in one: only the last-arriving CTA talks to the peers.
+// REMOTE_WRITES: the phase before the barrier stored into peer memory -> every CTA releases at system scope
+// (fence.acq_rel.sys); otherwise a gpu-scope fence per CTA is enough and the last arriver's system-scope fence
+// is cumulative over what it observed through the arrival counter.
+template <bool REMOTE_WRITES>
 __device__ __forceinline__ void sys_barrier(const GridSync &gs, SyncState &st, const PeerDev &pd, XState &xs) {
     st.epoch += 1;
     xs.xepoch += 1;
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence_system();   // this CTA's writes, including stores to peer memory
+        if (REMOTE_WRITES) asm volatile("fence.acq_rel.sys;" ::: "memory");
+        else __threadfence();
         const unsigned long long old = atomicAdd(gs.count, 1ULL);
         if (old == st.epoch * gridDim.x - 1ULL) {
-            __threadfence_system();
+            asm volatile("fence.acq_rel.sys;" ::: "memory");
             for (int q = 0; q < pd.nranks; ++q)
                 if (q != pd.rank)
                     st_release_sys(reinterpret_cast<unsigned long long *>(pd.region[q] + pd.off_flags) + pd.rank, xs.xepoch);
@@ -73,13 +78,12 @@ __device__ __forceinline__ void sys_barrier(const GridSync &gs, SyncState &st, c
                     if (clock64() - t0 > 60000000000LL) __trap();   // ~30 s: a peer is gone; fail loudly, do not hang
                 }
             }
-            __threadfence_system();
             st_release_gpu(gs.flag, st.epoch);
         } else {
             while (ld_acquire_gpu(gs.flag) < st.epoch) {
             }
         }
-        __threadfence();
+        __threadfence();   // acquire + L1 invalidate for the phase that follows
     }
     __syncthreads();
 }
@@ -87,7 +91,7 @@ __device__ __forceinline__ void sys_barrier(const GridSync &gs, SyncState &st, c
 // all-reduce(sum) of `len` doubles: partial at off_part in every region -> result at off_red in every region
 __device__ __forceinline__ void peer_allreduce(const GridSync &gs, SyncState &st, const PeerDev &pd, XState &xs,
                                                long long off_part, long long off_red, int len) {
-    sys_barrier(gs, st, pd, xs);                      // all partials written and visible
+    sys_barrier<false>(gs, st, pd, xs);               // all partials written (locally) and visible
     const int R = pd.nranks;
     const int j0 = (int)((long long)len * pd.rank / R), j1 = (int)((long long)len * (pd.rank + 1) / R);
     const double *src[kMaxPeers];
@@ -122,14 +126,14 @@ __device__ __forceinline__ void peer_allreduce(const GridSync &gs, SyncState &st
                 }
             }
     }
-    sys_barrier(gs, st, pd, xs);                      // all slices delivered everywhere
+    sys_barrier<true>(gs, st, pd, xs);                // all slices delivered everywhere
 }
 
 // all-reduce(max) of 4 doubles per rank: every rank pushes its 4 values into slot `rank` of every region
 __device__ __forceinline__ void peer_allmax4(const GridSync &gs, SyncState &st, const PeerDev &pd, XState &xs, double (&v)[4]) {
     if (blockIdx.x == 0 && threadIdx.x < 4)
         for (int q = 0; q < pd.nranks; ++q) pd.region[q][pd.off_lmax + 4 * pd.rank + threadIdx.x] = v[threadIdx.x];
-    sys_barrier(gs, st, pd, xs);
+    sys_barrier<true>(gs, st, pd, xs);
     const double *slots = pd.region[pd.rank] + pd.off_lmax;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
