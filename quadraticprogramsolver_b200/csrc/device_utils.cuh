@@ -65,6 +65,9 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// release/acquire fence at gpu scope (lighter than the sequentially-consistent __threadfence())
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
 __device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long *p) {
     unsigned long long v;
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -97,20 +100,20 @@ __device__ __forceinline__ void grid_barrier(const GridSync &gs, SyncState &st) 
     __syncthreads();
     if (threadIdx.x == 0) {
         // release: this CTA's writes (ordered before us by the bar.sync above) become visible before the arrival
-        __threadfence();
+        fence_acq_rel_gpu();
         const unsigned long long old = atomicAdd(gs.count, 1ULL);
         if (old == st.epoch * gridDim.x - 1ULL) {
             // last arriver: it has observed every other arrival through the RMW chain; the fence makes that
             // cumulative before the flag is published (only this one CTA pays for it)
-            __threadfence();
+            fence_acq_rel_gpu();
             st_release_gpu(gs.flag, st.epoch);
         } else {
             while (ld_acquire_gpu(gs.flag) < st.epoch) {
             }
         }
-        // acquire + L1 invalidate (MEMBAR.SC.GPU ; CCTL.IVALL): the phase that follows reads vectors other CTAs
+        // acquire + L1 invalidate (SASS: MEMBAR ; CCTL.IVALL): the phase that follows reads vectors other CTAs
         // wrote with plain cached loads
-        __threadfence();
+        fence_acq_rel_gpu();
     }
     __syncthreads();
 }

@@ -350,6 +350,8 @@ int peer_solve(SparseSolver &s, DistContext &d, double *x_inout, double *z_out, 
         const double k = hi.pcg_iters_total > 0 ? 1e-3 / (double)hi.pcg_iters_total : 0.0;
         fprintf(stderr, "[qpb200 peer rank %d] us per CG iteration: A pass %.1f, H pass %.1f, all-reduce %.1f, c+u.c %.1f, x~/r %.1f, u %.1f, other %.1f (solve %.1f ms, %lld CG its)\n",
                 d.rank, t[0] * k, t[1] * k, t[2] * k, t[3] * k, t[4] * k, t[5] * k, t[6] * k, ms, (long long)hi.pcg_iters_total);
+        fprintf(stderr, "[qpb200 peer rank %d] barrier cost in isolation (us): grid %.2f, system(local writes) %.2f, system(remote writes) %.2f, grid+reduce %.2f\n",
+                d.rank, t[8] / 200e3, t[9] / 200e3, t[10] / 200e3, t[11] / 200e3);
     }
     if (info) {
         std::memset(info, 0, sizeof(*info));
