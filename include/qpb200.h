@@ -135,7 +135,12 @@ void qpb200_batch_destroy(qpb200_batch *h);
  * Rank r owns rows [row_begin, row_end) of A (and of l, u, z, y) and the same-numbered share of P's
  * columns; the CSC arrays passed are that slice: A_slice is (row_end-row_begin) x n with LOCAL row
  * indices, P_slice is n x n holding only the columns [pcol_begin, pcol_end).  x, q are replicated.
- * nccl_unique_id: 128 bytes from qpb200_dist_unique_id on rank 0, distributed by the caller.      */
+ * nccl_unique_id: 128 bytes from qpb200_dist_unique_id on rank 0, distributed by the caller; 128 zero bytes
+ * mean "reuse the communicator this process created for its previous distributed handle" (same rank, nranks
+ * and device) -- ncclCommInitRank costs about a second, a solve often less.
+ * settings.reserved_i[1] selects the collective: 0 = all-reduce inside the persistent kernel over NVLink peer
+ * memory (cudaIpc) when every rank can map every peer, else NCCL; 1 = ncclAllReduce + host-driven kernel
+ * segments; 2 = peer path required (error if unavailable).                                                  */
 int qpb200_dist_unique_id(void *id128);
 int qpb200_dist_create(qpb200_handle **out, int32_t rank, int32_t nranks, const void *nccl_unique_id,
                        int64_t n, int64_t m_local,

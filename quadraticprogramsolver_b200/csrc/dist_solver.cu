@@ -58,6 +58,15 @@ static NcclApi *nccl_api() {
             return ::qpb::fail(QPB200_ERR_NCCL, "%s failed: %s (%s:%d)", #call, api->GetErrorString(r_), __FILE__, __LINE__); \
     } while (0)
 
+struct CommCacheEntry {
+    ncclComm_t comm = nullptr;
+    int rank = -1, nranks = 0, device = -1;
+};
+static CommCacheEntry &comm_cache() {
+    static CommCacheEntry e;
+    return e;
+}
+
 struct DistContext {
     int rank = 0, nranks = 1;
     ncclComm_t comm = nullptr;
@@ -77,7 +86,8 @@ struct DistContext {
 void dist_destroy(DistContext *d) {
     if (!d) return;
     NcclApi *api = nccl_api();
-    if (d->comm && api) api->CommDestroy(d->comm);
+    // the communicator is process-cached (comm_cache): creating one costs ~1 s, re-solves / new handles reuse it
+    (void)api;
     if (d->host_state) cudaFreeHost(d->host_state);
     for (auto &e : d->ev) if (e) cudaEventDestroy(e);
     for (void *o : d->opened) if (o) cudaIpcCloseMemHandle(o);
@@ -209,7 +219,24 @@ int dist_init(SparseSolver &s, DistContext *&out, int rank, int nranks, const vo
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
     std::memcpy(&id, unique_id, sizeof(id));
     QPB_CUDA(cudaSetDevice(s.device));
-    QPB_NCCL(api->CommInitRank(&d->comm, nranks, id, rank));
+    {
+        // An all-zero id means "reuse this process's communicator for (device, rank, nranks)": ncclCommInitRank
+        // is a ~1 s collective, far more than a solve, and a caller that re-solves related QPs should not pay it
+        // per handle.  Communicators live until process exit.
+        bool zero_id = true;
+        for (size_t i = 0; i < sizeof(id); ++i) zero_id = zero_id && reinterpret_cast<const unsigned char *>(&id)[i] == 0;
+        CommCacheEntry &e = comm_cache();
+        if (zero_id) {
+            if (!e.comm || e.rank != rank || e.nranks != nranks || e.device != s.device)
+                return fail(QPB200_ERR_NCCL, "qpb200_dist_create: zero NCCL id but no cached communicator for rank %d/%d on device %d", rank, nranks, s.device);
+        } else {
+            if (e.comm) api->CommDestroy(e.comm);
+            e.comm = nullptr;
+            QPB_NCCL(api->CommInitRank(&e.comm, nranks, id, rank));
+            e.rank = rank; e.nranks = nranks; e.device = s.device;
+        }
+        d->comm = e.comm;
+    }
     QPB_CUDA(s.arena.alloc(&d->buf.state, 1, true));
     QPB_CUDA(s.arena.alloc(&d->buf.wbuf, (size_t)s.n + 8, true));
     QPB_CUDA(s.arena.alloc(&d->buf.wbuf2, (size_t)2 * s.n + 8, true));
@@ -265,6 +292,19 @@ static int peer_init(SparseSolver &s, DistContext &d) {
     pd.off_wred = (long long)off; off += up(n);
     pd.off_w2part = (long long)off; off += up(2 * n);
     pd.off_w2red = (long long)off; off += up(2 * n);
+    // sliced variant: per-CTA dot partials of every rank, and the gathered vector pairs [u ; t], [x~ ; g]
+    // (their n-parts are written by the peers) -- same offsets on every rank, hence sized with max_r m_r
+    pd.grid_max = s.num_sms * kMinCtas;
+    pd.off_cta = (long long)off; off += up((size_t)2 * d.nranks * pd.grid_max * 4);
+    double mmax = (double)s.m, *dm = nullptr;
+    QPB_CUDA(s.arena.alloc(&dm, 2, true));
+    QPB_CUDA(cudaMemcpyAsync(dm, &mmax, sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    QPB_NCCL(api->AllReduce(dm, dm, 1, ncclDouble, ncclMax, d.comm, s.stream));
+    QPB_CUDA(cudaMemcpyAsync(&mmax, dm, sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    QPB_CUDA(cudaStreamSynchronize(s.stream));
+    const size_t pair = up(n + (size_t)mmax + 8);
+    const size_t off_UT = off; off += pair;
+    const size_t off_XG = off; off += pair;
     d.region_doubles = off;
     QPB_CUDA(cudaMalloc(&d.region, off * sizeof(double)));
     QPB_CUDA(cudaMemset(d.region, 0, off * sizeof(double)));
@@ -293,13 +333,19 @@ static int peer_init(SparseSolver &s, DistContext &d) {
         d.opened[q] = ptr;
         pd.region[q] = static_cast<double *>(ptr);
     }
+    // the gathered pairs move into the peer-visible region (the arena copies stay unused)
+    s.prob.UT = d.region + off_UT;
+    s.prob.XG = d.region + off_XG;
     pd.info = s.prob.info;
     pd.dbg = nullptr;
     if (getenv("QPB200_TIMING")) QPB_CUDA(s.arena.alloc(&pd.dbg, 16, true));
     QPB_CUDA(s.arena.alloc(&d.tiny, 2, true));
     for (const void *fn : {(const void *)admm_peer_kernel<0, false>, (const void *)admm_peer_kernel<0, true>,
                            (const void *)admm_peer_kernel<1, false>, (const void *)admm_peer_kernel<1, true>,
-                           (const void *)admm_peer_kernel<2, false>, (const void *)admm_peer_kernel<2, true>}) {
+                           (const void *)admm_peer_kernel<2, false>, (const void *)admm_peer_kernel<2, true>,
+                           (const void *)admm_peer_sliced_kernel<0, false>, (const void *)admm_peer_sliced_kernel<0, true>,
+                           (const void *)admm_peer_sliced_kernel<1, false>, (const void *)admm_peer_sliced_kernel<1, true>,
+                           (const void *)admm_peer_sliced_kernel<2, false>, (const void *)admm_peer_sliced_kernel<2, true>}) {
         QPB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpmvSmem)));
         int per_sm = 0;
         QPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, sizeof(SpmvSmem)));
@@ -327,8 +373,14 @@ int peer_solve(SparseSolver &s, DistContext &d, double *x_inout, double *z_out, 
         const void *fns[3][2] = {{(const void *)admm_peer_kernel<0, false>, (const void *)admm_peer_kernel<0, true>},
                                  {(const void *)admm_peer_kernel<1, false>, (const void *)admm_peer_kernel<1, true>},
                                  {(const void *)admm_peer_kernel<2, false>, (const void *)admm_peer_kernel<2, true>}};
-        QPB_CUDA(cudaLaunchCooperativeKernel(fns[s.loader][s.use_pre ? 1 : 0], dim3(s.grid), dim3(kThreads), args,
-                                             sizeof(SpmvSmem), s.stream));
+        const void *fns_sliced[3][2] = {{(const void *)admm_peer_sliced_kernel<0, false>, (const void *)admm_peer_sliced_kernel<0, true>},
+                                        {(const void *)admm_peer_sliced_kernel<1, false>, (const void *)admm_peer_sliced_kernel<1, true>},
+                                        {(const void *)admm_peer_sliced_kernel<2, false>, (const void *)admm_peer_sliced_kernel<2, true>}};
+        // default: sliced CG vectors; QPB200_PEER_SLICED=0 selects the replicated variant (A/B)
+        const char *e = getenv("QPB200_PEER_SLICED");
+        const bool sliced = !(e && atoi(e) == 0);
+        const void *fn = sliced ? fns_sliced[s.loader][s.use_pre ? 1 : 0] : fns[s.loader][s.use_pre ? 1 : 0];
+        QPB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(s.grid), dim3(kThreads), args, sizeof(SpmvSmem), s.stream));
     }
     QPB_CUDA(cudaEventRecord(s.ev1, s.stream));
     QPB_CUDA(cudaMemcpyAsync(x_inout, s.prob.XY, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s.stream));

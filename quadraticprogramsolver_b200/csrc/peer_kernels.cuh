@@ -29,6 +29,8 @@ struct PeerDev {
     long long off_w2part, off_w2red; // 2n each
     long long off_lmax;              // nranks * 4
     long long off_flags;             // kMaxPeers unsigned long long
+    long long off_cta;               // 2 (parity) * nranks * grid_max * 4 : per-CTA partial sums of the cross-GPU dots
+    int grid_max;
     AdmmInfoDev *info;
     unsigned long long *dbg;         // 16 phase timers in ns (block 0 / thread 0), printed with QPB200_TIMING
 };
@@ -341,6 +343,300 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) admm_peer_kernel(SparsePro
                 ++n_h;
             }
             grid_barrier_reduce<4, true>(p.gs, st, nrm, sm.red, sm.bcast);   // local maxima (identical in all CTAs)
+            peer_allmax4(p.gs, st, pd, xs, nrm);
+            peer_allreduce(p.gs, st, pd, xs, pd.off_w2part, pd.off_w2red, 2 * n);
+            double nd[2] = {0.0, 0.0};
+            for (int j = gtid; j < n; j += gstride) {
+                const double px = w2red[j], aty = w2red[n + j];
+                nd[0] = nanmax(nd[0], fabs(px + p.q[j] + aty));
+                nd[1] = nanmax(nd[1], fabs(px));
+                nd[1] = nanmax(nd[1], fabs(aty));
+            }
+            grid_barrier_reduce<2, true>(p.gs, st, nd, sm.red, sm.bcast);
+            const double dx = nrm[0], dz = nrm[1];
+            res_prim = nrm[2];
+            res_dual = nd[0];
+            const double max_prim = nrm[3];
+            const double max_dual = nanmax(nd[1], p.normQ);
+            if (p.s.adaptive_rho) {
+                const double num = res_prim * max_dual, den = res_dual * max_prim;
+                rhorho = clamp_julia(rho * sqrt(num / den), 1e-3, 1e6);
+            }
+            if ((res_prim < p.s.eps_abs + p.s.eps_rel * max_prim) && (res_dual < p.s.eps_abs + p.s.eps_rel * max_dual)) conv_flag = 3;
+            if ((dx <= eps_admm) && (dz <= eps_admm)) conv_flag = 2;
+            if (conv_flag != 1) break;
+        }
+    }
+    if (ii > p.s.max_iter) ii = p.s.max_iter;
+
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        AdmmInfoDev &o = *pd.info;
+        o.conv_flag = conv_flag;
+        o.iterations = ii;
+        o.rho_final = rho;
+        o.res_prim = res_prim;
+        o.res_dual = res_dual;
+        o.rho_updates = rho_updates;
+        o.pcg_iters_total = pcg_total;
+        o.pcg_maxed = pcg_maxed;
+        o.n_h_passes = n_h;
+        o.n_a_passes = n_a;
+    }
+}
+
+// =====================================================================================================
+// Sliced variant: the CG vectors are NOT replicated.  Rank r owns slice S_r = [n r / R, n (r+1) / R) of
+// x~, r, z, c and is the only one to update it; u (gathered by A_r and H_r) and x~ (gathered once per ADMM
+// iteration) are kept coherent by pushing the owner's slice into every rank's copy (all-gather by remote
+// stores).  The reduce-scatter of H_r [u ; rho A_r u] is fused with c = w + sigma u and the u.c partial sums;
+// dot products are reduced across GPUs by pushing every CTA's partial into every rank's slot table and
+// summing the R x G partials in the same fixed order everywhere after ONE system barrier.
+// Per CG iteration: 1 grid barrier + 4 system barriers, vector traffic 1/R of the replicated variant.
+// =====================================================================================================
+template <int NV>
+__device__ __forceinline__ void peer_barrier_sum(const GridSync &gs, SyncState &st, const PeerDev &pd, XState &xs,
+                                                 double (&v)[NV], SpmvSmem &sm, unsigned &parity) {
+    static_assert(NV <= 4, "slot width");
+    block_reduce<NV, false>(v, sm.red);
+    parity ^= 1u;
+    const long long base = pd.off_cta + (long long)parity * pd.nranks * pd.grid_max * 4;
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < pd.nranks; ++q) {
+            double *slot = pd.region[q] + base + ((long long)pd.rank * pd.grid_max + blockIdx.x) * 4;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) slot[i] = v[i];
+        }
+    }
+    sys_barrier<true>(gs, st, pd, xs);
+    if (threadIdx.x < 32) {
+        const double *tab = pd.region[pd.rank] + base;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            double x = 0.0;
+            for (int q = 0; q < pd.nranks; ++q)     // all grid_max slots: ranks may run different grids, unused slots stay 0
+                for (int j = threadIdx.x; j < pd.grid_max; j += 32) x += __ldcg(tab + ((long long)q * pd.grid_max + j) * 4 + i);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+            if (threadIdx.x == 0) sm.bcast[i] = x;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = sm.bcast[i];
+    __syncthreads();
+}
+
+template <int TMA, bool PRE>
+__global__ void __launch_bounds__(kThreads, kMinCtas) admm_peer_sliced_kernel(SparseProblemDev p, PeerDev pd) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SpmvSmem &sm = *reinterpret_cast<SpmvSmem *>(smem_raw);
+    PipeState ps;
+    spmv_smem_init(sm, ps);
+    SyncState st;
+    st.epoch = 0;
+    XState xs;
+    xs.xepoch = 0;
+    unsigned parity = 0;
+
+    const int n = p.n, m = p.m, R = pd.nranks;
+    const int gtid = blockIdx.x * kThreads + threadIdx.x;
+    const int gstride = gridDim.x * kThreads;
+    const int s0 = (int)((long long)n * pd.rank / R), s1 = (int)((long long)n * (pd.rank + 1) / R);   // my slice
+    double *const x = p.XY, *const y = p.XY + n;
+    double *const xt = p.XG, *const g = p.XG + n;          // p.XG / p.UT live in the peer-visible region
+    double *const u = p.UT, *const t = p.UT + n;
+    double *const zpv = PRE ? p.zp : p.r;
+    double *const wpart = pd.region[pd.rank] + pd.off_wpart;
+    double *const w2part = pd.region[pd.rank] + pd.off_w2part;
+    const double *const w2red = pd.region[pd.rank] + pd.off_w2red;
+    // remote views of u and x~ (same offset in every region)
+    const long long off_u = (long long)(p.UT - pd.region[pd.rank]), off_xt = (long long)(p.XG - pd.region[pd.rank]);
+    const double *wsrc[kMaxPeers];
+    double *udst[kMaxPeers], *xtdst[kMaxPeers];
+#pragma unroll
+    for (int q = 0; q < kMaxPeers; ++q) {
+        wsrc[q] = pd.region[q < R ? q : 0] + pd.off_wpart;
+        udst[q] = pd.region[q < R ? q : 0] + off_u;
+        xtdst[q] = pd.region[q < R ? q : 0] + off_xt;
+    }
+
+    double rho = p.s.rho, rho1 = 1.0 / rho;
+    const double alpha = p.s.alpha, alpha1 = 1.0 - alpha;
+    const double sigma = p.s.sigma;
+    const double eps_admm = fmin(p.s.eps_abs, p.s.eps_rel) * 1e-2;
+    double rhorho = rho;
+    int conv_flag = 1;
+    long long rho_updates = 0, pcg_total = 0, pcg_maxed = 0, n_h = 0, n_a = 0;
+    double res_prim = nan(""), res_dual = nan("");
+    bool dinv_ready = false;
+
+    unsigned long long t_last = gtimer();
+    auto tick = [&](int slot) {
+        if (pd.dbg && blockIdx.x == 0 && threadIdx.x == 0) {
+            const unsigned long long now = gtimer();
+            pd.dbg[slot] += now - t_last;
+            t_last = now;
+        }
+    };
+    auto spmv_A_t = [&]() {
+        auto epi = [&](int i, double s0_, double) { t[i] = rho * s0_; };
+        spmv_tiles<TMA, false>(p.A, u, sm, ps, epi);
+        ++n_a;
+    };
+    auto spmv_H_partial = [&](const double *pair) {
+        auto epi = [&](int j, double s0_, double) { wpart[j] = s0_; };
+        spmv_tiles<TMA, false>(p.H, pair, sm, ps, epi);
+        ++n_h;
+    };
+    auto reduced_w = [&](int j) {          // sum of all ranks' partials in rank order (deterministic)
+        double w = 0.0;
+#pragma unroll
+        for (int q = 0; q < kMaxPeers; ++q)
+            if (q < R) w += __ldcg(wsrc[q] + j);
+        return w;
+    };
+
+    long long ii = 0;
+    for (ii = 1; ii <= p.s.max_iter; ++ii) {
+        bool changed = false;
+        if (p.s.adaptive_rho && ((rhorho * p.s.rho_factor < rho) || (rhorho > p.s.rho_factor * rho))) {
+            rho = rhorho;
+            rho1 = 1.0 / rho;
+            changed = true;
+            ++rho_updates;
+        }
+        if (changed || !dinv_ready) {
+            if (PRE)
+                for (int j = s0 + gtid; j < s1; j += gstride) p.dinv[j] = 1.0 / (p.dP[j] + sigma + rho * p.dAA[j]);
+            if (changed)
+                for (int i = gtid; i < m; i += gstride) g[i] = rho * (p.zt[i] - p.z[i]) + y[i];
+            dinv_ready = true;
+            grid_barrier(p.gs, st);
+        }
+        // ---- r0 on my slice: r = sigma (x - x~) - q - sum_q H_q [x~ ; g_q];  u = z = Pl \ r, pushed to everyone
+        spmv_H_partial(p.XG);
+        sys_barrier<false>(p.gs, st, pd, xs);
+        double acc[2] = {0.0, 0.0};
+        for (int j = s0 + gtid; j < s1; j += gstride) {
+            const double rj = sigma * (x[j] - xt[j]) - p.q[j] - reduced_w(j);
+            p.r[j] = rj;
+            const double zj = PRE ? p.dinv[j] * rj : rj;
+            if (PRE) p.zp[j] = zj;
+#pragma unroll
+            for (int q = 0; q < kMaxPeers; ++q)
+                if (q < R) udst[q][j] = zj;
+            acc[0] += rj * rj;
+            acc[1] += rj * zj;
+        }
+        peer_barrier_sum<2>(p.gs, st, pd, xs, acc, sm, parity);      // also publishes the u slices
+        double residual = sqrt(acc[0]);
+        double rz = acc[1];
+        const double tol = fmax(p.s.pcg_rel_eps * residual, p.s.pcg_eps);
+        long long k = 0;
+        while (k < p.s.pcg_max_iter && !(residual <= tol)) {
+            tick(6);
+            spmv_A_t();
+            grid_barrier(p.gs, st);
+            tick(0);
+            spmv_H_partial(p.UT);
+            tick(1);
+            sys_barrier<false>(p.gs, st, pd, xs);
+            // reduce-scatter fused with c = w + sigma u and u.c (my slice only)
+            double uc[1] = {0.0};
+            for (int j = s0 + gtid; j < s1; j += gstride) {
+                const double uj = u[j];
+                const double cj = reduced_w(j) + sigma * uj;
+                p.c[j] = cj;
+                uc[0] += uj * cj;
+            }
+            peer_barrier_sum<1>(p.gs, st, pd, xs, uc, sm, parity);
+            tick(2);
+            if (!(uc[0] > 0.0)) break;
+            const double a_cg = rz / uc[0];
+            double acc2[2] = {0.0, 0.0};
+            for (int j = s0 + gtid; j < s1; j += gstride) {
+                xt[j] += a_cg * u[j];
+                const double rj = p.r[j] - a_cg * p.c[j];
+                p.r[j] = rj;
+                const double zj = PRE ? p.dinv[j] * rj : rj;
+                if (PRE) p.zp[j] = zj;
+                acc2[0] += rj * rj;
+                acc2[1] += rj * zj;
+            }
+            peer_barrier_sum<2>(p.gs, st, pd, xs, acc2, sm, parity);
+            residual = sqrt(acc2[0]);
+            const double rz_new = acc2[1];
+            ++k;
+            tick(4);
+            if (k < p.s.pcg_max_iter && !(residual <= tol)) {
+                const double beta = rz_new / rz;
+                for (int j = s0 + gtid; j < s1; j += gstride) {
+                    const double un = zpv[j] + beta * u[j];
+#pragma unroll
+                    for (int q = 0; q < kMaxPeers; ++q)
+                        if (q < R) udst[q][j] = un;
+                }
+                sys_barrier<true>(p.gs, st, pd, xs);
+            }
+            rz = rz_new;
+            tick(5);
+        }
+        pcg_total += k;
+        if (k >= p.s.pcg_max_iter && !(residual <= tol)) ++pcg_maxed;
+        // ---- all-gather x~ (every rank pushes its slice), then the row-local update
+        for (int j = s0 + gtid; j < s1; j += gstride) {
+            const double v = xt[j];
+#pragma unroll
+            for (int q = 0; q < kMaxPeers; ++q)
+                if (q < R && q != pd.rank) xtdst[q][j] = v;
+        }
+        sys_barrier<true>(p.gs, st, pd, xs);
+
+        const bool do_check = (ii % p.s.check_every) == 0;
+        double nrm[4] = {0.0, 0.0, 0.0, 0.0};
+        {
+            auto epi = [&](int i, double s0_, double) {
+                const double zt_i = s0_;
+                const double z_old = p.z[i], y_old = y[i];
+                const double zr = alpha * zt_i + alpha1 * z_old;
+                const double z_new = clamp_julia(zr + rho1 * y_old, p.l[i], p.u[i]);
+                const double y_new = y_old + rho * (zr - z_new);
+                p.z[i] = z_new;
+                y[i] = y_new;
+                p.zt[i] = zt_i;
+                g[i] = rho * (zt_i - z_new) + y_new;
+                nrm[1] = nanmax(nrm[1], fabs(z_new - z_old));
+            };
+            spmv_tiles<TMA, false>(p.A, xt, sm, ps, epi);
+            ++n_a;
+        }
+        for (int j = gtid; j < n; j += gstride) {
+            const double x_old = x[j];
+            const double x_new = alpha * xt[j] + alpha1 * x_old;
+            x[j] = x_new;
+            nrm[0] = nanmax(nrm[0], fabs(x_new - x_old));
+        }
+        grid_barrier(p.gs, st);
+        if (do_check) {
+            {
+                auto epi = [&](int i, double s0_, double) {
+                    const double zi = p.z[i];
+                    nrm[2] = nanmax(nrm[2], fabs(s0_ - zi));
+                    nrm[3] = nanmax(nrm[3], fabs(s0_));
+                    nrm[3] = nanmax(nrm[3], fabs(zi));
+                };
+                spmv_tiles<TMA, false>(p.A, x, sm, ps, epi);
+                ++n_a;
+            }
+            {
+                auto epi = [&](int j, double s0_, double s1_) {
+                    w2part[j] = s0_;
+                    w2part[n + j] = s1_;
+                };
+                spmv_tiles<TMA, true>(p.H, p.XY, sm, ps, epi);
+                ++n_h;
+            }
+            grid_barrier_reduce<4, true>(p.gs, st, nrm, sm.red, sm.bcast);
             peer_allmax4(p.gs, st, pd, xs, nrm);
             peer_allreduce(p.gs, st, pd, xs, pd.off_w2part, pd.off_w2red, 2 * n);
             double nd[2] = {0.0, 0.0};

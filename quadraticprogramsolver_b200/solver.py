@@ -269,7 +269,9 @@ def SolveQuadraticProgramBatch(P, q, A_cm, l, u, X0=None, **kw):
 class QPB200DistSolver:
     """One large sparse QP row-partitioned over the ranks of a ``torch.distributed`` group (one rank per
     GPU).  Every rank constructs it with the full problem (or pre-sliced parts via ``presliced``) and calls
-    :meth:`solve` collectively.  NCCL carries the n-vector all-reduces."""
+    :meth:`solve` collectively.  The n-vector all-reduces run inside the persistent kernel over NVLink peer
+    memory (``distMode="auto"``/``"peer"``) or through NCCL (``"nccl"``)."""
+    _comm_key = None
 
     def __init__(self, mP, vQ, mA, vL, vU, group=None, presliced=None, **kw):
         import torch
@@ -285,11 +287,15 @@ class QPB200DistSolver:
         self.m_local = int(A_r.shape[0])
         # rank 0 creates the NCCL id; the group (any backend) carries its 128 bytes
         idbuf = np.zeros(128, dtype=np.uint8)
-        if self.rank == 0:
-            _lib.check(lib.qpb200_dist_unique_id(idbuf.ctypes.data_as(C.c_void_p)))
-        box = [idbuf.tobytes()]
-        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
-        idbuf = np.frombuffer(box[0], dtype=np.uint8).copy()
+        key = (id(group), self.rank, self.nranks)
+        if QPB200DistSolver._comm_key != key:
+            # first handle of this process for this group: make an NCCL communicator (~1 s); later handles pass
+            # an all-zero id, which libqpb200 reads as "reuse the cached communicator"
+            if self.rank == 0:
+                _lib.check(lib.qpb200_dist_unique_id(idbuf.ctypes.data_as(C.c_void_p)))
+            box = [idbuf.tobytes()]
+            dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            idbuf = np.frombuffer(box[0], dtype=np.uint8).copy()
         Pp, Pi, Pv = _csc_arrays(P_r)
         Ap, Ai, Av = _csc_arrays(A_r)
         vQ = np.ascontiguousarray(vQ, dtype=np.float64)
@@ -304,6 +310,7 @@ class QPB200DistSolver:
         _lib.check(lib.qpb200_dist_create(C.byref(self._h), self.rank, self.nranks, idbuf.ctypes.data_as(C.c_void_p),
                                           self.n, self.m_local, _p64(Pp), _p64(Pi), _pd(Pv), _p64(Ap), _p64(Ai), _pd(Av),
                                           _pd(vQ), _pd(l_r), _pd(u_r), C.byref(self.settings), 0))
+        QPB200DistSolver._comm_key = key
         self.info = None
 
     def solve(self, vX, want_zy: bool = False):
