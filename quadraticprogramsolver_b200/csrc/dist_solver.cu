@@ -295,7 +295,7 @@ static int peer_init(SparseSolver &s, DistContext &d) {
     // sliced variant: per-CTA dot partials of every rank, and the gathered vector pairs [u ; t], [x~ ; g]
     // (their n-parts are written by the peers) -- same offsets on every rank, hence sized with max_r m_r
     pd.grid_max = s.num_sms * kMinCtas;
-    pd.off_cta = (long long)off; off += up((size_t)2 * d.nranks * pd.grid_max * 4);
+    pd.off_cta = (long long)off; off += up((size_t)2 * ((size_t)pd.grid_max * 4 + kMaxPeers * 4));
     double mmax = (double)s.m, *dm = nullptr;
     QPB_CUDA(s.arena.alloc(&dm, 2, true));
     QPB_CUDA(cudaMemcpyAsync(dm, &mmax, sizeof(double), cudaMemcpyHostToDevice, s.stream));

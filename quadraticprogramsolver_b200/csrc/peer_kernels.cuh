@@ -29,7 +29,7 @@ struct PeerDev {
     long long off_w2part, off_w2red; // 2n each
     long long off_lmax;              // nranks * 4
     long long off_flags;             // kMaxPeers unsigned long long
-    long long off_cta;               // 2 (parity) * nranks * grid_max * 4 : per-CTA partial sums of the cross-GPU dots
+    long long off_cta;               // 2 (parity) * (grid_max * 4 + kMaxPeers * 4): CTA partials + per-GPU totals of the dots
     int grid_max;
     AdmmInfoDev *info;
     unsigned long long *dbg;         // 16 phase timers in ns (block 0 / thread 0), printed with QPB200_TIMING
@@ -54,42 +54,88 @@ struct XState {
     unsigned long long xepoch;
 };
 
-// grid barrier + cross-GPU barrier in one: only the last-arriving CTA talks to the peers.
-// REMOTE_WRITES: the phase before the barrier stored into peer memory -> every CTA releases at system scope
-// (fence.acq_rel.sys); otherwise a gpu-scope fence per CTA is enough and the last arriver's system-scope fence
-// is cumulative over what it observed through the arrival counter.
-template <bool REMOTE_WRITES>
-__device__ __forceinline__ void sys_barrier(const GridSync &gs, SyncState &st, const PeerDev &pd, XState &xs) {
+// grid barrier + cross-GPU barrier in one: only the last-arriving CTA talks to the peers, and it does so with
+// one lane per peer (signal + poll in parallel: the handshake costs one NVLink round trip for any R).
+// Memory ordering: every CTA releases at gpu scope (that waits for its outstanding stores, local or peer, to be
+// performed); system-scope visibility is established once, cumulatively, by the last arriver's
+// fence.acq_rel.sys before it raises the peers' flags.  (A system-scope fence in every CTA costs +7.7 us per
+// barrier at 592 CTAs: measured.)
+// NV > 0: a sum all-reduce of NV doubles rides on the barrier.  Every CTA deposits its partial before arriving;
+// the last arriver adds the G partials in a fixed order (deterministic whoever arrives last), pushes the GPU
+// total into slot `rank` of every rank's table, and after the barrier everybody adds the R totals in rank
+// order -> bit-identical results on all ranks, ONE barrier for a cross-GPU dot product.
+template <int NV>
+__device__ __forceinline__ void sys_barrier_impl(const GridSync &gs, SyncState &st, const PeerDev &pd, XState &xs,
+                                                 double *v, SpmvSmem &sm, unsigned &parity) {
+    static_assert(NV <= 4, "slot width");
+    double *loc = nullptr, *tot = nullptr;
+    if (NV > 0) {
+        parity ^= 1u;
+        const long long per = (long long)pd.grid_max * 4 + kMaxPeers * 4;
+        loc = pd.region[pd.rank] + pd.off_cta + (long long)parity * per;   // [grid_max][4] CTA partials
+        tot = loc + (long long)pd.grid_max * 4;                            // [kMaxPeers][4] GPU totals
+        if (threadIdx.x == 0)
+            for (int i = 0; i < NV; ++i) loc[blockIdx.x * 4 + i] = v[i];
+    }
     st.epoch += 1;
     xs.xepoch += 1;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        // gpu-scope release per CTA (it waits for this CTA's outstanding writes, local or peer, to be performed);
-        // system-scope visibility is established once, cumulatively, by the last arriver's fence.acq_rel.sys.
-        // (A system-scope fence in every CTA costs +7.7 us per barrier at 592 CTAs: measured.)
-        fence_acq_rel_gpu();
-        const unsigned long long old = atomicAdd(gs.count, 1ULL);
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        unsigned long long old = 0;
+        if (lane == 0) {
+            fence_acq_rel_gpu();
+            old = atomicAdd(gs.count, 1ULL);
+        }
+        old = __shfl_sync(0xffffffffu, old, 0);
         if (old == st.epoch * gridDim.x - 1ULL) {
+            fence_acq_rel_gpu();
+            if (NV > 0) {
+                for (int i = 0; i < NV; ++i) {
+                    double x = 0.0;
+                    for (unsigned j = lane; j < gridDim.x; j += 32) x += __ldcg(loc + j * 4 + i);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+                    x = __shfl_sync(0xffffffffu, x, 0);
+                    if (lane < pd.nranks) {
+                        const long long off = (long long)(tot - pd.region[pd.rank]) + pd.rank * 4 + i;
+                        pd.region[lane][off] = x;
+                    }
+                }
+            }
             asm volatile("fence.acq_rel.sys;" ::: "memory");
-            for (int q = 0; q < pd.nranks; ++q)
-                if (q != pd.rank)
-                    st_release_sys(reinterpret_cast<unsigned long long *>(pd.region[q] + pd.off_flags) + pd.rank, xs.xepoch);
-            const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(pd.region[pd.rank] + pd.off_flags);
-            const long long t0 = clock64();
-            for (int q = 0; q < pd.nranks; ++q) {
-                if (q == pd.rank) continue;
-                while (ld_acquire_sys(mine + q) < xs.xepoch) {
+            __syncwarp();
+            if (lane < pd.nranks && lane != pd.rank) {
+                st_release_sys(reinterpret_cast<unsigned long long *>(pd.region[lane] + pd.off_flags) + pd.rank, xs.xepoch);
+                const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(pd.region[pd.rank] + pd.off_flags) + lane;
+                const long long t0 = clock64();
+                while (ld_acquire_sys(mine) < xs.xepoch) {
                     if (clock64() - t0 > 60000000000LL) __trap();   // ~30 s: a peer is gone; fail loudly, do not hang
                 }
             }
-            st_release_gpu(gs.flag, st.epoch);
-        } else {
+            __syncwarp();
+            if (lane == 0) st_release_gpu(gs.flag, st.epoch);
+        } else if (lane == 0) {
             while (ld_acquire_gpu(gs.flag) < st.epoch) {
             }
         }
         fence_acq_rel_gpu();   // acquire + L1 invalidate for the phase that follows
     }
     __syncthreads();
+    if (NV > 0) {
+        for (int i = 0; i < NV; ++i) {
+            double x = 0.0;
+            for (int q = 0; q < pd.nranks; ++q) x += __ldcg(tot + q * 4 + i);
+            v[i] = x;
+        }
+    }
+}
+
+template <bool REMOTE_WRITES>
+__device__ __forceinline__ void sys_barrier(const GridSync &gs, SyncState &st, const PeerDev &pd, XState &xs) {
+    SpmvSmem *none = nullptr;
+    unsigned dummy = 0;
+    sys_barrier_impl<0>(gs, st, pd, xs, nullptr, *none, dummy);
 }
 
 // all-reduce(sum) of `len` doubles: partial at off_part in every region -> result at off_red in every region
@@ -396,34 +442,8 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) admm_peer_kernel(SparsePro
 template <int NV>
 __device__ __forceinline__ void peer_barrier_sum(const GridSync &gs, SyncState &st, const PeerDev &pd, XState &xs,
                                                  double (&v)[NV], SpmvSmem &sm, unsigned &parity) {
-    static_assert(NV <= 4, "slot width");
-    block_reduce<NV, false>(v, sm.red);
-    parity ^= 1u;
-    const long long base = pd.off_cta + (long long)parity * pd.nranks * pd.grid_max * 4;
-    if (threadIdx.x == 0) {
-        for (int q = 0; q < pd.nranks; ++q) {
-            double *slot = pd.region[q] + base + ((long long)pd.rank * pd.grid_max + blockIdx.x) * 4;
-#pragma unroll
-            for (int i = 0; i < NV; ++i) slot[i] = v[i];
-        }
-    }
-    sys_barrier<true>(gs, st, pd, xs);
-    if (threadIdx.x < 32) {
-        const double *tab = pd.region[pd.rank] + base;
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            double x = 0.0;
-            for (int q = 0; q < pd.nranks; ++q)     // all grid_max slots: ranks may run different grids, unused slots stay 0
-                for (int j = threadIdx.x; j < pd.grid_max; j += 32) x += __ldcg(tab + ((long long)q * pd.grid_max + j) * 4 + i);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-            if (threadIdx.x == 0) sm.bcast[i] = x;
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = sm.bcast[i];
-    __syncthreads();
+    block_reduce<NV, false>(v, sm.red);            // thread 0 holds the CTA partial
+    sys_barrier_impl<NV>(gs, st, pd, xs, v, sm, parity);
 }
 
 template <int TMA, bool PRE>
