@@ -92,8 +92,18 @@ __device__ __forceinline__ void sys_barrier_impl(const GridSync &gs, SyncState &
             fence_acq_rel_gpu();
             if (NV > 0) {
                 for (int i = 0; i < NV; ++i) {
+                    // this warp is alone on the critical path: keep 8 independent L2 loads in flight per lane
                     double x = 0.0;
-                    for (unsigned j = lane; j < gridDim.x; j += 32) x += __ldcg(loc + j * 4 + i);
+                    for (unsigned jb = lane; jb < gridDim.x; jb += 32 * 8) {
+                        double tl[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const unsigned j = jb + 32 * e;
+                            tl[e] = j < gridDim.x ? __ldcg(loc + j * 4 + i) : 0.0;
+                        }
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) x += tl[e];
+                    }
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
                     x = __shfl_sync(0xffffffffu, x, 0);
