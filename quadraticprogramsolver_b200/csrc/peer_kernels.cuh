@@ -89,7 +89,8 @@ __device__ __forceinline__ void sys_barrier_impl(const GridSync &gs, SyncState &
         }
         old = __shfl_sync(0xffffffffu, old, 0);
         if (old == st.epoch * gridDim.x - 1ULL) {
-            fence_acq_rel_gpu();
+            if (lane == 0) fence_acq_rel_gpu();     // one fence per warp: a fence executed by 32 lanes is 32 fences
+            __syncwarp();
             if (NV > 0) {
                 for (int i = 0; i < NV; ++i) {
                     // this warp is alone on the critical path: keep 8 independent L2 loads in flight per lane
@@ -113,7 +114,8 @@ __device__ __forceinline__ void sys_barrier_impl(const GridSync &gs, SyncState &
                     }
                 }
             }
-            asm volatile("fence.acq_rel.sys;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) asm volatile("fence.acq_rel.sys;" ::: "memory");
             __syncwarp();
             if (lane < pd.nranks && lane != pd.rank) {
                 st_release_sys(reinterpret_cast<unsigned long long *>(pd.region[lane] + pd.off_flags) + pd.rank, xs.xepoch);
@@ -129,7 +131,7 @@ __device__ __forceinline__ void sys_barrier_impl(const GridSync &gs, SyncState &
             while (ld_acquire_gpu(gs.flag) < st.epoch) {
             }
         }
-        fence_acq_rel_gpu();   // acquire + L1 invalidate for the phase that follows
+        if (lane == 0) fence_acq_rel_gpu();   // acquire + L1 invalidate for the phase that follows
     }
     __syncthreads();
     if (NV > 0) {
