@@ -272,9 +272,11 @@ def run_b200(args):
     barrier()
     t0 = time.perf_counter()
     e2e_iters = 0
+    e2e_create_ms, e2e_solve_ms = 0.0, 0.0
     for _ in range(e2e_steps):
         info = e2e_once()
         e2e_iters += info["iterations"]
+        e2e_create_ms += info["setup_ms"]; e2e_solve_ms += info["solve_ms"]
     barrier()
     e2e_wall = time.perf_counter() - t0
     if dist is not None:
@@ -298,7 +300,9 @@ def run_b200(args):
                    "pcg_iters_per_step": pcg / max(1, args.steps), "gen_s": round(gen_s, 1)},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "iter/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "steps": e2e_steps, "ms_per_step": 1e3 * e2e_wall / e2e_steps},
+                "steps": e2e_steps, "ms_per_step": 1e3 * e2e_wall / e2e_steps,
+                "breakdown_ms_per_step": {"qpb200_create": e2e_create_ms / e2e_steps, "solve_device": e2e_solve_ms / e2e_steps,
+                                          "copies_destroy_host": 1e3 * e2e_wall / e2e_steps - (e2e_create_ms + e2e_solve_ms) / e2e_steps}},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "kernel": "admm_kernel (persistent; 1 launch per step)" if world == 1 else
