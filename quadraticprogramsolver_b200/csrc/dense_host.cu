@@ -76,7 +76,7 @@ int qpb200_batch_create(qpb200_batch **out, int64_t batch, int64_t n, int64_t m,
         }                                                                                                    \
     } while (0)
     QPB_CUDA_H(cudaGetDevice(&B.device));
-    B.batch = batch; B.n = (int)n; B.m = (int)m; B.mp = ((int)m + 7) & ~7;
+    B.batch = batch; B.n = (int)n; B.m = (int)m; B.mp = ((int)m + 3) & ~3;
     B.settings = s;
     double *dP, *dA, *dq, *dl, *du;
     QPB_CUDA_H(B.arena.alloc(&dP, nP));

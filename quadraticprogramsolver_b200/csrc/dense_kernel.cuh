@@ -27,12 +27,11 @@
 namespace qpb {
 
 constexpr int kDN = 64;          // n padded to 64
-constexpr int kDThreads = 256;     // 8 warps per QP (A/B: 128 threads ran the FP64 pipe at 13 %, issue slots at 22 %)
-constexpr int kDSplit = kDThreads / 64;   // threads cooperating on one output of a 64-wide matrix-vector product
+constexpr int kDThreads = 128;
 constexpr int kLd = kDN + 2;     // leading dimension of the 64 x 64 factor / inverse
 
 struct DenseBatchParams {
-    int batch, n, m, mp;         // mp = m rounded up to a multiple of 8
+    int batch, n, m, mp;         // mp = m rounded up to a multiple of 4
     const double *P, *A, *q, *l, *u;
     double *X;
     int *flags;
@@ -56,7 +55,7 @@ struct DenseSmem {
     double *As;    // lda * 64   (i + lda * j), lda = mp + 2
     double *Lp;    // 64 x kLd row-major: K, then L, then L^-1, then K^-1 (full, symmetric)
     double *x, *xt, *rhs, *q, *colb;   // 64 each
-    double *part;  // kDThreads
+    double *part;  // 128
     double *z, *y, *w, *l, *u;         // mp each
     double *red;   // 64
 };
@@ -71,7 +70,7 @@ __device__ __forceinline__ DenseSmem carve(unsigned char *raw, int mp) {
     s.rhs = p; p += kDN;
     s.q = p; p += kDN;
     s.colb = p; p += kDN;
-    s.part = p; p += kDThreads;
+    s.part = p; p += 2 * kDN;
     s.z = p; p += mp;
     s.y = p; p += mp;
     s.w = p; p += mp;
@@ -82,18 +81,20 @@ __device__ __forceinline__ DenseSmem carve(unsigned char *raw, int mp) {
 }
 
 static size_t dense_smem_bytes(int mp) {
-    return sizeof(double) * ((size_t)(mp + 2) * kDN + kDN * kLd + 5 * kDN + kDThreads + 5 * (size_t)mp + 64);
+    return sizeof(double) * ((size_t)(mp + 2) * kDN + kDN * kLd + 5 * kDN + 2 * kDN + 5 * (size_t)mp + 64);
 }
 
 // ---- K = P + sigma I + rho A'A (lower triangle) via DMMA ----------------------------------------
-// Warp w owns the 8-row tile w of the lower triangle (tiles (w, 0..w)).
+// Warp w owns the 8-row tiles w and 7-w of the lower triangle (9 tiles each: balanced).
 __device__ __forceinline__ void build_K(const DenseSmem &sm, int mp, const double *Pg, int n, double rho, double sigma) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const int rt = warp;
+    const int rtA = warp, rtB = 7 - warp;
     const int lda = mp + 2;
-    double acc[8][2];
+    double accA[4][2], accB[8][2];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[c][0] = acc[c][1] = 0.0;
+    for (int c = 0; c < 4; ++c) accA[c][0] = accA[c][1] = 0.0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) accB[c][0] = accB[c][1] = 0.0;
     const double *As = sm.As;
     for (int kk = 0; kk < mp; kk += 4) {
         // fragment of column tile ct: element (k = kk + t, column 8 ct + g) -- serves as the A operand
@@ -101,22 +102,39 @@ __device__ __forceinline__ void build_K(const DenseSmem &sm, int mp, const doubl
         double f[8];
 #pragma unroll
         for (int ct = 0; ct < 8; ++ct) f[ct] = As[(kk + t) + lda * (8 * ct + g)];
-        const double fa = As[(kk + t) + lda * (8 * rt + g)];
+        const double fa = As[(kk + t) + lda * (8 * rtA + g)];
+        const double fb = As[(kk + t) + lda * (8 * rtB + g)];
+#pragma unroll
+        for (int ct = 0; ct < 4; ++ct)
+            if (ct <= rtA) dmma8x8x4(accA[ct], fa, f[ct]);
 #pragma unroll
         for (int ct = 0; ct < 8; ++ct)
-            if (ct <= rt) dmma8x8x4(acc[ct], fa, f[ct]);
+            if (ct <= rtB) dmma8x8x4(accB[ct], fb, f[ct]);
     }
     // C fragment: lane holds (row 8 rt + g, cols 8 ct + 2t, +1)
 #pragma unroll
-    for (int ct = 0; ct < 8; ++ct)
-        if (ct <= rt) {
-            const int i = 8 * rt + g;
+    for (int ct = 0; ct < 4; ++ct)
+        if (ct <= rtA) {
+            const int i = 8 * rtA + g;
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int j = 8 * ct + 2 * t + e;
                 if (j <= i) {
                     const double pij = (i < n && j < n) ? __ldg(Pg + i + (size_t)n * j) : 0.0;
-                    sm.Lp[pidx(i, j)] = pij + rho * acc[ct][e] + (i == j ? (i < n ? sigma : 1.0) : 0.0);
+                    sm.Lp[pidx(i, j)] = pij + rho * accA[ct][e] + (i == j ? (i < n ? sigma : 1.0) : 0.0);
+                }
+            }
+        }
+#pragma unroll
+    for (int ct = 0; ct < 8; ++ct)
+        if (ct <= rtB) {
+            const int i = 8 * rtB + g;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int j = 8 * ct + 2 * t + e;
+                if (j <= i) {
+                    const double pij = (i < n && j < n) ? __ldg(Pg + i + (size_t)n * j) : 0.0;
+                    sm.Lp[pidx(i, j)] = pij + rho * accB[ct][e] + (i == j ? (i < n ? sigma : 1.0) : 0.0);
                 }
             }
         }
@@ -143,7 +161,7 @@ __device__ __forceinline__ bool chol_unblocked(const DenseSmem &sm) {
         const int ti = threadIdx.x & 63, tk = threadIdx.x >> 6;
         if (ti > j) {
             const double ci = colb[ti];
-            for (int k = j + 1 + tk; k <= ti; k += kDSplit) Lp[pidx(ti, k)] -= ci * colb[k];
+            for (int k = j + 1 + tk; k <= ti; k += 2) Lp[pidx(ti, k)] -= ci * colb[k];
         }
     }
     __syncthreads();
@@ -178,13 +196,13 @@ __device__ __forceinline__ bool chol_blocked(const DenseSmem &sm) {
             if (ti > j) {
                 const double ci = colb[ti];
                 const int kend = ti < c1 - 1 ? ti : c1 - 1;
-                for (int k = j + 1 + tk; k <= kend; k += kDSplit) Lp[pidx(ti, k)] -= ci * colb[k];
+                for (int k = j + 1 + tk; k <= kend; k += 2) Lp[pidx(ti, k)] -= ci * colb[k];
             }
         }
         __syncthreads();
         const int nt = 7 - p;                       // trailing tile rows/cols
         const int ntiles = nt * (nt + 1) / 2;
-        for (int tile = warp; tile < ntiles; tile += kDThreads / 32) {
+        for (int tile = warp; tile < ntiles; tile += 4) {
             int a = 0;                              // tile -> (a, b), b <= a < nt (row-major lower enumeration)
             while ((a + 1) * (a + 2) / 2 <= tile) ++a;
             const int b = tile - a * (a + 1) / 2;
@@ -218,19 +236,15 @@ __device__ __forceinline__ void trtri_lower(const DenseSmem &sm) {
         const int i = threadIdx.x & 63, th = threadIdx.x >> 6;
         double s = 0.0;
         if (i > j) {
-            const int len = i - j;                       // k = j+1 .. i, cut into kDSplit contiguous pieces
-            const int ka = j + 1 + len * th / kDSplit, kb = j + 1 + len * (th + 1) / kDSplit;
+            const int len = i - j, kmid = j + 1 + len / 2;
+            const int ka = th == 0 ? j + 1 : kmid, kb = th == 0 ? kmid : i + 1;
             const double *row = Lp + pidx(i, 0);
             for (int k = ka; k < kb; ++k) s += row[k] * colb[k];
         }
         part[threadIdx.x] = s;
         __syncthreads();
-        if ((int)threadIdx.x < kDN && (int)threadIdx.x > j) {
-            double tot = 0.0;
-#pragma unroll
-            for (int e = 0; e < kDSplit; ++e) tot += part[threadIdx.x + 64 * e];
-            Lp[pidx(threadIdx.x, j)] = -ajj * tot;
-        }
+        if ((int)threadIdx.x < kDN && (int)threadIdx.x > j)
+            Lp[pidx(threadIdx.x, j)] = -ajj * (part[threadIdx.x] + part[threadIdx.x + 64]);
     }
     __syncthreads();
 }
@@ -245,18 +259,13 @@ __device__ __forceinline__ void lauum_lower_and_mirror(const DenseSmem &sm) {
         const int j = threadIdx.x & 63, th = threadIdx.x >> 6;
         double s = 0.0;
         if (j <= i) {
-            const int len = kDN - i;                     // k = i .. 63, cut into kDSplit contiguous pieces
-            const int ka = i + len * th / kDSplit, kb = i + len * (th + 1) / kDSplit;
+            const int len = kDN - i, kmid = i + (len + 1) / 2;
+            const int ka = th == 0 ? i : kmid, kb = th == 0 ? kmid : kDN;
             for (int k = ka; k < kb; ++k) s += Lp[pidx(k, i)] * Lp[pidx(k, j)];
         }
         part[threadIdx.x] = s;
         __syncthreads();                      // every read of row i (k = i terms) is done
-        if ((int)threadIdx.x <= i) {
-            double tot = 0.0;
-#pragma unroll
-            for (int e = 0; e < kDSplit; ++e) tot += part[threadIdx.x + 64 * e];
-            Lp[pidx(i, threadIdx.x)] = tot;
-        }
+        if ((int)threadIdx.x <= i) Lp[pidx(i, threadIdx.x)] = part[threadIdx.x] + part[threadIdx.x + 64];
     }
     __syncthreads();
     for (int e = threadIdx.x; e < kDN * kDN; e += kDThreads) {
@@ -267,72 +276,70 @@ __device__ __forceinline__ void lauum_lower_and_mirror(const DenseSmem &sm) {
 }
 
 // ---- per-iteration matrix-vector products ---------------------------------------------------------
-// Thread -> (output o, part h): o = (tid & 7) + 8 (tid >> 5), h = (tid >> 3) & 3.  The 8 lanes of a 128-bit
+// Thread -> (output o, half h): o = (tid & 7) + 8 (tid >> 4), h = (tid >> 3) & 1.  The 8 lanes of a 128-bit
 // shared-memory phase therefore work on 8 consecutive outputs with the same h (8 different bank groups,
-// thanks to the padded leading dimensions), and the four parts of one output sit 8 and 16 lanes apart
-// (combined with two __shfl_xor).
-__device__ __forceinline__ int out_index() { return (threadIdx.x & 7) + 8 * (threadIdx.x >> 5); }
-__device__ __forceinline__ int out_part() { return (threadIdx.x >> 3) & 3; }
-__device__ __forceinline__ double combine4(double s) {
-    s += __shfl_xor_sync(0xffffffffu, s, 8);
-    s += __shfl_xor_sync(0xffffffffu, s, 16);
-    return s;
-}
+// thanks to the padded leading dimensions), and the two halves of one output sit 8 lanes apart
+// (combined with one __shfl_xor(.., 8)).
+__device__ __forceinline__ int out_index() { return (threadIdx.x & 7) + 8 * (threadIdx.x >> 4); }
+__device__ __forceinline__ int out_half() { return (threadIdx.x >> 3) & 1; }
 
-// s_o = sum_i A[i, o] v_i,  o = 0..63   (all four lanes of an output return the full sum)
+// s_o = sum_i A[i, o] v_i,  o = 0..63   (both lanes of a pair return the full sum)
 __device__ __forceinline__ double at_times_v(const double *As, int mp, const double *v) {
-    const int o = out_index(), h = out_part();
-    const int qlen = mp >> 2;                                    // mp % 8 == 0 -> qlen even
-    const double2 *col = reinterpret_cast<const double2 *>(As + (size_t)(mp + 2) * o + h * qlen);
-    const double2 *vv = reinterpret_cast<const double2 *>(v + h * qlen);
+    const int o = out_index(), h = out_half();
+    const int hlen = mp >> 1;                                    // mp % 4 == 0 -> hlen even
+    const double2 *col = reinterpret_cast<const double2 *>(As + (size_t)(mp + 2) * o + h * hlen);
+    const double2 *vv = reinterpret_cast<const double2 *>(v + h * hlen);
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     int c = 0;
-    for (; c + 2 <= (qlen >> 1); c += 2) {
+    for (; c + 2 <= (hlen >> 1); c += 2) {
         const double2 a0 = col[c], b0 = vv[c], a1 = col[c + 1], b1 = vv[c + 1];
         s0 += a0.x * b0.x;
         s1 += a0.y * b0.y;
         s2 += a1.x * b1.x;
         s3 += a1.y * b1.y;
     }
-    if (c < (qlen >> 1)) {
+    if (c < (hlen >> 1)) {
         const double2 a0 = col[c], b0 = vv[c];
         s0 += a0.x * b0.x;
         s1 += a0.y * b0.y;
     }
-    return combine4((s0 + s1) + (s2 + s3));
+    double s = (s0 + s1) + (s2 + s3);
+    s += __shfl_xor_sync(0xffffffffu, s, 8);
+    return s;
 }
 
 // s_o = sum_j Kinv[o][j] v_j,  o = 0..63
 __device__ __forceinline__ double kinv_times_v(const double *Kf, const double *v) {
-    const int o = out_index(), h = out_part();
-    const double2 *row = reinterpret_cast<const double2 *>(Kf + pidx(o, 16 * h));
-    const double2 *vv = reinterpret_cast<const double2 *>(v + 16 * h);
+    const int o = out_index(), h = out_half();
+    const double2 *row = reinterpret_cast<const double2 *>(Kf + pidx(o, 32 * h));
+    const double2 *vv = reinterpret_cast<const double2 *>(v + 32 * h);
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
-    for (int c = 0; c < 8; c += 2) {
+    for (int c = 0; c < 16; c += 2) {
         const double2 a0 = row[c], b0 = vv[c], a1 = row[c + 1], b1 = vv[c + 1];
         s0 += a0.x * b0.x;
         s1 += a0.y * b0.y;
         s2 += a1.x * b1.x;
         s3 += a1.y * b1.y;
     }
-    return combine4((s0 + s1) + (s2 + s3));
+    double s = (s0 + s1) + (s2 + s3);
+    s += __shfl_xor_sync(0xffffffffu, s, 8);
+    return s;
 }
 
-// (A v)_i for the row pair (2p, 2p+1), p = out_index() < mp / 2: lane part h sums columns [16 h, 16 h + 16); after
-// the shuffles all four lanes hold both sums; parts 0 and 1 return rows 2p and 2p+1 (one row per thread),
-// parts 2 and 3 return row = mp (no row).
+// (A v)_i for the row pair (2p, 2p+1), p = out_index() < mp / 2: lane h sums columns [32 h, 32 h + 32); after
+// the shuffle both lanes hold both sums; returns the sum of row 2p + h (so every thread owns ONE row).
 __device__ __forceinline__ double a_times_v_row(const double *As, int mp, const double *v, int &row) {
-    const int p = out_index(), h = out_part();
+    const int p = out_index(), h = out_half();
     const int lda = mp + 2;
-    row = h < 2 ? 2 * p + h : mp;
+    row = 2 * p + h;
     double r0 = 0.0, r1 = 0.0;
     if (2 * p < mp) {
-        const double *base = As + 2 * p + (size_t)lda * (16 * h);
-        const double2 *vv = reinterpret_cast<const double2 *>(v + 16 * h);
+        const double *base = As + 2 * p + (size_t)lda * (32 * h);
+        const double2 *vv = reinterpret_cast<const double2 *>(v + 32 * h);
         double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
+#pragma unroll 4
+        for (int c = 0; c < 16; ++c) {
             const double2 xv = vv[c];
             const double2 m0 = *reinterpret_cast<const double2 *>(base + (size_t)lda * (2 * c));
             const double2 m1 = *reinterpret_cast<const double2 *>(base + (size_t)lda * (2 * c + 1));
@@ -344,8 +351,8 @@ __device__ __forceinline__ double a_times_v_row(const double *As, int mp, const 
         r0 = a0 + b0;
         r1 = a1 + b1;
     }
-    r0 = combine4(r0);
-    r1 = combine4(r1);
+    r0 += __shfl_xor_sync(0xffffffffu, r0, 8);
+    r1 += __shfl_xor_sync(0xffffffffu, r1, 8);
     return h == 0 ? r0 : r1;
 }
 
@@ -371,7 +378,7 @@ __device__ __forceinline__ void block_max(double (&v)[NV], double *red) {
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(kDThreads, 2) dense_batch_kernel(DenseBatchParams p) {
+__global__ void __launch_bounds__(kDThreads) dense_batch_kernel(DenseBatchParams p) {
     extern __shared__ __align__(16) unsigned char raw[];
     const DenseSmem sm = carve(raw, p.mp);
     const int n = p.n, m = p.m, mp = p.mp, lda = p.mp + 2;
@@ -379,7 +386,7 @@ __global__ void __launch_bounds__(kDThreads, 2) dense_batch_kernel(DenseBatchPar
     const double alpha = p.s.alpha, alpha1 = 1.0 - alpha, sigma = p.s.sigma;
     const double eps_admm = fmin(p.s.eps_abs, p.s.eps_rel) * 1e-2;
     unsigned long long tot_iters = 0, tot_rho = 0;
-    const int o = out_index(), h = out_part();
+    const int o = out_index(), h = out_half();
 
     __shared__ int next_b;
     for (;;) {
@@ -489,10 +496,10 @@ __global__ void __launch_bounds__(kDThreads, 2) dense_batch_kernel(DenseBatchPar
                 const double aty = at_times_v(sm.As, mp, sm.y);
                 double px = 0.0;
                 if (o < n) {
-                    const int ja = n * h / 4, jb = n * (h + 1) / 4;
+                    const int ja = h == 0 ? 0 : (n >> 1), jb = h == 0 ? (n >> 1) : n;
                     for (int j = ja; j < jb; ++j) px += __ldg(Pg + o + (size_t)n * j) * sm.x[j];
                 }
-                px = combine4(px);
+                px += __shfl_xor_sync(0xffffffffu, px, 8);
                 if (h == 0) {
                     nr[4] = fabs(px + sm.q[o] + aty);
                     nr[5] = nanmax(fabs(px), fabs(aty));
