@@ -106,9 +106,10 @@ int qpb200_batch_create(qpb200_batch **out, int64_t batch, int64_t n, int64_t m,
     d.eps_abs = s.eps_abs; d.eps_rel = s.eps_rel; d.rho = s.rho; d.sigma = s.sigma; d.alpha = s.alpha;
     d.rho_factor = s.rho_factor; d.pcg_eps = 0; d.pcg_rel_eps = 0; d.adaptive_rho = s.adaptive_rho;
     B.smem = dense_smem_bytes(B.mp);
-    QPB_CUDA_H(cudaFuncSetAttribute(dense_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.smem));
+    const void *kfn = B.mp == 96 ? (const void *)dense_batch_kernel<96> : (const void *)dense_batch_kernel<0>;
+    QPB_CUDA_H(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.smem));
     int per_sm = 0;
-    QPB_CUDA_H(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dense_batch_kernel, kDThreads, B.smem));
+    QPB_CUDA_H(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kDThreads, B.smem));
     if (per_sm < 1) { delete h; return fail(QPB200_ERR_CUDA, "dense batch kernel does not fit on an SM (smem %zu)", B.smem); }
     cudaDeviceProp prop;
     QPB_CUDA_H(cudaGetDeviceProperties(&prop, B.device));
@@ -130,7 +131,8 @@ int qpb200_batch_solve(qpb200_batch *h, double *X_inout, int32_t *flags, int64_t
     QPB_CUDA(cudaMemsetAsync(B.prm.factor_fail, 0, sizeof(int), B.stream));
     QPB_CUDA(cudaMemsetAsync(B.prm.queue, 0, 4 * sizeof(unsigned int), B.stream));
     QPB_CUDA(cudaEventRecord(B.ev0, B.stream));
-    dense_batch_kernel<<<B.grid, kDThreads, B.smem, B.stream>>>(B.prm);
+    if (B.mp == 96) dense_batch_kernel<96><<<B.grid, kDThreads, B.smem, B.stream>>>(B.prm);   // configs[2] shape: compile-time loops
+    else dense_batch_kernel<0><<<B.grid, kDThreads, B.smem, B.stream>>>(B.prm);
     QPB_CUDA(cudaGetLastError());
     QPB_CUDA(cudaEventRecord(B.ev1, B.stream));
     QPB_CUDA(cudaMemcpyAsync(X_inout, B.prm.X, nx * sizeof(double), cudaMemcpyDeviceToHost, B.stream));

@@ -284,21 +284,42 @@ __device__ __forceinline__ int out_index() { return (threadIdx.x & 7) + 8 * (thr
 __device__ __forceinline__ int out_half() { return (threadIdx.x >> 3) & 1; }
 
 // s_o = sum_i A[i, o] v_i,  o = 0..63   (both lanes of a pair return the full sum)
-__device__ __forceinline__ double at_times_v(const double *As, int mp, const double *v) {
+// MPC > 0: the padded row count is a compile-time constant (configs[2]: 96) -> fully unrolled, the 128-bit loads
+// of a batch are all issued before the first FMA that needs them (the kernel is shared-memory-latency bound).
+template <int MPC>
+__device__ __forceinline__ double at_times_v(const double *As, int mp_rt, const double *v) {
+    const int mp = MPC ? MPC : mp_rt;
     const int o = out_index(), h = out_half();
     const int hlen = mp >> 1;                                    // mp % 4 == 0 -> hlen even
     const double2 *col = reinterpret_cast<const double2 *>(As + (size_t)(mp + 2) * o + h * hlen);
     const double2 *vv = reinterpret_cast<const double2 *>(v + h * hlen);
+    const int nd2 = hlen >> 1;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     int c = 0;
-    for (; c + 2 <= (hlen >> 1); c += 2) {
+    if (MPC) {
+#pragma unroll
+        for (int cb = 0; cb + 8 <= nd2; cb += 8) {
+            double2 a[8], b[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { a[e] = col[cb + e]; b[e] = vv[cb + e]; }
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) {
+                s0 += a[e].x * b[e].x;
+                s1 += a[e].y * b[e].y;
+                s2 += a[e + 1].x * b[e + 1].x;
+                s3 += a[e + 1].y * b[e + 1].y;
+            }
+        }
+        c = nd2 & ~7;
+    }
+    for (; c + 2 <= nd2; c += 2) {
         const double2 a0 = col[c], b0 = vv[c], a1 = col[c + 1], b1 = vv[c + 1];
         s0 += a0.x * b0.x;
         s1 += a0.y * b0.y;
         s2 += a1.x * b1.x;
         s3 += a1.y * b1.y;
     }
-    if (c < (hlen >> 1)) {
+    if (c < nd2) {
         const double2 a0 = col[c], b0 = vv[c];
         s0 += a0.x * b0.x;
         s1 += a0.y * b0.y;
@@ -315,12 +336,17 @@ __device__ __forceinline__ double kinv_times_v(const double *Kf, const double *v
     const double2 *vv = reinterpret_cast<const double2 *>(v + 32 * h);
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
-    for (int c = 0; c < 16; c += 2) {
-        const double2 a0 = row[c], b0 = vv[c], a1 = row[c + 1], b1 = vv[c + 1];
-        s0 += a0.x * b0.x;
-        s1 += a0.y * b0.y;
-        s2 += a1.x * b1.x;
-        s3 += a1.y * b1.y;
+    for (int cb = 0; cb < 16; cb += 8) {
+        double2 a[8], b[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { a[e] = row[cb + e]; b[e] = vv[cb + e]; }
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+            s0 += a[e].x * b[e].x;
+            s1 += a[e].y * b[e].y;
+            s2 += a[e + 1].x * b[e + 1].x;
+            s3 += a[e + 1].y * b[e + 1].y;
+        }
     }
     double s = (s0 + s1) + (s2 + s3);
     s += __shfl_xor_sync(0xffffffffu, s, 8);
@@ -329,7 +355,9 @@ __device__ __forceinline__ double kinv_times_v(const double *Kf, const double *v
 
 // (A v)_i for the row pair (2p, 2p+1), p = out_index() < mp / 2: lane h sums columns [32 h, 32 h + 32); after
 // the shuffle both lanes hold both sums; returns the sum of row 2p + h (so every thread owns ONE row).
-__device__ __forceinline__ double a_times_v_row(const double *As, int mp, const double *v, int &row) {
+template <int MPC>
+__device__ __forceinline__ double a_times_v_row(const double *As, int mp_rt, const double *v, int &row) {
+    const int mp = MPC ? MPC : mp_rt;
     const int p = out_index(), h = out_half();
     const int lda = mp + 2;
     row = 2 * p + h;
@@ -338,15 +366,22 @@ __device__ __forceinline__ double a_times_v_row(const double *As, int mp, const 
         const double *base = As + 2 * p + (size_t)lda * (32 * h);
         const double2 *vv = reinterpret_cast<const double2 *>(v + 32 * h);
         double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
-#pragma unroll 4
-        for (int c = 0; c < 16; ++c) {
-            const double2 xv = vv[c];
-            const double2 m0 = *reinterpret_cast<const double2 *>(base + (size_t)lda * (2 * c));
-            const double2 m1 = *reinterpret_cast<const double2 *>(base + (size_t)lda * (2 * c + 1));
-            a0 += m0.x * xv.x;
-            a1 += m0.y * xv.x;
-            b0 += m1.x * xv.y;
-            b1 += m1.y * xv.y;
+#pragma unroll
+        for (int cb = 0; cb < 16; cb += 4) {
+            double2 xv[4], m0[4], m1[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                xv[e] = vv[cb + e];
+                m0[e] = *reinterpret_cast<const double2 *>(base + (size_t)lda * (2 * (cb + e)));
+                m1[e] = *reinterpret_cast<const double2 *>(base + (size_t)lda * (2 * (cb + e) + 1));
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                a0 += m0[e].x * xv[e].x;
+                a1 += m0[e].y * xv[e].x;
+                b0 += m1[e].x * xv[e].y;
+                b1 += m1[e].y * xv[e].y;
+            }
         }
         r0 = a0 + b0;
         r1 = a1 + b1;
@@ -378,10 +413,11 @@ __device__ __forceinline__ void block_max(double (&v)[NV], double *red) {
     __syncthreads();
 }
 
+template <int MPC>
 __global__ void __launch_bounds__(kDThreads) dense_batch_kernel(DenseBatchParams p) {
     extern __shared__ __align__(16) unsigned char raw[];
     const DenseSmem sm = carve(raw, p.mp);
-    const int n = p.n, m = p.m, mp = p.mp, lda = p.mp + 2;
+    const int n = p.n, m = p.m, mp = MPC ? MPC : p.mp, lda = mp + 2;
     const int tid = threadIdx.x;
     const double alpha = p.s.alpha, alpha1 = 1.0 - alpha, sigma = p.s.sigma;
     const double eps_admm = fmin(p.s.eps_abs, p.s.eps_rel) * 1e-2;
@@ -448,7 +484,7 @@ __global__ void __launch_bounds__(kDThreads) dense_batch_kernel(DenseBatchParams
             __syncthreads();
             // ---- rhs = sigma x - q + A' w,  w = rho z - y      (LinearSystemSolvers.jl:37-38 reduced)
             {
-                const double s = at_times_v(sm.As, mp, sm.w);
+                const double s = at_times_v<MPC>(sm.As, mp, sm.w);
                 if (h == 0) sm.rhs[o] = sigma * sm.x[o] - sm.q[o] + s;
             }
             __syncthreads();
@@ -468,7 +504,7 @@ __global__ void __launch_bounds__(kDThreads) dense_batch_kernel(DenseBatchParams
             // ---- z~ = A x~, then the z / y update (:59-61), one row per thread
             {
                 int row;
-                const double zt = a_times_v_row(sm.As, mp, sm.xt, row);
+                const double zt = a_times_v_row<MPC>(sm.As, mp, sm.xt, row);
                 if (row < m) {
                     const double z_old = sm.z[row], y_old = sm.y[row];
                     const double zr = alpha * zt + alpha1 * z_old;
@@ -486,14 +522,14 @@ __global__ void __launch_bounds__(kDThreads) dense_batch_kernel(DenseBatchParams
                 double nr[6] = {dx, dz, 0.0, 0.0, 0.0, 0.0};   // dx dz rp max(|Ax|,|z|) rd max(|Px|,|A'y|)
                 {
                     int row;
-                    const double ax = a_times_v_row(sm.As, mp, sm.x, row);
+                    const double ax = a_times_v_row<MPC>(sm.As, mp, sm.x, row);
                     if (row < m) {
                         const double zi = sm.z[row];
                         nr[2] = fabs(ax - zi);
                         nr[3] = nanmax(fabs(ax), fabs(zi));
                     }
                 }
-                const double aty = at_times_v(sm.As, mp, sm.y);
+                const double aty = at_times_v<MPC>(sm.As, mp, sm.y);
                 double px = 0.0;
                 if (o < n) {
                     const int ja = h == 0 ? 0 : (n >> 1), jb = h == 0 ? (n >> 1) : n;
