@@ -236,3 +236,55 @@ def test_pcg_reduces_residual_of_kkt_system(lib):
     import scipy.sparse.linalg as spla
     xt = spla.spsolve(K, -q)
     assert np.max(np.abs(x - alpha * xt)) <= 1e-8 * (1 + np.max(np.abs(xt)))
+
+
+def test_one_based_indices_like_julia(lib):
+    """The Julia shim passes SparseMatrixCSC fields as they are (1-based Int64, index_base = 1): the raw C-ABI
+    call with shifted arrays must give bit-identical results to the 0-based call."""
+    import ctypes as C
+    from quadraticprogramsolver_b200 import _lib
+    S = _solver()
+    P, q, A, l, u = config_cfg1(1236)
+    n, m = P.shape[0], A.shape[0]
+    Pp, Pi, Pv = S.csc_arrays_int64(P)
+    Ap, Ai, Av = S.csc_arrays_int64(A)
+    xs = []
+    for base in (0, 1):
+        h = C.c_void_p()
+        s = S.make_settings(epsPcg=1e-10)
+        _lib.check(lib.qpb200_create(C.byref(h), n, m, S._p64(Pp + base), S._p64(Pi + base), S._pd(Pv), S._p64(Ap + base),
+                                     S._p64(Ai + base), S._pd(Av), S._pd(q), S._pd(l), S._pd(u), C.byref(s), base))
+        x = np.zeros(n)
+        info = _lib.Info()
+        _lib.check(lib.qpb200_solve(h, S._pd(x), None, None, C.byref(info)))
+        lib.qpb200_destroy(h)
+        xs.append((x, info.conv_flag, info.iterations))
+    assert np.array_equal(xs[0][0], xs[1][0]) and xs[0][1:] == xs[1][1:]
+
+
+def test_update_settings_and_raw_array_call(lib):
+    """qpb200_update_settings on a live handle (rho / adaptive rho change) equals a fresh handle; the raw CSC
+    array call sequence of julia/QPB200.jl (solve_csc_arrays) equals the object wrapper."""
+    S = _solver()
+    P, q, A, l, u = config_cfg1(1234)
+    n, m = P.shape[0], A.shape[0]
+    kw2 = dict(rho=0.1, adptRho=True, epsAbs=1e-7, epsRel=1e-7, numIterations=50000, epsPcg=1e-11)
+    with S.QPB200Solver(P, q, A, l, u, epsPcg=1e-10) as s:
+        x1 = np.zeros(n); s.solve(x1)
+        s.update_settings(**kw2)
+        x2 = np.zeros(n); f2 = s.solve(x2); i2 = dict(s.info)
+    x3 = np.zeros(n)
+    f3, i3 = S.solve_csc_arrays(n, m, S.csc_arrays_int64(P), q, S.csc_arrays_int64(A), l, u, x3, **kw2)
+    assert int(f2) == int(f3) and i2["iterations"] == i3["iterations"] and i2["rho_updates"] == i3["rho_updates"]
+    assert np.array_equal(x2, x3) and not np.array_equal(x1, x2)
+
+
+def test_dense_batch_is_bitwise_reproducible(lib):
+    """Dynamic work queue, but every QP is solved by one CTA with fixed-order sums: results do not depend on
+    which CTA picks which problem."""
+    S = _solver()
+    from quadraticprogramsolver_b200.problems import config_cfg3_batch
+    P, q, A, l, u = config_cfg3_batch(700, 64, 96, seed=4)
+    X1, f1, i1, _ = S.SolveQuadraticProgramBatch(P, q, A, l, u)
+    X2, f2, i2, _ = S.SolveQuadraticProgramBatch(P, q, A, l, u)
+    assert np.array_equal(X1, X2) and np.array_equal(f1, f2) and np.array_equal(i1, i2)
