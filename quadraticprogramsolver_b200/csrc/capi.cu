@@ -1,5 +1,8 @@
 // capi.cu -- the extern "C" surface declared in include/qpb200.h.
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -84,7 +87,14 @@ int qpb200_update_settings(qpb200_handle *h, const qpb200_settings *settings) {
     return h->solver.settings_to_dev(*settings);
 }
 
-void qpb200_destroy(qpb200_handle *h) { delete h; }
+void qpb200_destroy(qpb200_handle *h) {
+    if (!h) return;
+    const auto t0 = std::chrono::steady_clock::now();
+    delete h;
+    if (getenv("QPB200_TIMING"))
+        fprintf(stderr, "[qpb200_destroy] %.1f ms\n",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+}
 
 int qpb200_apply(qpb200_handle *h, int32_t which, const double *x, double *y) {
     if (!h) return qpb::fail(QPB200_ERR_ARG, "qpb200_apply: handle is NULL");

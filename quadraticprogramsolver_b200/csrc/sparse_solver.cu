@@ -283,6 +283,7 @@ int SparseSolver::launch_admm() {
 
 int SparseSolver::solve(double *x_inout, double *z_out, double *y_out, qpb200_info *info) {
     if (!x_inout) return fail(QPB200_ERR_ARG, "qpb200_solve: x_inout is NULL");
+    const auto wall0 = std::chrono::steady_clock::now();
     QPB_CUDA(cudaSetDevice(device));
     int rc = reset_state(x_inout);
     if (rc) return rc;
@@ -312,6 +313,9 @@ int SparseSolver::solve(double *x_inout, double *z_out, double *y_out, qpb200_in
         info->setup_ms = setup_ms;
         info->kernel_launches = 1;
     }
+    if (getenv("QPB200_TIMING"))
+        fprintf(stderr, "[qpb200_solve] device %.1f ms, wall %.1f ms\n", ms,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count());
     return QPB200_OK;
 }
 
