@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstring>
+#include <mutex>
 #include <thread>
 
 namespace qpb {
@@ -227,6 +228,106 @@ bool all_finite(const double *v, size_t count) {
         if (s != 0.0) bad = 1;
     }, 1 << 18);
     return bad == 0;
+}
+
+// ---- block caches -----------------------------------------------------------------------------------
+namespace {
+struct BlockCache {
+    std::mutex mu;
+    std::vector<std::pair<void *, size_t>> blocks;   // (pointer, capacity)
+    size_t total = 0;
+    int device = -1;                                  // device cache: valid for one device at a time
+};
+size_t cache_limit() {
+    static size_t lim = [] {
+        const char *e = getenv("QPB200_CACHE_MB");
+        return (size_t)(e ? atoll(e) : 4096) << 20;
+    }();
+    return lim;
+}
+constexpr size_t kCacheMinBlock = 1 << 20;   // only blocks >= 1 MB are worth keeping
+BlockCache &dev_cache() { static BlockCache c; return c; }
+BlockCache &host_cache() { static BlockCache c; return c; }
+
+void *take(BlockCache &c, size_t bytes, size_t *cap) {
+    std::lock_guard<std::mutex> g(c.mu);
+    size_t best = (size_t)-1, bi = 0;
+    for (size_t i = 0; i < c.blocks.size(); ++i) {
+        const size_t k = c.blocks[i].second;
+        if (k >= bytes && k <= bytes + bytes / 4 + (1 << 20) && k < best) { best = k; bi = i; }
+    }
+    if (best == (size_t)-1) return nullptr;
+    void *p = c.blocks[bi].first;
+    *cap = best;
+    c.total -= best;
+    c.blocks.erase(c.blocks.begin() + (long)bi);
+    return p;
+}
+bool give(BlockCache &c, void *p, size_t cap) {
+    if (cap < kCacheMinBlock) return false;
+    std::lock_guard<std::mutex> g(c.mu);
+    if (c.total + cap > cache_limit()) return false;
+    c.blocks.push_back({p, cap});
+    c.total += cap;
+    return true;
+}
+}  // namespace
+
+cudaError_t cached_device_alloc(void **p, size_t bytes, size_t *capacity) {
+    int dev = -1;
+    cudaGetDevice(&dev);
+    BlockCache &c = dev_cache();
+    {
+        std::lock_guard<std::mutex> g(c.mu);
+        if (c.device != dev) {          // cached blocks belong to another device: drop them
+            for (auto &b : c.blocks) cudaFree(b.first);
+            c.blocks.clear();
+            c.total = 0;
+            c.device = dev;
+        }
+    }
+    if (bytes >= kCacheMinBlock) {
+        void *q = take(c, bytes, capacity);
+        if (q) { *p = q; return cudaSuccess; }
+    }
+    *capacity = bytes;
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) {
+        // out of memory with blocks parked in the cache: release them and retry once
+        cudaGetLastError();
+        {
+            std::lock_guard<std::mutex> g(c.mu);
+            for (auto &b : c.blocks) cudaFree(b.first);
+            c.blocks.clear();
+            c.total = 0;
+        }
+        e = cudaMalloc(p, bytes);
+    }
+    return e;
+}
+
+void cached_device_free(void *p, size_t capacity) {
+    if (!p) return;
+    int dev = -1;
+    cudaGetDevice(&dev);
+    BlockCache &c = dev_cache();
+    if (dev == c.device && give(c, p, capacity)) return;
+    cudaFree(p);
+}
+
+void *cached_host_alloc(size_t bytes, size_t *capacity) {
+    if (bytes >= kCacheMinBlock) {
+        void *q = take(host_cache(), bytes, capacity);
+        if (q) return q;
+    }
+    *capacity = bytes;
+    return malloc(bytes);
+}
+
+void cached_host_free(void *p, size_t capacity) {
+    if (!p) return;
+    if (give(host_cache(), p, capacity)) return;
+    free(p);
 }
 
 int check_device(int device) {

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <functional>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "qpb200.h"
@@ -27,16 +28,27 @@ int fail(int code, const char *fmt, ...);
     } while (0)
 
 // Owns device allocations of one handle.
+// Large blocks (device and host) are recycled through small process-wide caches: a caller that creates and
+// destroys handles repeatedly (MPC-style re-solves, the end-to-end benchmark) otherwise pays cudaMalloc/cudaFree
+// of ~1 GB (25-150 ms, measured) and first-touch page faults of ~0.5 GB of host staging per create.
+// Bounded (QPB200_CACHE_MB, default 4096 MB per kind; 0 disables); blocks are reused only for requests of
+// similar size.
+cudaError_t cached_device_alloc(void **p, size_t bytes, size_t *capacity);
+void cached_device_free(void *p, size_t capacity);
+void *cached_host_alloc(size_t bytes, size_t *capacity);
+void cached_host_free(void *p, size_t capacity);
+
 struct DeviceArena {
-    std::vector<void *> ptrs;
+    std::vector<std::pair<void *, size_t>> ptrs;
     size_t bytes = 0;
     template <class T>
     cudaError_t alloc(T **out, size_t count, bool zero = false) {
         void *p = nullptr;
         const size_t nb = (count > 0 ? count : 1) * sizeof(T);
-        cudaError_t e = cudaMalloc(&p, nb);
+        size_t cap = 0;
+        cudaError_t e = cached_device_alloc(&p, nb, &cap);
         if (e != cudaSuccess) return e;
-        ptrs.push_back(p);
+        ptrs.push_back({p, cap});
         bytes += nb;
         if (zero) {
             e = cudaMemset(p, 0, nb);
@@ -46,7 +58,7 @@ struct DeviceArena {
         return cudaSuccess;
     }
     void release() {
-        for (void *p : ptrs) cudaFree(p);
+        for (auto &pc : ptrs) cached_device_free(pc.first, pc.second);
         ptrs.clear();
         bytes = 0;
     }
@@ -57,14 +69,14 @@ struct DeviceArena {
 template <class T>
 struct PodBuf {
     T *p = nullptr;
-    size_t n = 0;
+    size_t n = 0, cap = 0;
     PodBuf() = default;
     PodBuf(const PodBuf &) = delete;
     PodBuf &operator=(const PodBuf &) = delete;
-    ~PodBuf() { free(p); }
+    ~PodBuf() { if (p) cached_host_free(p, cap); }
     void resize(size_t k) {
-        free(p);
-        p = static_cast<T *>(malloc((k > 0 ? k : 1) * sizeof(T)));
+        if (p) cached_host_free(p, cap);
+        p = static_cast<T *>(cached_host_alloc((k > 0 ? k : 1) * sizeof(T), &cap));
         n = k;
     }
     T *data() { return p; }
