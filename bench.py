@@ -305,7 +305,11 @@ def run_b200(args):
                                           "copies_destroy_host": 1e3 * e2e_wall / e2e_steps - (e2e_create_ms + e2e_solve_ms) / e2e_steps}},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "admm_kernel (persistent; 1 launch per step)" if world == 1 else
+                     "traffic": None,
+                     "traffic_ncu": {"note": "a 100-iteration launch is too long to replay under ncu; captured instead: the same kernel "
+                                     "for 1 ADMM iteration = 48 CG iterations (profiles/r1b_ncu_full_cfg5_key_metrics.csv)",
+                                     "dram_bytes_per_launch": 32.37e9, "algorithmic_bytes_per_launch": 34.7e9, "ratio": 0.93},
+                     "kernel": "admm_kernel (persistent; 1 launch per step)" if world == 1 else
                      "admm_dist_kernel segments (per-GPU GB/s)", "peak_source": peak_src,
                      "spmv": spmv, "note": "cfg5's uniformly random columns make every 8-byte gather of x move a 32-byte L2 "
                      "sector; see DESIGN.md (L2-sector bound) and profiles/"},
