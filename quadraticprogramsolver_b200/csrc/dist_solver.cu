@@ -337,15 +337,19 @@ static int peer_init(SparseSolver &s, DistContext &d) {
     s.prob.UT = d.region + off_UT;
     s.prob.XG = d.region + off_XG;
     pd.info = s.prob.info;
+    pd.wslice = d.buf.wbuf;
     pd.dbg = nullptr;
     if (getenv("QPB200_TIMING")) QPB_CUDA(s.arena.alloc(&pd.dbg, 16, true));
     QPB_CUDA(s.arena.alloc(&d.tiny, 2, true));
     for (const void *fn : {(const void *)admm_peer_kernel<0, false>, (const void *)admm_peer_kernel<0, true>,
                            (const void *)admm_peer_kernel<1, false>, (const void *)admm_peer_kernel<1, true>,
                            (const void *)admm_peer_kernel<2, false>, (const void *)admm_peer_kernel<2, true>,
-                           (const void *)admm_peer_sliced_kernel<0, false>, (const void *)admm_peer_sliced_kernel<0, true>,
-                           (const void *)admm_peer_sliced_kernel<1, false>, (const void *)admm_peer_sliced_kernel<1, true>,
-                           (const void *)admm_peer_sliced_kernel<2, false>, (const void *)admm_peer_sliced_kernel<2, true>}) {
+                           (const void *)admm_peer_sliced_kernel<0, false, false>, (const void *)admm_peer_sliced_kernel<0, true, false>,
+                           (const void *)admm_peer_sliced_kernel<1, false, false>, (const void *)admm_peer_sliced_kernel<1, true, false>,
+                           (const void *)admm_peer_sliced_kernel<2, false, false>, (const void *)admm_peer_sliced_kernel<2, true, false>,
+                           (const void *)admm_peer_sliced_kernel<0, false, true>, (const void *)admm_peer_sliced_kernel<0, true, true>,
+                           (const void *)admm_peer_sliced_kernel<1, false, true>, (const void *)admm_peer_sliced_kernel<1, true, true>,
+                           (const void *)admm_peer_sliced_kernel<2, false, true>, (const void *)admm_peer_sliced_kernel<2, true, true>}) {
         QPB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpmvSmem)));
         int per_sm = 0;
         QPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, sizeof(SpmvSmem)));
@@ -373,13 +377,20 @@ int peer_solve(SparseSolver &s, DistContext &d, double *x_inout, double *z_out, 
         const void *fns[3][2] = {{(const void *)admm_peer_kernel<0, false>, (const void *)admm_peer_kernel<0, true>},
                                  {(const void *)admm_peer_kernel<1, false>, (const void *)admm_peer_kernel<1, true>},
                                  {(const void *)admm_peer_kernel<2, false>, (const void *)admm_peer_kernel<2, true>}};
-        const void *fns_sliced[3][2] = {{(const void *)admm_peer_sliced_kernel<0, false>, (const void *)admm_peer_sliced_kernel<0, true>},
-                                        {(const void *)admm_peer_sliced_kernel<1, false>, (const void *)admm_peer_sliced_kernel<1, true>},
-                                        {(const void *)admm_peer_sliced_kernel<2, false>, (const void *)admm_peer_sliced_kernel<2, true>}};
+        const void *fns_sliced[3][2] = {{(const void *)admm_peer_sliced_kernel<0, false, false>, (const void *)admm_peer_sliced_kernel<0, true, false>},
+                                        {(const void *)admm_peer_sliced_kernel<1, false, false>, (const void *)admm_peer_sliced_kernel<1, true, false>},
+                                        {(const void *)admm_peer_sliced_kernel<2, false, false>, (const void *)admm_peer_sliced_kernel<2, true, false>}};
+        const void *fns_cg[3][2] = {{(const void *)admm_peer_sliced_kernel<0, false, true>, (const void *)admm_peer_sliced_kernel<0, true, true>},
+                                    {(const void *)admm_peer_sliced_kernel<1, false, true>, (const void *)admm_peer_sliced_kernel<1, true, true>},
+                                    {(const void *)admm_peer_sliced_kernel<2, false, true>, (const void *)admm_peer_sliced_kernel<2, true, true>}};
         // default: sliced CG vectors; QPB200_PEER_SLICED=0 selects the replicated variant (A/B)
         const char *e = getenv("QPB200_PEER_SLICED");
         const bool sliced = !(e && atoi(e) == 0);
-        const void *fn = sliced ? fns_sliced[s.loader][s.use_pre ? 1 : 0] : fns[s.loader][s.use_pre ? 1 : 0];
+        // QPB200_PEER_CG=1: Chronopoulos-Gear arrangement (one reduction per CG iteration) of the sliced kernel
+        const char *ecg = getenv("QPB200_PEER_CG");
+        const bool cgv = sliced && ecg && atoi(ecg) == 1;
+        const void *fn = cgv ? fns_cg[s.loader][s.use_pre ? 1 : 0]
+                             : (sliced ? fns_sliced[s.loader][s.use_pre ? 1 : 0] : fns[s.loader][s.use_pre ? 1 : 0]);
         QPB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(s.grid), dim3(kThreads), args, sizeof(SpmvSmem), s.stream));
     }
     QPB_CUDA(cudaEventRecord(s.ev1, s.stream));

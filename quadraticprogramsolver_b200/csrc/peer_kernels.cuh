@@ -33,6 +33,7 @@ struct PeerDev {
     int grid_max;
     AdmmInfoDev *info;
     unsigned long long *dbg;         // 16 phase timers in ns (block 0 / thread 0), printed with QPB200_TIMING
+    double *wslice;                  // n doubles (local): w = K z of the Chronopoulos-Gear variant
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
@@ -458,7 +459,9 @@ __device__ __forceinline__ void peer_barrier_sum(const GridSync &gs, SyncState &
     sys_barrier_impl<NV>(gs, st, pd, xs, v, sm, parity);
 }
 
-template <int TMA, bool PRE>
+// CGV = true: Chronopoulos-Gear arrangement of the same PCG (one fused reduction per iteration, no all-gather of
+// the search direction): see the loop below.
+template <int TMA, bool PRE, bool CGV>
 __global__ void __launch_bounds__(kThreads, kMinCtas) admm_peer_sliced_kernel(SparseProblemDev p, PeerDev pd) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SpmvSmem &sm = *reinterpret_cast<SpmvSmem *>(smem_raw);
@@ -553,18 +556,80 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) admm_peer_sliced_kernel(Sp
             const double rj = sigma * (x[j] - xt[j]) - p.q[j] - reduced_w(j);
             p.r[j] = rj;
             const double zj = PRE ? p.dinv[j] * rj : rj;
-            if (PRE) p.zp[j] = zj;
+            if (PRE && !CGV) p.zp[j] = zj;
 #pragma unroll
             for (int q = 0; q < kMaxPeers; ++q)
                 if (q < R) udst[q][j] = zj;
             acc[0] += rj * rj;
             acc[1] += rj * zj;
         }
-        peer_barrier_sum<2>(p.gs, st, pd, xs, acc, sm, parity);      // also publishes the u slices
-        double residual = sqrt(acc[0]);
-        double rz = acc[1];
-        const double tol = fmax(p.s.pcg_rel_eps * residual, p.s.pcg_eps);
+        double residual, tol;
         long long k = 0;
+        if (CGV) {
+            // ---- Chronopoulos-Gear PCG: u holds z = Pl \ r (the only gathered CG vector), p.zp holds the search
+            //      direction, p.c holds s = K p, pd.wslice holds w = K z; gamma = r.z, delta = z.w and |r|^2 come out of
+            //      ONE reduction per iteration.  Same iterates as the standard recurrence in exact arithmetic; one
+            //      extra operator application per solve (the w of the converged residual is not used).
+            sys_barrier<true>(p.gs, st, pd, xs);                       // z slices published
+            double gam = 0.0, a_cg = 0.0;
+            bool first = true;
+            for (;;) {
+                tick(6);
+                spmv_A_t();
+                grid_barrier(p.gs, st);
+                tick(0);
+                spmv_H_partial(p.UT);
+                tick(1);
+                sys_barrier<false>(p.gs, st, pd, xs);
+                double d3[3] = {0.0, 0.0, 0.0};                        // r.z, z.w, r.r on my slice
+                for (int j = s0 + gtid; j < s1; j += gstride) {
+                    const double zj = u[j], rj = p.r[j];
+                    const double wj = reduced_w(j) + sigma * zj;
+                    pd.wslice[j] = wj;
+                    d3[0] += rj * zj;
+                    d3[1] += zj * wj;
+                    d3[2] += rj * rj;
+                }
+                peer_barrier_sum<3>(p.gs, st, pd, xs, d3, sm, parity);
+                tick(2);
+                residual = sqrt(d3[2]);
+                if (first) tol = fmax(p.s.pcg_rel_eps * residual, p.s.pcg_eps);
+                if (!first) ++k;
+                if (!(k < p.s.pcg_max_iter && !(residual <= tol))) break;
+                double beta = 0.0;
+                if (first) {
+                    a_cg = d3[0] / d3[1];
+                } else {
+                    beta = d3[0] / gam;
+                    const double den = d3[1] - beta * d3[0] / a_cg;
+                    if (!(den > 0.0)) break;
+                    a_cg = d3[0] / den;
+                }
+                if (first && !(d3[1] > 0.0)) break;
+                gam = d3[0];
+                first = false;
+                // p = z + beta p ; s = w + beta s ; x~ += a p ; r -= a s ; z = Pl \ r -> pushed to everyone
+                for (int j = s0 + gtid; j < s1; j += gstride) {
+                    const double pj = u[j] + beta * p.zp[j];
+                    const double sj = pd.wslice[j] + beta * p.c[j];
+                    p.zp[j] = pj;
+                    p.c[j] = sj;
+                    xt[j] += a_cg * pj;
+                    const double rj = p.r[j] - a_cg * sj;
+                    p.r[j] = rj;
+                    const double zj = PRE ? p.dinv[j] * rj : rj;
+#pragma unroll
+                    for (int q = 0; q < kMaxPeers; ++q)
+                        if (q < R) udst[q][j] = zj;
+                }
+                sys_barrier<true>(p.gs, st, pd, xs);
+                tick(4);
+            }
+        } else {
+        peer_barrier_sum<2>(p.gs, st, pd, xs, acc, sm, parity);      // also publishes the u slices
+        residual = sqrt(acc[0]);
+        double rz = acc[1];
+        tol = fmax(p.s.pcg_rel_eps * residual, p.s.pcg_eps);
         while (k < p.s.pcg_max_iter && !(residual <= tol)) {
             tick(6);
             spmv_A_t();
@@ -612,6 +677,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) admm_peer_sliced_kernel(Sp
             }
             rz = rz_new;
             tick(5);
+        }
         }
         pcg_total += k;
         if (k >= p.s.pcg_max_iter && !(residual <= tol)) ++pcg_maxed;
