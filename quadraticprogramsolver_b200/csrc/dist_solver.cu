@@ -386,9 +386,10 @@ int peer_solve(SparseSolver &s, DistContext &d, double *x_inout, double *z_out, 
         // default: sliced CG vectors; QPB200_PEER_SLICED=0 selects the replicated variant (A/B)
         const char *e = getenv("QPB200_PEER_SLICED");
         const bool sliced = !(e && atoi(e) == 0);
-        // QPB200_PEER_CG=1: Chronopoulos-Gear arrangement (one reduction per CG iteration) of the sliced kernel
+        // default: Chronopoulos-Gear arrangement of the sliced kernel (one fused reduction per CG iteration);
+        // QPB200_PEER_CG=0 selects the reference recurrence (three reductions per iteration) for A/B runs
         const char *ecg = getenv("QPB200_PEER_CG");
-        const bool cgv = sliced && ecg && atoi(ecg) == 1;
+        const bool cgv = sliced && !(ecg && atoi(ecg) == 0);
         const void *fn = cgv ? fns_cg[s.loader][s.use_pre ? 1 : 0]
                              : (sliced ? fns_sliced[s.loader][s.use_pre ? 1 : 0] : fns[s.loader][s.use_pre ? 1 : 0]);
         QPB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(s.grid), dim3(kThreads), args, sizeof(SpmvSmem), s.stream));
