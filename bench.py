@@ -195,7 +195,7 @@ def run_b200(args):
 
     # ---- device-resident arm ------------------------------------------------------------------
     # N = 1: the single-GPU persistent kernel.  N > 1: the SAME QP row-partitioned over the N ranks
-    # (rows of A / columns of P per rank, NCCL all-reduce of the n-vector partial sums) -> strong scaling.
+    # (rows of A / columns of P per rank, n-vector partial sums reduced in-kernel over NVLink) -> strong scaling.
     if world == 1:
         s = S.QPB200Solver(P, q, A, l, u, **kw)
         presliced = None
@@ -295,7 +295,7 @@ def run_b200(args):
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": desc, "iters_per_step": ITERS, "settings": "reference defaults (rho=1, sigma=1e-6, alpha=1.6, "
                    "eps 1e-6, check every 25), Jacobi-PCG abstol 1e-6", "parallelism": "1 GPU" if world == 1 else
-                   f"one QP row-partitioned over {world} GPUs (rows of A / columns of P per rank, ncclAllReduce of n-vectors)", "l2": "matrix streams (0.55 GB per operator application) exceed the 126 MB L2; "
+                   f"one QP row-partitioned over {world} GPUs (rows of A / columns of P per rank; one persistent kernel per GPU, reduce-scatter / all-gather of the n-vectors in-kernel over NVLink peer memory)", "l2": "matrix streams (0.55 GB per operator application) exceed the 126 MB L2; "
                    "stand-alone SpMV timings flush L2 between launches", "conv_flag": flag,
                    "pcg_iters_per_step": pcg / max(1, args.steps), "gen_s": round(gen_s, 1)},
         "clocks": clocks,
@@ -310,7 +310,7 @@ def run_b200(args):
                                      "for 1 ADMM iteration = 48 CG iterations (profiles/r1b_ncu_full_cfg5_key_metrics.csv)",
                                      "dram_bytes_per_launch": 32.37e9, "algorithmic_bytes_per_launch": 34.7e9, "ratio": 0.93},
                      "kernel": "admm_kernel (persistent; 1 launch per step)" if world == 1 else
-                     "admm_dist_kernel segments (per-GPU GB/s)", "peak_source": peak_src,
+                     "admm_peer_sliced_kernel (persistent; 1 launch per GPU per step; per-GPU GB/s)", "peak_source": peak_src,
                      "spmv": spmv, "note": "cfg5's uniformly random columns make every 8-byte gather of x move a 32-byte L2 "
                      "sector; see DESIGN.md (L2-sector bound) and profiles/"},
         "cg_iters_per_s": pcg / (dev_ms * 1e-3),
