@@ -21,8 +21,8 @@ int qpb200_device_count(void) {
     if (e != cudaSuccess) return qpb::fail(QPB200_ERR_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
     int ok = 0;
     for (int d = 0; d < count; ++d) {
-        cudaDeviceProp p;
-        if (cudaGetDeviceProperties(&p, d) == cudaSuccess && p.major == 10) ++ok;
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ++ok;
     }
     return ok;
 }

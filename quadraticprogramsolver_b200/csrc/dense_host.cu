@@ -111,9 +111,9 @@ int qpb200_batch_create(qpb200_batch **out, int64_t batch, int64_t n, int64_t m,
     int per_sm = 0;
     QPB_CUDA_H(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kDThreads, B.smem));
     if (per_sm < 1) { delete h; return fail(QPB200_ERR_CUDA, "dense batch kernel does not fit on an SM (smem %zu)", B.smem); }
-    cudaDeviceProp prop;
-    QPB_CUDA_H(cudaGetDeviceProperties(&prop, B.device));
-    B.grid = (int)std::min<int64_t>(batch, (int64_t)prop.multiProcessorCount * per_sm);
+    int num_sms = 0;
+    QPB_CUDA_H(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, B.device));
+    B.grid = (int)std::min<int64_t>(batch, (int64_t)num_sms * per_sm);
     QPB_CUDA_H(cudaStreamSynchronize(B.stream));
     B.setup_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     *out = h;

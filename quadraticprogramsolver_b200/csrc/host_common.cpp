@@ -3,7 +3,10 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <thread>
@@ -263,8 +266,8 @@ void *take(BlockCache &c, size_t bytes, size_t *cap) {
     c.blocks.erase(c.blocks.begin() + (long)bi);
     return p;
 }
-bool give(BlockCache &c, void *p, size_t cap) {
-    if (cap < kCacheMinBlock) return false;
+bool give(BlockCache &c, void *p, size_t cap, size_t min_block) {
+    if (cap < min_block) return false;
     std::lock_guard<std::mutex> g(c.mu);
     if (c.total + cap > cache_limit()) return false;
     c.blocks.push_back({p, cap});
@@ -286,9 +289,9 @@ cudaError_t cached_device_alloc(void **p, size_t bytes, size_t *capacity) {
             c.device = dev;
         }
     }
-    if (bytes >= kCacheMinBlock) {
-        void *q = take(c, bytes, capacity);
-        if (q) { *p = q; return cudaSuccess; }
+    if (void *q = take(c, bytes, capacity)) {
+        *p = q;
+        return cudaSuccess;
     }
     *capacity = bytes;
     cudaError_t e = cudaMalloc(p, bytes);
@@ -311,8 +314,14 @@ void cached_device_free(void *p, size_t capacity) {
     int dev = -1;
     cudaGetDevice(&dev);
     BlockCache &c = dev_cache();
-    if (dev == c.device && give(c, p, capacity)) return;
+    if (dev == c.device && give(c, p, capacity, 0)) return;   // small blocks too: a real cudaFree can stall for tens of ms
+    static const bool timing = getenv("QPB200_TIMING") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     cudaFree(p);
+    if (timing)
+        fprintf(stderr, "[qpb200 cache] cudaFree of %.2f MB took %.2f ms (cache holds %.0f MB, device %d/%d)\n", capacity / 1048576.0,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), c.total / 1048576.0, dev,
+                c.device);
 }
 
 void *cached_host_alloc(size_t bytes, size_t *capacity) {
@@ -326,7 +335,7 @@ void *cached_host_alloc(size_t bytes, size_t *capacity) {
 
 void cached_host_free(void *p, size_t capacity) {
     if (!p) return;
-    if (give(host_cache(), p, capacity)) return;
+    if (give(host_cache(), p, capacity, kCacheMinBlock)) return;
     free(p);
 }
 
@@ -341,12 +350,13 @@ int check_device(int device) {
         if (e != cudaSuccess) return fail(QPB200_ERR_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
     }
     if (device >= count) return fail(QPB200_ERR_ARG, "device %d out of range (%d visible)", device, count);
-    cudaDeviceProp prop;
-    e = cudaGetDeviceProperties(&prop, device);
-    if (e != cudaSuccess) return fail(QPB200_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
-    if (prop.major != 10)
-        return fail(QPB200_ERR_DEVICE, "device %d (%s) is sm_%d%d; libqpb200 is built for sm_100a only", device, prop.name,
-                    prop.major, prop.minor);
+    // attribute queries, not cudaGetDeviceProperties: the latter costs milliseconds (up to 100+ with other driver clients)
+    int major = 0, minor = 0;
+    e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device);
+    if (e != cudaSuccess) return fail(QPB200_ERR_CUDA, "cudaDeviceGetAttribute: %s", cudaGetErrorString(e));
+    if (major != 10)
+        return fail(QPB200_ERR_DEVICE, "device %d is sm_%d%d; libqpb200 is built for sm_100a only", device, major, minor);
     e = cudaSetDevice(device);
     if (e != cudaSuccess) return fail(QPB200_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
     return QPB200_OK;

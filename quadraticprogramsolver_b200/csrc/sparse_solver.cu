@@ -3,6 +3,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <mutex>
 #include <new>
 
 #include "admm_kernels.cuh"
@@ -168,18 +169,28 @@ int SparseSolver::init(int64_t n64, int64_t m64, const int64_t *Pp, const int64_
 
     // ---- grid: co-resident CTAs of the persistent kernel, shrunk for small problems
     lap("assemble_H");
-    cudaDeviceProp prop;
-    QPB_CUDA(cudaGetDeviceProperties(&prop, device));
-    num_sms = prop.multiProcessorCount;
+    QPB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
     int per_sm = 1 << 30, tmp = 0;
-    for (const void *fn : {(const void *)admm_kernel<0, false>, (const void *)admm_kernel<0, true>, (const void *)admm_kernel<1, false>,
-                           (const void *)admm_kernel<1, true>, (const void *)admm_kernel<2, false>, (const void *)admm_kernel<2, true>}) {
-        if ((rc = prep_kernel(fn, &tmp))) return rc;
-        per_sm = std::min(per_sm, tmp);
+    {
+        // shared-memory opt-in + occupancy of every kernel variant: once per device and process
+        static std::mutex mu;
+        static int cached_per_sm[64];
+        std::lock_guard<std::mutex> g(mu);
+        const bool cacheable = device >= 0 && device < 64;
+        if (cacheable && cached_per_sm[device] > 0) {
+            per_sm = cached_per_sm[device];
+        } else {
+            for (const void *fn : {(const void *)admm_kernel<0, false>, (const void *)admm_kernel<0, true>, (const void *)admm_kernel<1, false>,
+                                   (const void *)admm_kernel<1, true>, (const void *)admm_kernel<2, false>, (const void *)admm_kernel<2, true>}) {
+                if ((rc = prep_kernel(fn, &tmp))) return rc;
+                per_sm = std::min(per_sm, tmp);
+            }
+            for (const void *fn : {(const void *)spmv_kernel<0, false>, (const void *)spmv_kernel<0, true>, (const void *)spmv_kernel<1, false>,
+                                   (const void *)spmv_kernel<1, true>, (const void *)spmv_kernel<2, false>, (const void *)spmv_kernel<2, true>})
+                if ((rc = prep_kernel(fn, &tmp))) return rc;
+            if (cacheable) cached_per_sm[device] = per_sm;
+        }
     }
-    for (const void *fn : {(const void *)spmv_kernel<0, false>, (const void *)spmv_kernel<0, true>, (const void *)spmv_kernel<1, false>,
-                           (const void *)spmv_kernel<1, true>, (const void *)spmv_kernel<2, false>, (const void *)spmv_kernel<2, true>})
-        if ((rc = prep_kernel(fn, &tmp))) return rc;
     if (per_sm < 1) return fail(QPB200_ERR_CUDA, "persistent kernel does not fit on an SM");
     {
         const char *e = getenv("QPB200_CTAS_PER_SM");   // A/B experiments only
@@ -247,12 +258,23 @@ int SparseSolver::init(int64_t n64, int64_t m64, const int64_t *Pp, const int64_
 }
 
 SparseSolver::~SparseSolver() {
+    const bool timing = getenv("QPB200_TIMING") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    auto ms_since = [&](std::chrono::steady_clock::time_point a) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count();
+    };
     if (device >= 0) cudaSetDevice(device);
     if (flush_buf) cudaFree(flush_buf);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (stream) cudaStreamDestroy(stream);
+    const double t_obj = ms_since(t0);
+    const auto t1 = std::chrono::steady_clock::now();
+    const size_t nblocks = arena.ptrs.size();
     arena.release();
+    if (timing)
+        fprintf(stderr, "[qpb200 ~SparseSolver] stream/events/flush %.1f ms, arena release (%zu blocks) %.1f ms\n", t_obj, nblocks,
+                ms_since(t1));
 }
 
 int SparseSolver::reset_state(const double *x0_host) {
