@@ -67,6 +67,21 @@ static CommCacheEntry &comm_cache() {
     return e;
 }
 
+// Peer-visible region of this process, kept across handles like the communicator: cudaMalloc + IPC export +
+// (R-1) cudaIpcOpenMemHandle at create and the matching close/free at destroy cost 100-500 ms per handle --
+// as much as a whole solve on 8 GPUs.  One entry; a handle created while another one owns it allocates privately.
+struct PeerRegionCache {
+    bool in_use = false;
+    int device = -1, rank = -1, nranks = 0;
+    double *region = nullptr;
+    size_t doubles = 0;
+    void *opened[kMaxPeers] = {nullptr};
+};
+static PeerRegionCache &region_cache() {
+    static PeerRegionCache c;
+    return c;
+}
+
 struct DistContext {
     int rank = 0, nranks = 1;
     ncclComm_t comm = nullptr;
@@ -80,6 +95,7 @@ struct DistContext {
     double *region = nullptr;              // this rank's peer-visible allocation (not in the arena: IPC-exported)
     void *opened[kMaxPeers] = {nullptr};   // cudaIpcOpenMemHandle results
     size_t region_doubles = 0;
+    bool region_cached = false;            // region / opened[] belong to region_cache(): handed back, not freed
     double *tiny = nullptr;                // 1 double for the host-level rendezvous all-reduce
 };
 
@@ -90,8 +106,12 @@ void dist_destroy(DistContext *d) {
     (void)api;
     if (d->host_state) cudaFreeHost(d->host_state);
     for (auto &e : d->ev) if (e) cudaEventDestroy(e);
-    for (void *o : d->opened) if (o) cudaIpcCloseMemHandle(o);
-    if (d->region) cudaFree(d->region);
+    if (d->region_cached) {
+        region_cache().in_use = false;     // mappings stay open for the next handle of this process
+    } else {
+        for (void *o : d->opened) if (o) cudaIpcCloseMemHandle(o);
+        if (d->region) cudaFree(d->region);
+    }
     delete d;
 }
 
@@ -306,32 +326,70 @@ static int peer_init(SparseSolver &s, DistContext &d) {
     const size_t off_UT = off; off += pair;
     const size_t off_XG = off; off += pair;
     d.region_doubles = off;
-    QPB_CUDA(cudaMalloc(&d.region, off * sizeof(double)));
-    QPB_CUDA(cudaMemset(d.region, 0, off * sizeof(double)));
-    // exchange the IPC handles through the NCCL communicator we already have
-    cudaIpcMemHandle_t mine;
-    QPB_CUDA(cudaIpcGetMemHandle(&mine, d.region));
-    unsigned char *hbuf = nullptr;
-    const size_t hsz = sizeof(cudaIpcMemHandle_t);
-    QPB_CUDA(s.arena.alloc(&hbuf, hsz * d.nranks, true));
-    QPB_CUDA(cudaMemcpyAsync(hbuf + hsz * d.rank, &mine, hsz, cudaMemcpyHostToDevice, s.stream));
-    QPB_NCCL(api->AllGather(hbuf + hsz * d.rank, hbuf, hsz, ncclChar, d.comm, s.stream));
-    std::vector<cudaIpcMemHandle_t> all((size_t)d.nranks);
-    QPB_CUDA(cudaMemcpyAsync(all.data(), hbuf, hsz * d.nranks, cudaMemcpyDeviceToHost, s.stream));
+    // ---- collective decision: reuse the process-cached region + mappings only if EVERY rank can
+    PeerRegionCache &rc = region_cache();
+    const bool mine_ok = !rc.in_use && rc.region && rc.device == s.device && rc.rank == d.rank && rc.nranks == d.nranks && rc.doubles >= off;
+    double cannot = mine_ok ? 0.0 : 1.0;
+    QPB_CUDA(cudaMemcpyAsync(dm, &cannot, sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    QPB_NCCL(api->AllReduce(dm, dm, 1, ncclDouble, ncclMax, d.comm, s.stream));
+    QPB_CUDA(cudaMemcpyAsync(&cannot, dm, sizeof(double), cudaMemcpyDeviceToHost, s.stream));
     QPB_CUDA(cudaStreamSynchronize(s.stream));
-    for (int q = 0; q < d.nranks; ++q) {
-        if (q == d.rank) {
-            pd.region[q] = d.region;
-            continue;
+    if (cannot < 0.5) {
+        rc.in_use = true;
+        d.region_cached = true;
+        d.region = rc.region;
+        QPB_CUDA(cudaMemsetAsync(d.region, 0, off * sizeof(double), s.stream));
+        for (int q = 0; q < d.nranks; ++q) pd.region[q] = q == d.rank ? d.region : static_cast<double *>(rc.opened[q]);
+    } else {
+        const bool own_cache = !rc.in_use;       // nobody holds the entry: replace it; else allocate privately
+        if (own_cache) {
+            for (void *&o : rc.opened) {
+                if (o) cudaIpcCloseMemHandle(o);
+                o = nullptr;
+            }
         }
-        void *ptr = nullptr;
-        cudaError_t e = cudaIpcOpenMemHandle(&ptr, all[(size_t)q], cudaIpcMemLazyEnablePeerAccess);
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            return fail(QPB200_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s -- peer path unavailable", q, cudaGetErrorString(e));
+        // every rank has dropped its mappings of the old regions before anybody frees one
+        QPB_NCCL(api->AllReduce(dm, dm, 1, ncclDouble, ncclMax, d.comm, s.stream));
+        QPB_CUDA(cudaStreamSynchronize(s.stream));
+        if (own_cache && rc.region) {
+            cudaFree(rc.region);
+            rc.region = nullptr;
+            rc.doubles = 0;
         }
-        d.opened[q] = ptr;
-        pd.region[q] = static_cast<double *>(ptr);
+        QPB_CUDA(cudaMalloc(&d.region, off * sizeof(double)));
+        QPB_CUDA(cudaMemset(d.region, 0, off * sizeof(double)));
+        // exchange the IPC handles through the NCCL communicator we already have
+        cudaIpcMemHandle_t mine;
+        QPB_CUDA(cudaIpcGetMemHandle(&mine, d.region));
+        unsigned char *hbuf = nullptr;
+        const size_t hsz = sizeof(cudaIpcMemHandle_t);
+        QPB_CUDA(s.arena.alloc(&hbuf, hsz * d.nranks, true));
+        QPB_CUDA(cudaMemcpyAsync(hbuf + hsz * d.rank, &mine, hsz, cudaMemcpyHostToDevice, s.stream));
+        QPB_NCCL(api->AllGather(hbuf + hsz * d.rank, hbuf, hsz, ncclChar, d.comm, s.stream));
+        std::vector<cudaIpcMemHandle_t> all((size_t)d.nranks);
+        QPB_CUDA(cudaMemcpyAsync(all.data(), hbuf, hsz * d.nranks, cudaMemcpyDeviceToHost, s.stream));
+        QPB_CUDA(cudaStreamSynchronize(s.stream));
+        for (int q = 0; q < d.nranks; ++q) {
+            if (q == d.rank) {
+                pd.region[q] = d.region;
+                continue;
+            }
+            void *ptr = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&ptr, all[(size_t)q], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                return fail(QPB200_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s -- peer path unavailable", q, cudaGetErrorString(e));
+            }
+            d.opened[q] = ptr;
+            pd.region[q] = static_cast<double *>(ptr);
+        }
+        if (own_cache) {                         // hand the new region to the cache; this handle borrows it
+            rc.in_use = true;
+            rc.device = s.device; rc.rank = d.rank; rc.nranks = d.nranks;
+            rc.region = d.region; rc.doubles = off;
+            for (int q = 0; q < kMaxPeers; ++q) rc.opened[q] = d.opened[q];
+            d.region_cached = true;
+        }
     }
     // the gathered pairs move into the peer-visible region (the arena copies stay unused)
     s.prob.UT = d.region + off_UT;
