@@ -72,9 +72,19 @@ typedef struct qpb200_settings {
     int32_t precond;      /* QPB200_PRECOND_* (default JACOBI)                                    */
     int32_t device;       /* CUDA device ordinal; -1 = the calling thread's current device        */
     int32_t spmv_loader;  /* 0 = auto (2), 1 = coalesced LDG, 2 = TMA bulk staged, 3 = TMA + pipelined */
-    int32_t reserved_i[7];
+    int32_t reserved_i[7]; /* [QPB200_RSV_*] below; the rest must be 0                            */
     double reserved_d[4];
 } qpb200_settings;
+
+/* Meaning of settings.reserved_i[k] (all default 0 = the reference's behaviour)                     */
+#define QPB200_RSV_CHOL_UNBLOCKED 0 /* dense batch: 1 = unblocked Cholesky (A/B runs)                  */
+#define QPB200_RSV_DIST_MODE 1      /* qpb200_dist_*: 0 auto / peer memory, 1 NCCL, 2 peer required    */
+#define QPB200_RSV_SCALING_ITERS 2  /* sparse single-GPU path: k > 0 = k iterations of modified Ruiz
+                                       equilibration of [P A'; A 0] with cost scaling (OSQP paper,
+                                       Algorithm 2; README.md:71-72 of the reference lists it as a
+                                       TODO).  The scaled QP is iterated; CheckConvergence's norms
+                                       (SolveQuadraticProgram.jl:85-105) are evaluated on the
+                                       UNSCALED residuals, x / z / y are returned unscaled.            */
 
 typedef struct qpb200_info {
     int32_t conv_flag;       /* QPB200_CONV_*                                                      */

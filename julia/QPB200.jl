@@ -93,13 +93,14 @@ end
 Same positional arguments, keyword names, defaults and return value as the reference method
 (SolveQuadraticProgram.jl:14-17); `vX` is the start point and is overwritten with the solution.
 New keywords: `ϵPcg`, `numItrPcg` (the plugin kwargs of LinearSystemSolvers.jl:125, which the reference
-driver never forwards), `precond ∈ (:jacobi, :none)`, `device`.
+driver never forwards), `precond ∈ (:jacobi, :none)`, `device`, `numItrScaling` (Ruiz equilibration, default off).
 """
 function SolveQuadraticProgram!(vX::Vector{Float64}, mP::SparseMatrixCSC{Float64, Int64}, vQ::Vector{Float64},
         mA::SparseMatrixCSC{Float64, Int64}, vL::Vector{Float64}, vU::Vector{Float64}, ::B200InitT, ::B200SolT;
         numIterations = 5000, ϵAbs = 1e-6, ϵRel = 1e-6, ρ = 1, σ = 1e-6, α = 1.6, δ = 1e-6, adptΡ::Bool = false,
         fctrΡ = 5, numItrConv = 25, numItrPolish = 10, ϵMinres = 1e-6, numItrMinres = 500,
-        ϵPcg = 1e-6, numItrPcg = 1000, precond::Symbol = :jacobi, device::Integer = -1, info::Union{Info, Nothing} = nothing)
+        ϵPcg = 1e-6, numItrPcg = 1000, precond::Symbol = :jacobi, device::Integer = -1, numItrScaling::Integer = 0,
+        info::Union{Info, Nothing} = nothing)
 
     numElements, numConstraints = length(vX), size(mA, 1);
     (size(mP) == (numElements, numElements) && size(mA, 2) == numElements && length(vQ) == numElements &&
@@ -111,6 +112,8 @@ function SolveQuadraticProgram!(vX::Vector{Float64}, mP::SparseMatrixCSC{Float64
     s.adaptive_rho = adptΡ; s.rho_factor = fctrΡ; s.check_every = numItrConv; s.polish_iter = numItrPolish;
     s.minres_eps = ϵMinres; s.minres_iter = numItrMinres; s.pcg_eps = ϵPcg; s.pcg_max_iter = numItrPcg;
     s.precond = precond == :none ? 0 : 1; s.device = device;
+    # reserved_i[QPB200_RSV_SCALING_ITERS = 2] (0-based): Ruiz equilibration iterations, 0 = off (README.md:71 TODO)
+    s.reserved_i = ntuple(k -> k == 3 ? Int32(numItrScaling) : s.reserved_i[k], 7);
 
     hRef = Ref{Ptr{Cvoid}}(C_NULL);
     # SparseMatrixCSC fields are passed as they are: colptr/rowval are 1-based Int64 -> index_base = 1, zero copies

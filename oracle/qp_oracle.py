@@ -234,17 +234,27 @@ PLUGINS = {
 # ADMM driver
 # --------------------------------------------------------------------------------------------
 
-def check_convergence(vX, mP, vQ, mA, vZ, vY, vXP, vZP, rho, rhorho, adptRho, epsAbs, epsRel, epsAdmm, convFlag):
-    """``CheckConvergence`` (SolveQuadraticProgram.jl:79-112).  Returns (rhorho, convFlag, norms)."""
+def check_convergence(vX, mP, vQ, mA, vZ, vY, vXP, vZP, rho, rhorho, adptRho, epsAbs, epsRel, epsAdmm, convFlag,
+                      scaling=None):
+    """``CheckConvergence`` (SolveQuadraticProgram.jl:79-112).  Returns (rhorho, convFlag, norms).
+
+    ``scaling = (D, Dinvc, Einv, normQ)`` (not in the reference): the iterates belong to the equilibrated
+    problem and every norm is taken on the residual of the UNSCALED problem -- ``|.| * Einv`` on
+    constraint-space vectors, ``|.| * Dinvc`` (= 1/(c D)) on dual-residual vectors, ``|dx| * D``."""
     MIN_VAL_RHO = 1e-3                                              # :81
     MAX_VAL_RHO = 1e6                                               # :82
     vAx = mA @ vX
     vPx = mP @ vX
     vAty = mA.T @ vY
-    normResPrim = _norm_inf(vAx - vZ)                               # :85
-    normResDual = _norm_inf(vPx + vQ + vAty)                        # :86
-    maxNormPrim = max(_norm_inf(vAx), _norm_inf(vZ))                # :88
-    maxNormDual = max(_norm_inf(vPx), _norm_inf(vAty), _norm_inf(vQ))   # :89
+    if scaling is None:
+        wX = wD = wE = 1.0
+        normQ = _norm_inf(vQ)
+    else:
+        wX, wD, wE, normQ = scaling
+    normResPrim = _norm_inf(np.abs(vAx - vZ) * wE)                  # :85
+    normResDual = _norm_inf(np.abs(vPx + vQ + vAty) * wD)           # :86
+    maxNormPrim = max(_norm_inf(np.abs(vAx) * wE), _norm_inf(np.abs(vZ) * wE))            # :88
+    maxNormDual = max(_norm_inf(np.abs(vPx) * wD), _norm_inf(np.abs(vAty) * wD), normQ)   # :89
     if adptRho:                                                     # :92-96
         numeratorVal = normResPrim * maxNormDual
         denominatorVal = normResDual * maxNormPrim
@@ -255,7 +265,7 @@ def check_convergence(vX, mP, vQ, mA, vZ, vY, vXP, vZP, rho, rhorho, adptRho, ep
     epsDual = epsAbs + epsRel * maxNormDual                         # :100
     if (normResPrim < epsPrim) and (normResDual < epsDual):         # :102
         convFlag = ConvergenceFlag.convPrimDual
-    if (_norm_inf(vX - vXP) <= epsAdmm) and (_norm_inf(vZ - vZP) <= epsAdmm):   # :105
+    if (_norm_inf(np.abs(vX - vXP) * wX) <= epsAdmm) and (_norm_inf(np.abs(vZ - vZP) * wE) <= epsAdmm):   # :105
         convFlag = ConvergenceFlag.convAdmm
     return rhorho, convFlag, (normResPrim, normResDual)
 
@@ -263,7 +273,7 @@ def check_convergence(vX, mP, vQ, mA, vZ, vY, vXP, vZP, rho, rhorho, adptRho, ep
 def solve_quadratic_program(vX, mP, vQ, mA, vL, vU, LinSysSolInit, LinSysSol, *,
                             numIterations=5000, epsAbs=1e-6, epsRel=1e-6, rho=1.0, sigma=1e-6, alpha=1.6,
                             delta=1e-6, adptRho=False, fctrRho=5.0, numItrConv=25, numItrPolish=10,
-                            epsMinres=1e-6, numItrMinres=500, epsPcg=None, numItrPcg=None, trace=None):
+                            epsMinres=1e-6, numItrMinres=500, epsPcg=None, numItrPcg=None, trace=None, scaling=None):
     """``SolveQuadraticProgram!`` (SolveQuadraticProgram.jl:14-76).  Mutates ``vX``.
 
     Returns ``(convFlag, info)``; the reference returns only the flag -- ``info`` carries the
@@ -320,7 +330,7 @@ def solve_quadratic_program(vX, mP, vQ, mA, vL, vU, LinSysSolInit, LinSysSol, *,
 
         if ii % numItrConv == 0:                                    # :63
             rhorho, convFlag, norms = check_convergence(vX, mPr, vQ, mAr, vZ, vY, vXP, vZP, rho, rhorho,
-                                                        adptRho, epsAbs, epsRel, epsAdmm, convFlag)
+                                                        adptRho, epsAbs, epsRel, epsAdmm, convFlag, scaling)
             if convFlag != ConvergenceFlag.convNumItr:              # :66
                 break
 
@@ -329,12 +339,74 @@ def solve_quadratic_program(vX, mP, vQ, mA, vL, vU, LinSysSolInit, LinSysSol, *,
     return convFlag, info
 
 
-def solve(mP, vQ, mA, vL, vU, mode="D", x0=None, **kw):
-    """Convenience wrapper: ``(x, flag, info)`` for a plugin mode letter."""
+def _limit_scaling(v):
+    return np.where(v < 1e-4, 1.0, np.where(v > 1e4, 1e4, v))
+
+
+def _row_max_abs(M):
+    """inf-norm of every row of a CSR matrix (0 for empty rows)."""
+    out = np.zeros(M.shape[0])
+    nz = np.diff(M.indptr) > 0
+    if M.nnz:
+        out[nz] = np.maximum.reduceat(np.abs(M.data), M.indptr[:-1][nz])
+    return out
+
+
+def ruiz_equilibrate(mP, vQ, mA, vL, vU, numItr):
+    """Modified Ruiz equilibration of ``[P A'; A 0]`` with cost scaling -- Stellato et al., "OSQP: an operator
+    splitting solver for quadratic programs" (2020), Algorithm 2.  NOT in the reference (its README.md:71-72
+    lists scaling as a TODO): SURVEY.md 8(f) row 1.  Returns ``(P_s, q_s, A_s, l_s, u_s, D, E, c)`` with
+    ``P_s = c D P D``, ``A_s = E A D``, ``q_s = c D q``, ``l_s = E l``, ``u_s = E u``.
+
+    Per iteration: delta = 1/sqrt(limit(column inf-norms of the KKT matrix)), scale, then
+    gamma = 1/max(limit(mean column norm of P_s), limit(|q_s|inf)); limit(v) = 1 if v < 1e-4, min(v, 1e4).
+    Entries are scaled as ``a_ij * (d_j * e_i)`` and the mean is a left-to-right sum, like the C++ host code."""
+    P = sp.csr_matrix(mP, dtype=np.float64, copy=True)
+    A = sp.csr_matrix(mA, dtype=np.float64, copy=True)
+    P.sort_indices(); A.sort_indices()
+    n, m = P.shape[0], A.shape[0]
+    q = np.array(vQ, dtype=np.float64)
+    D, E, c = np.ones(n), np.ones(m), 1.0
+    prow = np.repeat(np.arange(n), np.diff(P.indptr))
+    arow = np.repeat(np.arange(m), np.diff(A.indptr))
+    for _ in range(int(numItr)):
+        At = sp.csr_matrix(A.T)
+        dn = np.maximum(_row_max_abs(P), _row_max_abs(At) if m else 0.0)
+        en = _row_max_abs(A)
+        dn = 1.0 / np.sqrt(_limit_scaling(dn))
+        en = 1.0 / np.sqrt(_limit_scaling(en))
+        P.data *= dn[prow] * dn[P.indices]
+        A.data *= dn[A.indices] * en[arow]
+        q *= dn
+        D *= dn
+        E *= en
+        pn = _row_max_abs(P)
+        mean = float(np.cumsum(pn)[-1]) / n                      # serial sum
+        mean = float(_limit_scaling(np.float64(mean)))
+        qn = float(_limit_scaling(np.float64(_norm_inf(q))))
+        gamma = 1.0 / max(mean, qn)
+        P.data *= gamma
+        q *= gamma
+        c *= gamma
+    return sp.csc_matrix(P), q, sp.csc_matrix(A), E * np.asarray(vL, dtype=np.float64), E * np.asarray(vU, dtype=np.float64), D, E, c
+
+
+def solve(mP, vQ, mA, vL, vU, mode="D", x0=None, numItrScaling=0, **kw):
+    """Convenience wrapper: ``(x, flag, info)`` for a plugin mode letter.  ``numItrScaling > 0`` iterates the
+    Ruiz-equilibrated problem and tests convergence on the unscaled residuals (see ``ruiz_equilibrate``)."""
     init, sol = PLUGINS[mode]
     vX = np.zeros(mP.shape[0]) if x0 is None else np.array(x0, dtype=np.float64)
-    flag, info = solve_quadratic_program(vX, mP, vQ, mA, vL, vU, init, sol, **kw)
-    return vX, flag, info
+    if not numItrScaling:
+        flag, info = solve_quadratic_program(vX, mP, vQ, mA, vL, vU, init, sol, **kw)
+        return vX, flag, info
+    Ps, qs, As, ls, us, D, E, c = ruiz_equilibrate(mP, vQ, mA, vL, vU, numItrScaling)
+    vXs = vX / D
+    scaling = (D, 1.0 / (c * D), 1.0 / E, _norm_inf(np.asarray(vQ, dtype=np.float64)))
+    flag, info = solve_quadratic_program(vXs, Ps, qs, As, ls, us, init, sol, scaling=scaling, **kw)
+    info["z"] = info["z"] / E
+    info["y"] = E * info["y"] / c
+    info["scaling"] = {"D": D, "E": E, "c": c}
+    return vXs * D, flag, info
 
 
 # --------------------------------------------------------------------------------------------

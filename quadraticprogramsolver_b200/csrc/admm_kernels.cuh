@@ -44,6 +44,9 @@ struct SparseProblemDev {
     double *z, *zt;             // m
     double *r, *c, *zp, *dinv;  // n
     double normQ;
+    // optional (Ruiz equilibration): D, 1/(c D) [n] and 1/E [m] turn the norms of CheckConvergence back into
+    // those of the unscaled problem; nullptr = the problem is solved as given (the reference's behaviour)
+    const double *Dv, *Dinvc, *Einv;
     GridSync gs;
     AdmmSettingsDev s;
     AdmmInfoDev *info;
@@ -208,7 +211,8 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) admm_kernel(SparseProblemD
                 y[i] = y_new;
                 p.zt[i] = zt_i;
                 g[i] = rho * (zt_i - z_new) + y_new;
-                nrm[1] = nanmax(nrm[1], fabs(z_new - z_old));
+                const double ei = (p.Einv && do_check) ? p.Einv[i] : 1.0;
+                nrm[1] = nanmax(nrm[1], fabs(z_new - z_old) * ei);
             };
             spmv_tiles<TMA, false>(p.A, xt, sm, ps, epi);
             ++n_a;
@@ -217,27 +221,31 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) admm_kernel(SparseProblemD
             const double x_old = x[j];
             const double x_new = alpha * xt[j] + alpha1 * x_old;      // :57
             x[j] = x_new;
-            nrm[0] = nanmax(nrm[0], fabs(x_new - x_old));
+            const double dj = (p.Dv && do_check) ? p.Dv[j] : 1.0;
+            nrm[0] = nanmax(nrm[0], fabs(x_new - x_old) * dj);
         }
         grid_barrier(p.gs, st);
 
         if (do_check) {
             // ---- [Chk] CheckConvergence (:79-112): A x, P x, A' y and their inf-norms in two passes
+            //      (ei, dj = 1 unless the problem was equilibrated: then the norms are those of the unscaled QP)
             {
                 auto epi = [&](int i, double s0, double) {
                     const double zi = p.z[i];
-                    nrm[2] = nanmax(nrm[2], fabs(s0 - zi));           // |Ax - z|
-                    nrm[3] = nanmax(nrm[3], fabs(s0));                // |Ax|
-                    nrm[3] = nanmax(nrm[3], fabs(zi));                // |z|   (maxNormPrim = max of both)
+                    const double ei = p.Einv ? p.Einv[i] : 1.0;
+                    nrm[2] = nanmax(nrm[2], fabs(s0 - zi) * ei);      // |Ax - z|
+                    nrm[3] = nanmax(nrm[3], fabs(s0) * ei);           // |Ax|
+                    nrm[3] = nanmax(nrm[3], fabs(zi) * ei);           // |z|   (maxNormPrim = max of both)
                 };
                 spmv_tiles<TMA, false>(p.A, x, sm, ps, epi);
                 ++n_a;
             }
             {
                 auto epi = [&](int j, double s0, double s1) {
-                    nrm[4] = nanmax(nrm[4], fabs(s0 + p.q[j] + s1));  // |Px + q + A'y|
-                    nrm[5] = nanmax(nrm[5], fabs(s0));                // |Px|
-                    nrm[5] = nanmax(nrm[5], fabs(s1));                // |A'y|
+                    const double dj = p.Dinvc ? p.Dinvc[j] : 1.0;
+                    nrm[4] = nanmax(nrm[4], fabs(s0 + p.q[j] + s1) * dj);   // |Px + q + A'y|
+                    nrm[5] = nanmax(nrm[5], fabs(s0) * dj);                 // |Px|
+                    nrm[5] = nanmax(nrm[5], fabs(s1) * dj);                 // |A'y|
                 };
                 spmv_tiles<TMA, true>(p.H, p.XY, sm, ps, epi);
                 ++n_h;

@@ -55,6 +55,8 @@ int qpb200_batch_create(qpb200_batch **out, int64_t batch, int64_t n, int64_t m,
         return fail(QPB200_ERR_ARG, "settings: need rho > 0, sigma >= 0, max_iter >= 0, check_every > 0");
     if (s.lin_solver != QPB200_LINSOLVE_CHOLESKY)
         return fail(QPB200_ERR_ARG, "qpb200_batch_create: the dense batch path implements lin_solver = QPB200_LINSOLVE_CHOLESKY only");
+    if (s.reserved_i[QPB200_RSV_SCALING_ITERS] != 0)
+        return fail(QPB200_ERR_ARG, "qpb200_batch_create: equilibration is implemented for the sparse single-GPU path only");
     // value checks on a strided sample would miss entries: scan everything (memory-bound, ~GB/s)
     const size_t nP = (size_t)batch * n * n, nA = (size_t)batch * m * n;
     if (!all_finite(P, nP)) return fail(QPB200_ERR_NONFINITE, "P has a non-finite entry");

@@ -517,6 +517,8 @@ int qpb200_dist_create(qpb200_handle **out, int32_t rank, int32_t nranks, const 
     qpb200_settings s;
     if (settings) s = *settings;
     else qpb200_default_settings(&s);
+    if (s.reserved_i[QPB200_RSV_SCALING_ITERS] != 0)
+        return fail(QPB200_ERR_ARG, "qpb200_dist_create: equilibration needs column norms over all ranks' rows; not implemented for the row-partitioned path");
     qpb200_handle *h = new (std::nothrow) qpb200_handle();
     if (!h) return fail(QPB200_ERR_ARG, "out of host memory");
     int rc = h->solver.init(n, m_local, P_colptr, P_rowval, P_nzval, A_colptr, A_rowval, A_nzval, q, l_local, u_local, s, index_base);

@@ -339,6 +339,72 @@ void cached_host_free(void *p, size_t capacity) {
     free(p);
 }
 
+namespace {
+inline double limit_scaling(double v) { return v < 1e-4 ? 1.0 : (v > 1e4 ? 1e4 : v); }
+
+void row_max_abs(const HostCsr &M, std::vector<double> &out, bool accumulate) {
+    parallel_chunks(M.rows, [&](int, int64_t r0, int64_t r1) {
+        for (int64_t r = r0; r < r1; ++r) {
+            double v = accumulate ? out[(size_t)r] : 0.0;
+            for (int k = M.ptr[(size_t)r]; k < M.ptr[(size_t)r + 1]; ++k) v = std::fmax(v, std::fabs(M.val.p[k]));
+            out[(size_t)r] = v;
+        }
+    }, 4096);
+}
+
+// M[r, c] *= rs[r] * cs[c]
+void scale_rows_cols(HostCsr &M, const std::vector<double> &rs, const std::vector<double> &cs, bool row_first) {
+    parallel_chunks(M.rows, [&](int, int64_t r0, int64_t r1) {
+        for (int64_t r = r0; r < r1; ++r)
+            for (int k = M.ptr[(size_t)r]; k < M.ptr[(size_t)r + 1]; ++k) {
+                const double a = rs[(size_t)r], b = cs[(size_t)M.idx.p[k]];
+                // the same factor (variable scale * constraint scale) for A[i,j] and A'[j,i]: both copies stay bit-identical
+                M.val.p[k] *= row_first ? (a * b) : (b * a);
+            }
+    }, 4096);
+}
+}  // namespace
+
+void ruiz_equilibrate(HostCsr &P, HostCsr &A, HostCsr &At, std::vector<double> &q, int iters, RuizScaling &out) {
+    const size_t n = (size_t)P.rows, m = (size_t)A.rows;
+    out.D.assign(n, 1.0);
+    out.E.assign(m, 1.0);
+    out.c = 1.0;
+    std::vector<double> dn(n), en(m);
+    for (int it = 0; it < iters; ++it) {
+        row_max_abs(P, dn, false);            // column norms of [P; A]
+        if (m) row_max_abs(At, dn, true);
+        if (m) row_max_abs(A, en, false);     // column norms of [A'; 0]
+        for (size_t j = 0; j < n; ++j) dn[j] = 1.0 / std::sqrt(limit_scaling(dn[j]));
+        for (size_t i = 0; i < m; ++i) en[i] = 1.0 / std::sqrt(limit_scaling(en[i]));
+        scale_rows_cols(P, dn, dn, true);
+        if (m) {
+            scale_rows_cols(A, en, dn, false);    // factor d_j * e_i
+            scale_rows_cols(At, dn, en, true);    // factor d_j * e_i
+        }
+        for (size_t j = 0; j < n; ++j) {
+            q[j] *= dn[j];
+            out.D[j] *= dn[j];
+        }
+        for (size_t i = 0; i < m; ++i) out.E[i] *= en[i];
+        // cost scaling: mean column norm of P against |q|inf
+        row_max_abs(P, dn, false);
+        double mean = 0.0, qn = 0.0;
+        for (size_t j = 0; j < n; ++j) {
+            mean += dn[j];
+            qn = std::fmax(qn, std::fabs(q[j]));
+        }
+        mean = limit_scaling(mean / (double)n);
+        qn = limit_scaling(qn);
+        const double gamma = 1.0 / std::fmax(mean, qn);
+        parallel_chunks(P.rows, [&](int, int64_t r0, int64_t r1) {
+            for (int64_t k = P.ptr[(size_t)r0]; k < P.ptr[(size_t)r1]; ++k) P.val.p[k] *= gamma;
+        }, 4096);
+        for (size_t j = 0; j < n; ++j) q[j] *= gamma;
+        out.c *= gamma;
+    }
+}
+
 int check_device(int device) {
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);

@@ -118,6 +118,16 @@ int choose_lpr(const HostCsr &M);
 int host_threads();
 void parallel_chunks(int64_t count, const std::function<void(int, int64_t, int64_t)> &fn, int64_t min_chunk);
 
+// Modified Ruiz equilibration of the KKT matrix [P A'; A 0] with cost scaling (Stellato et al., "OSQP", 2020,
+// Algorithm 2): P <- c D P D, A <- E A D, q <- c D q.  Works on the row-major copies the solver already holds
+// (P symmetric: CSR(P) rows = columns; At = CSR(A')), all three kept consistent.  Not in the reference
+// (README.md:71-72 lists it as TODO): SURVEY 8(f) row 1.
+struct RuizScaling {
+    std::vector<double> D, E;   // n, m
+    double c = 1.0;
+};
+void ruiz_equilibrate(HostCsr &P, HostCsr &A, HostCsr &At, std::vector<double> &q, int iters, RuizScaling &out);
+
 // true iff every entry is finite (vectorisable: v * 0 is NaN exactly for NaN / +-Inf)
 bool all_finite(const double *v, size_t count);
 

@@ -134,6 +134,28 @@ int SparseSolver::init(int64_t n64, int64_t m64, const int64_t *Pp, const int64_
     csc_to_csr(m, n, Ap, Ai, Av, base, A);
     csc_as_csr_of_transpose(m, n, Ap, Ai, Av, base, At);
     lap("transposes");
+    // ---- optional Ruiz equilibration (not in the reference; off by default): from here on P, A, A', q, l, u are the
+    //      scaled problem, the termination norms are brought back to the unscaled one inside the kernel
+    const int scaling_iters = s.reserved_i[QPB200_RSV_SCALING_ITERS];
+    if (scaling_iters < 0 || scaling_iters > 1000) return fail(QPB200_ERR_ARG, "settings: scaling iterations must be in [0, 1000]");
+    std::vector<double> qs, ls, us;
+    double nq_unscaled = 0.0;
+    for (int64_t j = 0; j < n64; ++j) nq_unscaled = std::fmax(nq_unscaled, std::fabs(q[j]));
+    scaled = scaling_iters > 0;
+    if (scaled) {
+        qs.assign(q, q + n);
+        ruiz_equilibrate(P, A, At, qs, scaling_iters, scaling);
+        ls.resize((size_t)m);
+        us.resize((size_t)m);
+        for (int i = 0; i < m; ++i) {
+            ls[(size_t)i] = scaling.E[(size_t)i] * l[i];
+            us[(size_t)i] = scaling.E[(size_t)i] * u[i];
+        }
+        q = qs.data();
+        l = ls.data();
+        u = us.data();
+        lap("ruiz");
+    }
     nnzP = P.nnz();
     nnzA = A.nnz();
     H.rows = n;
@@ -163,9 +185,7 @@ int SparseSolver::init(int64_t n64, int64_t m64, const int64_t *Pp, const int64_
             }
         }
     }, 4096);
-    double nq = 0.0;
-    for (int j = 0; j < n; ++j) nq = std::fmax(nq, std::fabs(q[j]));
-    prob.normQ = nq;
+    prob.normQ = nq_unscaled;
 
     // ---- grid: co-resident CTAs of the persistent kernel, shrunk for small problems
     lap("assemble_H");
@@ -230,6 +250,20 @@ int SparseSolver::init(int64_t n64, int64_t m64, const int64_t *Pp, const int64_
     QPB_CUDA(cudaMemcpy(ddAA, dAA.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
     prob.q = dq; prob.l = dl; prob.u = du; prob.dP = ddP; prob.dAA = ddAA;
     d_q = dq; d_l = dl; d_u = du;
+    prob.Dv = prob.Dinvc = prob.Einv = nullptr;
+    if (scaled) {
+        std::vector<double> dinvc((size_t)n), einv((size_t)m);
+        for (int j = 0; j < n; ++j) dinvc[(size_t)j] = 1.0 / (scaling.c * scaling.D[(size_t)j]);
+        for (int i = 0; i < m; ++i) einv[(size_t)i] = 1.0 / scaling.E[(size_t)i];
+        double *dD, *dDi, *dEi;
+        QPB_CUDA(arena.alloc(&dD, (size_t)n));
+        QPB_CUDA(arena.alloc(&dDi, (size_t)n));
+        QPB_CUDA(arena.alloc(&dEi, (size_t)std::max(m, 1)));
+        QPB_CUDA(cudaMemcpy(dD, scaling.D.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+        QPB_CUDA(cudaMemcpy(dDi, dinvc.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+        if (m) QPB_CUDA(cudaMemcpy(dEi, einv.data(), (size_t)m * sizeof(double), cudaMemcpyHostToDevice));
+        prob.Dv = dD; prob.Dinvc = dDi; prob.Einv = dEi;
+    }
     const size_t nm = (size_t)n + (size_t)m;
     QPB_CUDA(arena.alloc(&prob.XY, nm + 8, true));
     QPB_CUDA(arena.alloc(&prob.XG, nm + 8, true));
@@ -307,7 +341,12 @@ int SparseSolver::solve(double *x_inout, double *z_out, double *y_out, qpb200_in
     if (!x_inout) return fail(QPB200_ERR_ARG, "qpb200_solve: x_inout is NULL");
     const auto wall0 = std::chrono::steady_clock::now();
     QPB_CUDA(cudaSetDevice(device));
-    int rc = reset_state(x_inout);
+    std::vector<double> x0s;
+    if (scaled) {                                   // start point in the scaled variables: x_s = D^-1 x
+        x0s.resize((size_t)n);
+        for (int j = 0; j < n; ++j) x0s[(size_t)j] = x_inout[j] / scaling.D[(size_t)j];
+    }
+    int rc = reset_state(scaled ? x0s.data() : x_inout);
     if (rc) return rc;
     QPB_CUDA(cudaEventRecord(ev0, stream));
     if ((rc = launch_admm())) return rc;
@@ -318,6 +357,13 @@ int SparseSolver::solve(double *x_inout, double *z_out, double *y_out, qpb200_in
     AdmmInfoDev hi;
     QPB_CUDA(cudaMemcpyAsync(&hi, prob.info, sizeof(hi), cudaMemcpyDeviceToHost, stream));
     QPB_CUDA(cudaStreamSynchronize(stream));
+    if (scaled) {                                   // x = D x_s, z = z_s / E, y = E y_s / c
+        for (int j = 0; j < n; ++j) x_inout[j] *= scaling.D[(size_t)j];
+        if (z_out)
+            for (int i = 0; i < m; ++i) z_out[i] /= scaling.E[(size_t)i];
+        if (y_out)
+            for (int i = 0; i < m; ++i) y_out[i] = scaling.E[(size_t)i] * y_out[i] / scaling.c;
+    }
     float ms = 0.f;
     QPB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
     last_info = hi;
@@ -384,6 +430,7 @@ int SparseSolver::apply_device(int which, const double *x, double *y) {
 
 int SparseSolver::apply(int which, const double *x_host, double *y_host) {
     if (!x_host || !y_host) return fail(QPB200_ERR_ARG, "qpb200_apply: NULL vector");
+    if (scaled) return fail(QPB200_ERR_ARG, "qpb200_apply: the handle holds the equilibrated operators; create it with scaling off");
     QPB_CUDA(cudaSetDevice(device));
     const size_t nm = (size_t)n + (size_t)m;
     double *in = prob.UT;       // borrow the (u; t) pair and the scratch pair; a solve resets them anyway
@@ -462,6 +509,7 @@ int SparseSolver::time_apply(int which, int reps, int flush_l2, double *ms_out) 
 
 int SparseSolver::update_vectors(const double *q, const double *l, const double *u) {
     QPB_CUDA(cudaSetDevice(device));
+    std::vector<double> tmp;
     if (q) {
         double nq = 0.0;
         for (int j = 0; j < n; ++j) {
@@ -469,10 +517,25 @@ int SparseSolver::update_vectors(const double *q, const double *l, const double 
             nq = std::fmax(nq, std::fabs(q[j]));
         }
         prob.normQ = nq;
+        if (scaled) {                               // q_s = c D q (the equilibration itself is kept)
+            tmp.resize((size_t)n);
+            for (int j = 0; j < n; ++j) tmp[(size_t)j] = scaling.c * scaling.D[(size_t)j] * q[j];
+            q = tmp.data();
+        }
         QPB_CUDA(cudaMemcpy(d_q, q, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
     }
-    if (l && m) QPB_CUDA(cudaMemcpy(d_l, l, (size_t)m * sizeof(double), cudaMemcpyHostToDevice));
-    if (u && m) QPB_CUDA(cudaMemcpy(d_u, u, (size_t)m * sizeof(double), cudaMemcpyHostToDevice));
+    for (int which = 0; which < 2; ++which) {
+        const double *b = which ? u : l;
+        if (!b || !m) continue;
+        for (int i = 0; i < m; ++i)
+            if (std::isnan(b[i])) return fail(QPB200_ERR_NONFINITE, "bound %d is NaN", i);
+        if (scaled) {
+            tmp.resize((size_t)m);
+            for (int i = 0; i < m; ++i) tmp[(size_t)i] = scaling.E[(size_t)i] * b[i];
+            b = tmp.data();
+        }
+        QPB_CUDA(cudaMemcpy(which ? d_u : d_l, b, (size_t)m * sizeof(double), cudaMemcpyHostToDevice));
+    }
     return QPB200_OK;
 }
 

@@ -20,6 +20,10 @@ struct SparseSolver {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double setup_ms = 0.0;
+    // Ruiz equilibration (settings.reserved_i[QPB200_RSV_SCALING_ITERS] > 0): the device holds the scaled problem,
+    // x = D x_s, z = z_s / E, y = E y_s / c; the kernel tests convergence on the unscaled residuals
+    RuizScaling scaling;
+    bool scaled = false;
 
     ~SparseSolver();
     int init(int64_t n, int64_t m, const int64_t *Pp, const int64_t *Pi, const double *Pv, const int64_t *Ap,

@@ -318,3 +318,17 @@ def config_banded(n: int = 1_000_000, m: int = 2_000_000, nnz_row_p: int = 26, n
     l = centre - rng.random(m)
     u = centre + rng.random(m)
     return _finish(P, q, A, l, u)
+
+
+def badly_scaled(problem, seed: int = 0, var_decades: float = 2.0, con_decades: float = 3.0):
+    """The same QP in badly chosen units: variables x_j = d_j x'_j with d_j = 10^U(-var, var) and constraint rows
+    multiplied by e_i = 10^U(-con, con):  P' = D P D, q' = D q, A' = E A D, l' = E l, u' = E u.
+    ADMM with a scalar rho stalls on such a problem; Ruiz equilibration (numItrScaling) recovers it."""
+    mP, vQ, mA, vL, vU = problem
+    rng = np.random.default_rng(seed)
+    n, m = mP.shape[0], mA.shape[0]
+    d = 10.0 ** rng.uniform(-var_decades, var_decades, n)
+    e = 10.0 ** rng.uniform(-con_decades, con_decades, m)
+    D, E = sp.diags(d), sp.diags(e)
+    return sp.csc_matrix(D @ mP @ D), d * vQ, sp.csc_matrix(E @ mA @ D), e * vL, e * vU
+

@@ -57,7 +57,9 @@ _DEFAULTS = dict(numIterations=5000, epsAbs=1e-6, epsRel=1e-6, rho=1.0, sigma=1e
                  adptRho=False, fctrRho=5.0, numItrConv=25, numItrPolish=10, epsMinres=1e-6, numItrMinres=500,
                  # plugin kwargs (LinearSystemSolvers.jl:125) and the new ones
                  epsPcg=1e-6, numItrPcg=1000, relPcg=-1.0, linSolver="pcg", precond="jacobi", device=-1,
-                 spmvLoader="auto")
+                 spmvLoader="auto",
+                 # Ruiz equilibration iterations (0 = off = the reference's behaviour)
+                 numItrScaling=0)
 
 
 def make_settings(**kw) -> Settings:
@@ -83,6 +85,7 @@ def make_settings(**kw) -> Settings:
     s.precond = {"none": _lib.PRECOND_NONE, "jacobi": _lib.PRECOND_JACOBI}[str(opts["precond"]).lstrip(":")]
     s.device = int(opts["device"])
     s.spmv_loader = {"auto": 0, "ldg": 1, "tma": 2, "tma_pipe": 3}[str(opts["spmvLoader"])]
+    s.reserved_i[2] = int(opts["numItrScaling"])          # QPB200_RSV_SCALING_ITERS
     return s
 
 

@@ -288,3 +288,75 @@ def test_dense_batch_is_bitwise_reproducible(lib):
     X1, f1, i1, _ = S.SolveQuadraticProgramBatch(P, q, A, l, u)
     X2, f2, i2, _ = S.SolveQuadraticProgramBatch(P, q, A, l, u)
     assert np.array_equal(X1, X2) and np.array_equal(f1, f2) and np.array_equal(i1, i2)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Ruiz equilibration (numItrScaling).  Oracle = qp_oracle.solve(..., numItrScaling=k),
+# which scales with the same formulas and tests convergence on the unscaled residuals.
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["cfg1", "cfg1_badly_scaled", "svm_inf_bounds", "sparse_5k"])
+def test_equilibrated_solve_matches_oracle(lib, case):
+    from quadraticprogramsolver_b200.problems import badly_scaled
+    S = _solver()
+    if case == "cfg1":
+        prob = config_cfg1(seed=1236)
+    elif case == "cfg1_badly_scaled":
+        prob = badly_scaled(config_cfg1(seed=1234), seed=0)
+    elif case == "svm_inf_bounds":
+        prob = GenerateRandomQP(ProblemClass.svm, 10, seed=5)
+    else:
+        prob = badly_scaled(config_sparse(5000, 10000, 1e-3, seed=9), seed=1, var_decades=1.0, con_decades=2.0)
+    P, q, A, l, u = prob
+    kw = dict(rho=0.1, adptRho=True, numIterations=3000, epsPcg=1e-11, numItrScaling=10)
+    x_ref, flag_ref, info_ref = qp_oracle.solve(P, q, A, l, u, mode="J", **kw)
+    x = np.zeros(P.shape[0])
+    with S.QPB200Solver(P, q, A, l, u, **kw) as s:
+        flag = s.solve(x, want_zy=True)
+        info = dict(s.info)
+        with pytest.raises(S.QPB200Error):          # the handle holds the scaled operators
+            s.apply(0, np.ones(P.shape[0]))
+    _assert_parity(x, flag, info, x_ref, flag_ref, info_ref["iterations"])
+    assert info["rho_updates"] == info_ref["rho_updates"]
+    # z and y come back unscaled too
+    sc = 1.0 + np.max(np.abs(info_ref["y"]))
+    assert np.max(np.abs(info["y"] - info_ref["y"])) <= 1e-6 * sc
+    assert np.max(np.abs(info["z"] - info_ref["z"])) <= 1e-6 * (1.0 + np.max(np.abs(info_ref["z"])))
+    if int(flag) == 3:      # converged: the reported residuals are those of the unscaled problem
+        assert abs(info["res_prim"] - np.max(np.abs(A @ x - info["z"]))) <= 1e-9 * (1 + np.max(np.abs(info["z"])))
+
+
+def test_equilibration_rescues_a_badly_scaled_problem_and_update_vectors(lib):
+    from quadraticprogramsolver_b200.problems import badly_scaled
+    S = _solver()
+    P, q, A, l, u = badly_scaled(config_cfg1(seed=1234), seed=0)
+    kw = dict(rho=0.1, adptRho=True, numIterations=4000)
+    x0, x1 = np.zeros(P.shape[0]), np.zeros(P.shape[0])
+    with S.QPB200Solver(P, q, A, l, u, **kw) as s:
+        f0 = s.solve(x0)
+        it0 = s.info["iterations"]
+    with S.QPB200Solver(P, q, A, l, u, numItrScaling=10, **kw) as s:
+        f1 = s.solve(x1, want_zy=True)
+        it1, y1 = s.info["iterations"], s.info["y"].copy()
+        # parametric re-solve on the equilibrated handle: new q, l, u are scaled with the stored D, E, c
+        q2 = 0.5 * q
+        s.update_vectors(q2, l, u)
+        x2 = np.zeros(P.shape[0])
+        f2 = s.solve(x2, want_zy=True)
+        y2 = s.info["y"].copy()
+    assert int(f0) == 1 and it0 == 4000
+    assert int(f1) == 3 and it1 <= 500
+    assert max(qp_oracle.kkt_certificate(P, q, A, l, u, x1, y1).values()) < 1e-4
+    assert int(f2) == 3
+    assert max(qp_oracle.kkt_certificate(P, q2, A, l, u, x2, y2).values()) < 1e-4
+
+
+def test_scaling_is_rejected_where_it_is_not_implemented(lib):
+    S = _solver()
+    rng = np.random.default_rng(0)
+    n, m, b = 8, 12, 4
+    M = rng.standard_normal((b, n, n))
+    P = np.einsum("bij,bkj->bik", M, M) + np.eye(n)
+    A_cm = rng.standard_normal((b, n, m))
+    with pytest.raises(S.QPB200Error):
+        S.QPB200Batch(P, rng.standard_normal((b, n)), A_cm, -np.ones((b, m)), np.ones((b, m)), numItrScaling=5)
+

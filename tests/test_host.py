@@ -53,6 +53,11 @@ def test_settings_mirror_accepts_reference_keyword_names(lib):
     assert (s.sigma, s.alpha, s.rho_factor, s.check_every) == (1e-5, 1.5, 4.0, 10)
     with pytest.raises(TypeError):
         make_settings(notAKeyword=1)
+    # new keyword: off by default = the reference's behaviour; header slot QPB200_RSV_SCALING_ITERS
+    assert list(make_settings().reserved_i) == [0] * 7
+    assert make_settings(numItrScaling=10).reserved_i[2] == 10
+    hdr = open(os.path.join(os.path.dirname(__file__), "..", "include", "qpb200.h")).read()
+    assert "#define QPB200_RSV_SCALING_ITERS 2" in hdr and "#define QPB200_RSV_DIST_MODE 1" in hdr
 
 
 def _create(lib, P, q, A, l, u, base=0, settings=None):

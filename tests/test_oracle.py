@@ -119,3 +119,56 @@ def test_golden_fixtures_reproduce(path):
     assert int(flag) == int(g["flag"])
     assert info["iterations"] == int(g["iterations"])
     assert np.max(np.abs(x - g["x"])) <= 1e-9 * (1 + np.max(np.abs(g["x"])))
+
+
+# ---------------------------------------------------------------------------------------------------
+# Ruiz equilibration (not in the reference; the oracle defines it, see ruiz_equilibrate)
+# ---------------------------------------------------------------------------------------------------
+def test_ruiz_equilibrate_balances_the_kkt_matrix():
+    from quadraticprogramsolver_b200.problems import badly_scaled
+    P, q, A, l, u = badly_scaled(config_cfg1(seed=1234), seed=3)
+    Ps, qs, As, ls, us, D, E, c = qp_oracle.ruiz_equilibrate(P, q, A, l, u, 15)
+    assert np.all(D > 0) and np.all(E > 0) and c > 0
+    # the scaled data are exactly what the definition says (up to rounding of the repeated products)
+    ref_P = (c * sp.diags(D) @ P @ sp.diags(D)).toarray()
+    ref_A = (sp.diags(E) @ A @ sp.diags(D)).toarray()
+    np.testing.assert_allclose(Ps.toarray(), ref_P, rtol=1e-12, atol=0)
+    np.testing.assert_allclose(As.toarray(), ref_A, rtol=1e-12, atol=0)
+    np.testing.assert_allclose(qs, c * D * q, rtol=1e-12)
+    np.testing.assert_allclose(ls, E * l, rtol=1e-15)
+    # column inf-norms of [P A'; A 0]: spread over 10 decades before (cost scaling aside), within 2x after
+    K0 = sp.bmat([[P, A.T], [A, None]]).tocsc()
+    K1 = sp.bmat([[Ps / c, As.T], [As, None]]).tocsc()
+    n0 = np.array([np.abs(K0[:, j].data).max() for j in range(K0.shape[1])])
+    n1 = np.array([np.abs(K1[:, j].data).max() for j in range(K1.shape[1])])
+    assert n0.max() / n0.min() > 1e6
+    assert n1.max() / n1.min() < 2.0
+
+
+@pytest.mark.parametrize("mode", ["D", "J"])
+def test_scaling_leaves_the_solution_unchanged(mode):
+    P, q, A, l, u = config_cfg1(seed=1235)
+    kw = dict(rho=0.1, adptRho=True, epsAbs=1e-7, epsRel=1e-7, numIterations=50000, epsPcg=1e-11)
+    x0, f0, i0 = qp_oracle.solve(P, q, A, l, u, mode=mode, **kw)
+    x1, f1, i1 = qp_oracle.solve(P, q, A, l, u, mode=mode, numItrScaling=10, **kw)
+    assert int(f0) == int(f1) == 3
+    assert np.max(np.abs(x0 - x1)) <= 1e-5 * (1 + np.max(np.abs(x0)))          # RunTests.jl:58 threshold
+    cert = qp_oracle.kkt_certificate(P, q, A, l, u, x1, i1["y"])               # unscaled problem, unscaled y
+    assert max(cert.values()) < 1e-5
+    np.testing.assert_allclose(A @ x1, i1["z"], atol=1e-5)
+
+
+def test_scaling_rescues_a_badly_scaled_problem():
+    from quadraticprogramsolver_b200.problems import badly_scaled
+    P, q, A, l, u = badly_scaled(config_cfg1(seed=1234), seed=0)
+    kw = dict(rho=0.1, adptRho=True, numIterations=4000)
+    x0, f0, i0 = qp_oracle.solve(P, q, A, l, u, mode="D", **kw)
+    x1, f1, i1 = qp_oracle.solve(P, q, A, l, u, mode="D", numItrScaling=10, **kw)
+    assert int(f0) == 1 and i0["iterations"] == 4000                           # stalls without equilibration
+    assert int(f1) == 3 and i1["iterations"] <= 500
+    # termination is tested on the UNSCALED residuals: the reference's criterion holds for the original data
+    rp = np.max(np.abs(A @ x1 - i1["z"]))
+    rd = np.max(np.abs(P @ x1 + q + A.T @ i1["y"]))
+    eps_p = 1e-6 + 1e-6 * max(np.max(np.abs(A @ x1)), np.max(np.abs(i1["z"])))
+    eps_d = 1e-6 + 1e-6 * max(np.max(np.abs(P @ x1)), np.max(np.abs(A.T @ i1["y"])), np.max(np.abs(q)))
+    assert rp < 1.01 * eps_p and rd < 1.01 * eps_d
