@@ -169,6 +169,14 @@ int qpb200_dist_solve(qpb200_handle *h, double *x_inout, double *z_out, double *
 int64_t qpb200_debug_tile_plan(int32_t rows, const int32_t *rowptr, int32_t grid, int32_t *tiles_out,
                                int64_t tiles_cap, int32_t *cta_begin_out, int32_t *lpr_out);
 int32_t qpb200_debug_tile_nnz(void);   /* kTileNnz */
+/* The host part of qpb200_create with scaling on, without a device: CSC -> row-major copies -> `iters`
+ * iterations of the equilibration (QPB200_RSV_SCALING_ITERS).  Writes D[n], E[m], *c and the scaled q[n],
+ * and the scaled values of P and A back in CSC order (Pnzval_out[nnzP], Anzval_out[nnzA]; NULL to skip).  */
+int qpb200_debug_equilibrate(int64_t n, int64_t m, const int64_t *P_colptr, const int64_t *P_rowval,
+                             const double *P_nzval, const int64_t *A_colptr, const int64_t *A_rowval,
+                             const double *A_nzval, const double *q, int32_t iters, int32_t index_base,
+                             double *D_out, double *E_out, double *c_out, double *q_out, double *Pnzval_out,
+                             double *Anzval_out);
 
 #ifdef __cplusplus
 }

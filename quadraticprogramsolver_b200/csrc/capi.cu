@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <new>
 
@@ -136,5 +137,37 @@ int64_t qpb200_debug_tile_plan(int32_t rows, const int32_t *rowptr, int32_t grid
 }
 
 int32_t qpb200_debug_tile_nnz(void) { return qpb::kTileNnz; }
+
+int qpb200_debug_equilibrate(int64_t n, int64_t m, const int64_t *Pp, const int64_t *Pi, const double *Pv, const int64_t *Ap,
+                             const int64_t *Ai, const double *Av, const double *q, int32_t iters, int32_t base, double *D_out,
+                             double *E_out, double *c_out, double *q_out, double *Pv_out, double *Av_out) {
+    if (n <= 0 || m < 0 || !q || iters < 0 || (base != 0 && base != 1))
+        return qpb::fail(QPB200_ERR_ARG, "qpb200_debug_equilibrate: bad argument");
+    int rc = qpb::validate_csc("P", n, n, Pp, Pi, Pv, base);
+    if (rc) return rc;
+    if ((rc = qpb::validate_csc("A", m, n, Ap, Ai, Av, base))) return rc;
+    qpb::HostCsr P, A, At;
+    qpb::csc_to_csr((int)n, (int)n, Pp, Pi, Pv, base, P);
+    qpb::csc_to_csr((int)m, (int)n, Ap, Ai, Av, base, A);
+    qpb::csc_as_csr_of_transpose((int)m, (int)n, Ap, Ai, Av, base, At);
+    std::vector<double> qs(q, q + n);
+    qpb::RuizScaling sc;
+    qpb::ruiz_equilibrate(P, A, At, qs, iters, sc);
+    if (D_out) std::copy(sc.D.begin(), sc.D.end(), D_out);
+    if (E_out) std::copy(sc.E.begin(), sc.E.end(), E_out);
+    if (c_out) *c_out = sc.c;
+    if (q_out) std::copy(qs.begin(), qs.end(), q_out);
+    // CSR(A') rows are A's columns in CSC order: the scaled values map back 1:1; P by symmetry of the pattern
+    // is returned through a CSR -> CSC pass of its own (a second transpose)
+    if (Av_out) std::copy(At.val.p, At.val.p + At.nnz(), Av_out);
+    if (Pv_out) {
+        std::vector<int64_t> ptr(P.ptr.begin(), P.ptr.end()), idx((size_t)P.nnz());
+        for (int64_t k = 0; k < P.nnz(); ++k) idx[(size_t)k] = P.idx.p[k];
+        qpb::HostCsr Pt;   // CSR of P' from "CSC of P'" = CSR(P): rows of Pt are columns of P, i.e. CSC order of P
+        qpb::csc_to_csr((int)n, (int)n, ptr.data(), idx.data(), P.val.p, 0, Pt);
+        std::copy(Pt.val.p, Pt.val.p + Pt.nnz(), Pv_out);
+    }
+    return QPB200_OK;
+}
 
 }  // extern "C"

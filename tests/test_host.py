@@ -200,3 +200,39 @@ def test_tile_plan_is_balanced(lib):
     per_cta = np.array([nk[cta[b]:cta[b + 1]].sum() for b in range(296)])
     assert per_cta.sum() == M.nnz
     assert per_cta.max() <= 1.25 * per_cta.mean() + lib.qpb200_debug_tile_nnz()
+
+
+@pytest.mark.parametrize("case", ["cfg1", "cfg1_badly_scaled", "svm_inf_bounds", "m0"])
+def test_host_equilibration_matches_oracle(lib, case):
+    """qpb200_create's host-side Ruiz equilibration (no GPU needed) against oracle/qp_oracle.ruiz_equilibrate."""
+    import scipy.sparse as sp
+    from oracle import qp_oracle
+    from quadraticprogramsolver_b200.problems import GenerateRandomQP, ProblemClass, badly_scaled, config_cfg1
+    from quadraticprogramsolver_b200.solver import _csc_arrays, _p64, _pd
+    if case == "cfg1":
+        P, q, A, l, u = config_cfg1(seed=1234)
+    elif case == "cfg1_badly_scaled":
+        P, q, A, l, u = badly_scaled(config_cfg1(seed=1234), seed=0)
+    elif case == "svm_inf_bounds":
+        P, q, A, l, u = GenerateRandomQP(ProblemClass.supportVectorMachine, 10, seed=5)
+    else:
+        P, q, A, l, u = config_cfg1(seed=1234)
+        A, l, u = sp.csc_matrix((0, P.shape[0])), np.zeros(0), np.zeros(0)
+    n, m = P.shape[0], A.shape[0]
+    Pa, Aa = _csc_arrays(P), _csc_arrays(A)
+    D, E, c, qs = np.zeros(n), np.zeros(max(m, 1)), C.c_double(0.0), np.zeros(n)
+    Pv, Av = np.zeros(len(Pa[2])), np.zeros(max(len(Aa[2]), 1))
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    rc = lib.qpb200_debug_equilibrate(n, m, _p64(Pa[0]), _p64(Pa[1]), _pd(Pa[2]), _p64(Aa[0]), _p64(Aa[1]), _pd(Aa[2]), _pd(q),
+                                      10, 0, _pd(D), _pd(E), C.byref(c), _pd(qs), _pd(Pv), _pd(Av))
+    assert rc == 0, lib.qpb200_last_error()
+    Ps, qs_ref, As, ls, us, D_ref, E_ref, c_ref = qp_oracle.ruiz_equilibrate(P, q, A, l, u, 10)
+    # same formulas, same operation order: agreement to the last couple of bits
+    np.testing.assert_allclose(D, D_ref, rtol=1e-14)
+    np.testing.assert_allclose(E[:m], E_ref, rtol=1e-14)
+    assert abs(c.value - c_ref) <= 1e-14 * c_ref
+    np.testing.assert_allclose(qs, qs_ref, rtol=1e-13, atol=1e-300)
+    Ps, As = sp.csc_matrix(Ps), sp.csc_matrix(As)
+    Ps.sort_indices(); As.sort_indices()
+    np.testing.assert_allclose(Pv, Ps.data, rtol=1e-13)
+    np.testing.assert_allclose(Av[:As.nnz], As.data, rtol=1e-13)
