@@ -112,7 +112,11 @@ int qpb200_batch_create(qpb200_batch **out, int64_t batch, int64_t n, int64_t m,
     QPB_CUDA_H(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.smem));
     int per_sm = 0;
     QPB_CUDA_H(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kDThreads, B.smem));
-    if (per_sm < 1) { delete h; return fail(QPB200_ERR_CUDA, "dense batch kernel does not fit on an SM (smem %zu)", B.smem); }
+    if (per_sm < 1) {
+        const size_t smem = B.smem;
+        delete h;
+        return fail(QPB200_ERR_CUDA, "dense batch kernel does not fit on an SM (smem %zu)", smem);
+    }
     int num_sms = 0;
     QPB_CUDA_H(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, B.device));
     B.grid = (int)std::min<int64_t>(batch, (int64_t)num_sms * per_sm);
