@@ -169,6 +169,14 @@ int qpb200_dist_solve(qpb200_handle *h, double *x_inout, double *z_out, double *
 int64_t qpb200_debug_tile_plan(int32_t rows, const int32_t *rowptr, int32_t grid, int32_t *tiles_out,
                                int64_t tiles_cap, int32_t *cta_begin_out, int32_t *lpr_out);
 int32_t qpb200_debug_tile_nnz(void);   /* kTileNnz */
+/* The host part of qpb200_create with scaling off, without a device: the operator H = [P A'] (n x (n+m), CSR,
+ * 0-based int32; rowmid[j] = where row j switches from P's entries to column j of A), diag(P) and the column
+ * square sums of A (the Jacobi preconditioner's ingredients).  Output arrays sized n+1, n, nnzP+nnzA (x2), n, n;
+ * any may be NULL.                                                                                         */
+int qpb200_debug_assemble_h(int64_t n, int64_t m, const int64_t *P_colptr, const int64_t *P_rowval,
+                            const double *P_nzval, const int64_t *A_colptr, const int64_t *A_rowval,
+                            const double *A_nzval, int32_t index_base, int32_t *rowptr_out, int32_t *rowmid_out,
+                            int32_t *col_out, double *val_out, double *diagP_out, double *colsqA_out);
 /* The host part of qpb200_create with scaling on, without a device: CSC -> row-major copies -> `iters`
  * iterations of the equilibration (QPB200_RSV_SCALING_ITERS).  Writes D[n], E[m], *c and the scaled q[n],
  * and the scaled values of P and A back in CSC order (Pnzval_out[nnzP], Anzval_out[nnzA]; NULL to skip).  */

@@ -54,7 +54,7 @@ EXPORTS = [
     "qpb200_apply", "qpb200_time_apply", "qpb200_apply_bytes",
     "qpb200_batch_create", "qpb200_batch_solve", "qpb200_batch_destroy",
     "qpb200_dist_unique_id", "qpb200_dist_create", "qpb200_dist_solve",
-    "qpb200_debug_tile_plan", "qpb200_debug_tile_nnz", "qpb200_debug_equilibrate",
+    "qpb200_debug_tile_plan", "qpb200_debug_tile_nnz", "qpb200_debug_equilibrate", "qpb200_debug_assemble_h",
 ]
 
 _lib = None
@@ -102,6 +102,8 @@ def load():
     lib.qpb200_debug_equilibrate.argtypes = [C.c_int64, C.c_int64, p64, p64, pd, p64, p64, pd, pd, C.c_int32, C.c_int32,
                                              pd, pd, pd, pd, pd, pd]
     lib.qpb200_debug_equilibrate.restype = C.c_int
+    lib.qpb200_debug_assemble_h.argtypes = [C.c_int64, C.c_int64, p64, p64, pd, p64, p64, pd, C.c_int32, p32, p32, p32, pd, pd, pd]
+    lib.qpb200_debug_assemble_h.restype = C.c_int
     _lib = lib
     return lib
 

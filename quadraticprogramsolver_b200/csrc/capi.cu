@@ -138,6 +138,25 @@ int64_t qpb200_debug_tile_plan(int32_t rows, const int32_t *rowptr, int32_t grid
 
 int32_t qpb200_debug_tile_nnz(void) { return qpb::kTileNnz; }
 
+int qpb200_debug_assemble_h(int64_t n, int64_t m, const int64_t *Pp, const int64_t *Pi, const double *Pv, const int64_t *Ap,
+                            const int64_t *Ai, const double *Av, int32_t base, int32_t *rowptr_out, int32_t *rowmid_out,
+                            int32_t *col_out, double *val_out, double *diagP_out, double *colsqA_out) {
+    if (n <= 0 || m < 0 || (base != 0 && base != 1)) return qpb::fail(QPB200_ERR_ARG, "qpb200_debug_assemble_h: bad argument");
+    int rc = qpb::validate_csc("P", n, n, Pp, Pi, Pv, base);
+    if (rc) return rc;
+    if ((rc = qpb::validate_csc("A", m, n, Ap, Ai, Av, base))) return rc;
+    qpb::HostCsr H;
+    std::vector<double> dP, dAA;
+    qpb::assemble_h_direct(n, m, Pp, Pi, Pv, Ap, Ai, Av, base, H, dP, dAA);
+    if (rowptr_out) std::copy(H.ptr.begin(), H.ptr.end(), rowptr_out);
+    if (rowmid_out) std::copy(H.mid.begin(), H.mid.end(), rowmid_out);
+    if (col_out) std::copy(H.idx.p, H.idx.p + H.nnz(), col_out);
+    if (val_out) std::copy(H.val.p, H.val.p + H.nnz(), val_out);
+    if (diagP_out) std::copy(dP.begin(), dP.end(), diagP_out);
+    if (colsqA_out) std::copy(dAA.begin(), dAA.end(), colsqA_out);
+    return QPB200_OK;
+}
+
 int qpb200_debug_equilibrate(int64_t n, int64_t m, const int64_t *Pp, const int64_t *Pi, const double *Pv, const int64_t *Ap,
                              const int64_t *Ai, const double *Av, const double *q, int32_t iters, int32_t base, double *D_out,
                              double *E_out, double *c_out, double *q_out, double *Pv_out, double *Av_out) {

@@ -83,19 +83,64 @@ int validate_csc(const char *name, int64_t nrows, int64_t ncols, const int64_t *
     return QPB200_OK;
 }
 
-void csc_to_csr(int64_t nrows, int64_t ncols, const int64_t *colptr, const int64_t *rowval, const double *nzval,
-                int64_t base, HostCsr &out) {
-    // stable parallel counting sort: thread t owns a contiguous block of columns; per-thread row
-    // histograms give every (thread, row) its write offset, so each row keeps ascending column order
-    // regardless of the thread count (deterministic layout).
+namespace {
+// Stable counting sort on one thread (small matrices): rows keep ascending column order.
+void csc_to_csr_serial(int64_t nrows, int64_t ncols, const int64_t *colptr, const int64_t *rowval, const double *nzval,
+                       int64_t base, const int64_t *gap, HostCsr &out) {
+    std::vector<int> cur((size_t)nrows + 1, 0);
     const int64_t nnz = colptr[ncols] - base;
+    for (int64_t k = 0; k < nnz; ++k) cur[(size_t)(rowval[k] - base) + 1]++;
+    if (gap) out.mid.resize((size_t)nrows);
+    int pos = 0;
+    for (int64_t i = 0; i < nrows; ++i) {
+        const int cnt = cur[(size_t)i + 1];
+        out.ptr[(size_t)i] = pos;
+        cur[(size_t)i] = pos;
+        pos += cnt;
+        if (gap) {
+            out.mid[(size_t)i] = pos;
+            pos += (int)(gap[i + 1] - gap[i]);
+        }
+    }
+    out.ptr[(size_t)nrows] = pos;
+    for (int64_t j = 0; j < ncols; ++j)
+        for (int64_t k = colptr[j] - base; k < colptr[j + 1] - base; ++k) {
+            const int p = cur[(size_t)(rowval[k] - base)]++;
+            out.idx[(size_t)p] = (int)j;
+            out.val[(size_t)p] = nzval[k];
+        }
+}
+
+struct StagedEntry {   // one non-zero on its way from column-major to row-major order
+    int row, col;
+    double val;
+};
+}  // namespace
+
+void csc_to_csr(int64_t nrows, int64_t ncols, const int64_t *colptr, const int64_t *rowval, const double *nzval,
+                int64_t base, HostCsr &out, const int64_t *gap) {
+    // Two-pass bucketed transpose.  A plain counting sort scatters every non-zero to a random cache line of the
+    // output (cfg5: 26 M entries -> ~100 ms on 16 cores); here pass A partitions the entries by row block into a
+    // staging array with <= 512 sequential write streams per thread, and pass B finishes each row block inside a
+    // cache-sized window of the output.  Thread t owns a contiguous block of columns and the staging array is ordered
+    // (row block, thread), so every row keeps ascending column order whatever the thread count (deterministic layout).
+    // gap != nullptr (rows + 1 offsets): row r is followed by gap[r+1] - gap[r] free slots and out.mid[r] marks
+    // where they start -- H = [P A'] is assembled in place this way.
+    const int64_t nnz = colptr[ncols] - base;
+    const int64_t gap_total = gap ? gap[nrows] - gap[0] : 0;
     out.rows = (int)nrows;
     out.cols = (int)ncols;
     out.ptr.assign((size_t)nrows + 1, 0);
-    out.idx.resize((size_t)nnz);
-    out.val.resize((size_t)nnz);
+    out.idx.resize((size_t)(nnz + gap_total));
+    out.val.resize((size_t)(nnz + gap_total));
     int nt = host_threads();
-    if (nnz < (1 << 18)) nt = 1;
+    if (nnz < (1 << 18) || nt == 1) {
+        csc_to_csr_serial(nrows, ncols, colptr, rowval, nzval, base, gap, out);
+        return;
+    }
+    int shift = 0;
+    while ((nrows >> shift) > 512) ++shift;
+    const int64_t nb = ((nrows - 1) >> shift) + 1;
     // column block boundaries balanced by nnz
     std::vector<int64_t> cb((size_t)nt + 1, ncols);
     cb[0] = 0;
@@ -105,39 +150,95 @@ void csc_to_csr(int64_t nrows, int64_t ncols, const int64_t *colptr, const int64
         if (cb[(size_t)t] > ncols) cb[(size_t)t] = ncols;
         if (cb[(size_t)t] < cb[(size_t)t - 1]) cb[(size_t)t] = cb[(size_t)t - 1];
     }
-    std::vector<std::vector<int>> cnt((size_t)nt);
     auto run = [&](const std::function<void(int)> &f) {
-        if (nt == 1) { f(0); return; }
         std::vector<std::thread> th;
         for (int t = 0; t < nt; ++t) th.emplace_back(f, t);
         for (auto &x : th) x.join();
     };
+    // pass 0: entries per (thread, row block)
+    std::vector<int64_t> off((size_t)nt * (size_t)nb, 0);
     run([&](int t) {
-        cnt[(size_t)t].assign((size_t)nrows, 0);
-        int *c = cnt[(size_t)t].data();
-        for (int64_t k = colptr[cb[(size_t)t]] - base; k < colptr[cb[(size_t)t + 1]] - base; ++k) c[rowval[k] - base]++;
+        int64_t *h = off.data() + (size_t)t * (size_t)nb;
+        for (int64_t k = colptr[cb[(size_t)t]] - base; k < colptr[cb[(size_t)t + 1]] - base; ++k) h[(rowval[k] - base) >> shift]++;
     });
-    // per-row totals -> row pointers; per-(thread,row) offsets
-    run([&](int t) {
-        const int64_t r0 = nrows * t / nt, r1 = nrows * (t + 1) / nt;
-        for (int64_t i = r0; i < r1; ++i) {
-            int tot = 0;
-            for (int u = 0; u < nt; ++u) { const int c = cnt[(size_t)u][(size_t)i]; cnt[(size_t)u][(size_t)i] = tot; tot += c; }
-            out.ptr[(size_t)i + 1] = tot;
+    std::vector<int64_t> boff((size_t)nb + 1, 0);
+    {
+        int64_t pos = 0;
+        for (int64_t b = 0; b < nb; ++b) {
+            boff[(size_t)b] = pos;
+            for (int t = 0; t < nt; ++t) {
+                const int64_t c = off[(size_t)t * (size_t)nb + (size_t)b];
+                off[(size_t)t * (size_t)nb + (size_t)b] = pos;
+                pos += c;
+            }
         }
-    });
-    for (int64_t i = 0; i < nrows; ++i) out.ptr[(size_t)i + 1] += out.ptr[(size_t)i];
+        boff[(size_t)nb] = pos;
+    }
+    // pass A: partition into the staging array
+    PodBuf<StagedEntry> stage;
+    stage.resize((size_t)nnz);
     run([&](int t) {
-        int *c = cnt[(size_t)t].data();
-        const int *ptr = out.ptr.data();
+        int64_t *o = off.data() + (size_t)t * (size_t)nb;
+        StagedEntry *st = stage.data();
         for (int64_t j = cb[(size_t)t]; j < cb[(size_t)t + 1]; ++j)
             for (int64_t k = colptr[j] - base; k < colptr[j + 1] - base; ++k) {
                 const int64_t i = rowval[k] - base;
-                const int p = ptr[i] + c[i]++;
-                out.idx[(size_t)p] = (int)j;
-                out.val[(size_t)p] = nzval[k];
+                st[o[i >> shift]++] = StagedEntry{(int)i, (int)j, nzval[k]};
             }
     });
+    // pass B: one row block at a time (dynamic schedule: block sizes follow the row lengths)
+    if (gap) out.mid.resize((size_t)nrows);
+    std::atomic<int64_t> next(0);
+    run([&](int) {
+        std::vector<int> cur((size_t)1 << shift);
+        for (;;) {
+            const int64_t b = next.fetch_add(1);
+            if (b >= nb) break;
+            const int64_t r0 = b << shift, r1 = std::min<int64_t>(nrows, r0 + ((int64_t)1 << shift));
+            const StagedEntry *st = stage.data();
+            std::fill(cur.begin(), cur.begin() + (r1 - r0), 0);
+            for (int64_t e = boff[(size_t)b]; e < boff[(size_t)b + 1]; ++e) cur[(size_t)(st[e].row - r0)]++;
+            int64_t pos = boff[(size_t)b] + (gap ? gap[r0] - gap[0] : 0);
+            for (int64_t r = r0; r < r1; ++r) {
+                const int cnt = cur[(size_t)(r - r0)];
+                out.ptr[(size_t)r] = (int)pos;
+                cur[(size_t)(r - r0)] = (int)pos;
+                pos += cnt;
+                if (gap) {
+                    out.mid[(size_t)r] = (int)pos;
+                    pos += gap[r + 1] - gap[r];
+                }
+            }
+            for (int64_t e = boff[(size_t)b]; e < boff[(size_t)b + 1]; ++e) {
+                const int p = cur[(size_t)(st[e].row - r0)]++;
+                out.idx[(size_t)p] = st[e].col;
+                out.val[(size_t)p] = st[e].val;
+            }
+        }
+    });
+    out.ptr[(size_t)nrows] = (int)(nnz + gap_total);
+}
+
+void assemble_h_direct(int64_t n, int64_t m, const int64_t *Pp, const int64_t *Pi, const double *Pv, const int64_t *Ap,
+                       const int64_t *Ai, const double *Av, int64_t base, HostCsr &H, std::vector<double> &dP,
+                       std::vector<double> &dAA) {
+    csc_to_csr(n, n, Pp, Pi, Pv, base, H, Ap);   // rows of P, each followed by room for the matching column of A
+    H.cols = (int)(n + m);
+    dP.assign((size_t)n, 0.0);
+    dAA.assign((size_t)n, 0.0);
+    parallel_chunks(n, [&](int, int64_t j0, int64_t j1) {
+        for (int64_t j = j0; j < j1; ++j) {
+            for (int k = H.ptr[(size_t)j]; k < H.mid[(size_t)j]; ++k)
+                if (H.idx[(size_t)k] == j) dP[(size_t)j] += H.val[(size_t)k];
+            int pos = H.mid[(size_t)j];
+            for (int64_t k = Ap[j] - base; k < Ap[j + 1] - base; ++k) {
+                H.idx[(size_t)pos] = (int)(Ai[k] - base + n);
+                H.val[(size_t)pos] = Av[k];
+                dAA[(size_t)j] += Av[k] * Av[k];
+                ++pos;
+            }
+        }
+    }, 4096);
 }
 
 void csc_as_csr_of_transpose(int64_t nrows, int64_t ncols, const int64_t *colptr, const int64_t *rowval,

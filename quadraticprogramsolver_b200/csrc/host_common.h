@@ -102,9 +102,15 @@ struct HostTiles {
     int lpr = 1;
 };
 
-// Julia SparseMatrixCSC (cols = ncols) -> CSR of the same matrix.
+// Julia SparseMatrixCSC (cols = ncols) -> CSR of the same matrix.  gap (nrows + 1 offsets, optional): leave
+// gap[r+1] - gap[r] free slots behind row r and record their start in out.mid[r] (in-place assembly of [P A']).
 void csc_to_csr(int64_t nrows, int64_t ncols, const int64_t *colptr, const int64_t *rowval, const double *nzval,
-                int64_t base, HostCsr &out);
+                int64_t base, HostCsr &out, const int64_t *gap = nullptr);
+// H = [P A'] (n x (n+m), SURVEY 8(d) / DESIGN 3) straight from the two CSC inputs: row j = row j of P, then column j
+// of A with its row indices shifted by n; H.mid[j] marks the split.  Also diag(P) and the column square sums of A.
+void assemble_h_direct(int64_t n, int64_t m, const int64_t *Pp, const int64_t *Pi, const double *Pv, const int64_t *Ap,
+                       const int64_t *Ai, const double *Av, int64_t base, HostCsr &H, std::vector<double> &dP,
+                       std::vector<double> &dAA);
 // Julia SparseMatrixCSC -> CSR of the transpose (the same arrays re-indexed).
 void csc_as_csr_of_transpose(int64_t nrows, int64_t ncols, const int64_t *colptr, const int64_t *rowval,
                              const double *nzval, int64_t base, HostCsr &out);

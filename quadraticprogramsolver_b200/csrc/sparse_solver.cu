@@ -128,21 +128,31 @@ int SparseSolver::init(int64_t n64, int64_t m64, const int64_t *Pp, const int64_
 
     n = (int)n64;
     m = (int)m64;
-    // ---- host conversion: CSR(P), CSR(A), CSR(A') -> H = [P A'], A
-    HostCsr P, A, At, H;
-    csc_to_csr(n, n, Pp, Pi, Pv, base, P);
-    csc_to_csr(m, n, Ap, Ai, Av, base, A);
-    csc_as_csr_of_transpose(m, n, Ap, Ai, Av, base, At);
-    lap("transposes");
-    // ---- optional Ruiz equilibration (not in the reference; off by default): from here on P, A, A', q, l, u are the
-    //      scaled problem, the termination norms are brought back to the unscaled one inside the kernel
+    // ---- host conversion: CSC(P), CSC(A) -> H = [P A'] and CSR(A)
     const int scaling_iters = s.reserved_i[QPB200_RSV_SCALING_ITERS];
     if (scaling_iters < 0 || scaling_iters > 1000) return fail(QPB200_ERR_ARG, "settings: scaling iterations must be in [0, 1000]");
+    nnzP = Pp[n] - base;
+    nnzA = Ap[n] - base;
+    if (nnzP + nnzA >= (int64_t(1) << 31) - 64)
+        return fail(QPB200_ERR_ARG, "qpb200_create: nnz(P) + nnz(A) = %lld exceeds the int32 index range", (long long)(nnzP + nnzA));
+    HostCsr A, H;
     std::vector<double> qs, ls, us;
     double nq_unscaled = 0.0;
     for (int64_t j = 0; j < n64; ++j) nq_unscaled = std::fmax(nq_unscaled, std::fabs(q[j]));
+    std::vector<double> dP((size_t)n, 0.0), dAA((size_t)n, 0.0);
     scaled = scaling_iters > 0;
-    if (scaled) {
+    if (!scaled) {
+        assemble_h_direct(n, m, Pp, Pi, Pv, Ap, Ai, Av, base, H, dP, dAA);
+        csc_to_csr(m, n, Ap, Ai, Av, base, A);
+        lap("transposes");
+    } else {
+        // ---- optional Ruiz equilibration (not in the reference; off by default): from here on P, A, A', q, l, u are
+        //      the scaled problem, the termination norms are brought back to the unscaled one inside the kernel
+        HostCsr P, At;
+        csc_to_csr(n, n, Pp, Pi, Pv, base, P);
+        csc_to_csr(m, n, Ap, Ai, Av, base, A);
+        csc_as_csr_of_transpose(m, n, Ap, Ai, Av, base, At);
+        lap("transposes");
         qs.assign(q, q + n);
         ruiz_equilibrate(P, A, At, qs, scaling_iters, scaling);
         ls.resize((size_t)m);
@@ -155,36 +165,33 @@ int SparseSolver::init(int64_t n64, int64_t m64, const int64_t *Pp, const int64_
         l = ls.data();
         u = us.data();
         lap("ruiz");
+        H.rows = n;
+        H.cols = n + m;
+        H.ptr.resize((size_t)n + 1);
+        H.mid.resize((size_t)n);
+        H.idx.resize((size_t)(nnzP + nnzA));
+        H.val.resize((size_t)(nnzP + nnzA));
+        for (int j = 0; j <= n; ++j) H.ptr[(size_t)j] = P.ptr[(size_t)j] + At.ptr[(size_t)j];
+        const int nloc = n;
+        parallel_chunks(n, [&](int, int64_t j0, int64_t j1) {
+            for (int64_t j = j0; j < j1; ++j) {
+                int pos = H.ptr[(size_t)j];
+                for (int k = P.ptr[(size_t)j]; k < P.ptr[(size_t)j + 1]; ++k) {
+                    H.idx[(size_t)pos] = P.idx[(size_t)k];
+                    H.val[(size_t)pos] = P.val[(size_t)k];
+                    if (P.idx[(size_t)k] == j) dP[(size_t)j] += P.val[(size_t)k];
+                    ++pos;
+                }
+                H.mid[(size_t)j] = pos;
+                for (int k = At.ptr[(size_t)j]; k < At.ptr[(size_t)j + 1]; ++k) {
+                    H.idx[(size_t)pos] = At.idx[(size_t)k] + nloc;
+                    H.val[(size_t)pos] = At.val[(size_t)k];
+                    dAA[(size_t)j] += At.val[(size_t)k] * At.val[(size_t)k];
+                    ++pos;
+                }
+            }
+        }, 4096);
     }
-    nnzP = P.nnz();
-    nnzA = A.nnz();
-    H.rows = n;
-    H.cols = n + m;
-    H.ptr.resize((size_t)n + 1);
-    H.mid.resize((size_t)n);
-    H.idx.resize((size_t)(nnzP + nnzA));
-    H.val.resize((size_t)(nnzP + nnzA));
-    std::vector<double> dP((size_t)n, 0.0), dAA((size_t)n, 0.0);
-    for (int j = 0; j <= n; ++j) H.ptr[(size_t)j] = P.ptr[(size_t)j] + At.ptr[(size_t)j];
-    const int nloc = n;
-    parallel_chunks(n, [&](int, int64_t j0, int64_t j1) {
-        for (int64_t j = j0; j < j1; ++j) {
-            int pos = H.ptr[(size_t)j];
-            for (int k = P.ptr[(size_t)j]; k < P.ptr[(size_t)j + 1]; ++k) {
-                H.idx[(size_t)pos] = P.idx[(size_t)k];
-                H.val[(size_t)pos] = P.val[(size_t)k];
-                if (P.idx[(size_t)k] == j) dP[(size_t)j] += P.val[(size_t)k];
-                ++pos;
-            }
-            H.mid[(size_t)j] = pos;
-            for (int k = At.ptr[(size_t)j]; k < At.ptr[(size_t)j + 1]; ++k) {
-                H.idx[(size_t)pos] = At.idx[(size_t)k] + nloc;
-                H.val[(size_t)pos] = At.val[(size_t)k];
-                dAA[(size_t)j] += At.val[(size_t)k] * At.val[(size_t)k];
-                ++pos;
-            }
-        }
-    }, 4096);
     prob.normQ = nq_unscaled;
 
     // ---- grid: co-resident CTAs of the persistent kernel, shrunk for small problems

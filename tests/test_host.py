@@ -236,3 +236,38 @@ def test_host_equilibration_matches_oracle(lib, case):
     Ps.sort_indices(); As.sort_indices()
     np.testing.assert_allclose(Pv, Ps.data, rtol=1e-13)
     np.testing.assert_allclose(Av[:As.nnz], As.data, rtol=1e-13)
+
+
+@pytest.mark.parametrize("n,m,dens,base", [(60, 40, 0.2, 0), (60, 0, 0.2, 1), (3000, 5000, 0.02, 1), (40000, 70000, 3e-4, 0)])
+def test_host_operator_assembly_matches_scipy(lib, n, m, dens, base):
+    """qpb200_create's host conversion (CSC inputs -> H = [P A'] row-major, bucketed parallel transpose for the large
+    case, serial counting sort for the small ones) against scipy: same row pointers, split points, columns in
+    ascending order, bit-identical values; plus diag(P) and the column square sums of A."""
+    from quadraticprogramsolver_b200.solver import _p64, _pd
+    rng = np.random.default_rng(n + m)
+    M = sprandn(rng, n, n, dens)
+    P = sp.csc_matrix(M.T @ M + 0.01 * sp.identity(n))          # symmetric
+    P = sp.csc_matrix(P + sp.triu(sprandn(rng, n, n, dens / 4), 1))   # ... and a non-symmetric part: rows != columns
+    A = sp.csc_matrix(sprandn(rng, m, n, dens)) if m else sp.csc_matrix((0, n))
+    for X in (P, A):
+        X.sort_indices()
+    arrs = []
+    for X in (P, A):
+        arrs += [np.ascontiguousarray(X.indptr, dtype=np.int64) + base, np.ascontiguousarray(X.indices, dtype=np.int64) + base,
+                 np.ascontiguousarray(X.data, dtype=np.float64)]
+    nnz = P.nnz + A.nnz
+    ptr, mid = np.zeros(n + 1, np.int32), np.zeros(n, np.int32)
+    col, val = np.zeros(max(nnz, 1), np.int32), np.zeros(max(nnz, 1))
+    dP, dAA = np.zeros(n), np.zeros(n)
+    p32 = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+    rc = lib.qpb200_debug_assemble_h(n, m, _p64(arrs[0]), _p64(arrs[1]), _pd(arrs[2]), _p64(arrs[3]), _p64(arrs[4]), _pd(arrs[5]),
+                                     base, p32(ptr), p32(mid), p32(col), _pd(val), _pd(dP), _pd(dAA))
+    assert rc == 0, lib.qpb200_last_error()
+    H = sp.hstack([sp.csr_matrix(P), sp.csr_matrix(A.T)], format="csr")
+    H.sort_indices()
+    assert np.array_equal(ptr, H.indptr)
+    assert np.array_equal(col[:nnz], H.indices)
+    assert np.array_equal(val[:nnz], H.data)
+    assert np.array_equal(mid, H.indptr[:-1] + np.diff(sp.csr_matrix(P).indptr))
+    np.testing.assert_array_equal(dP, P.diagonal())
+    np.testing.assert_allclose(dAA, np.asarray(A.multiply(A).sum(axis=0)).ravel(), rtol=1e-14, atol=0)
