@@ -120,6 +120,12 @@ int qpb200_create(qpb200_handle **out, int64_t n, int64_t m,
 int qpb200_solve(qpb200_handle *h, double *x_inout, double *z_out, double *y_out, qpb200_info *info);
 int qpb200_update_vectors(qpb200_handle *h, const double *q, const double *l, const double *u); /* any may be NULL */
 int qpb200_update_settings(qpb200_handle *h, const qpb200_settings *settings);
+/* Per-constraint step size (OSQP's rho vector; the reference's README.md:71-72 TODO):
+ * rho_i = rho * rho_scale[i] in every place SolveQuadraticProgram.jl:56-61 and LinearSystemSolvers.jl:152-157,
+ * 178 use the scalar, i.e. K = P + sigma I + A' diag(rho_i) A, z = clamp(.. + y_i / rho_i), y += rho_i (..);
+ * CheckConvergence and the adaptive update keep working on the scalar rho.  rho_scale[m] > 0 (OSQP: 1e3 on rows
+ * with l == u); NULL restores the scalar.  Takes effect at the next qpb200_solve.  Single-GPU sparse path only. */
+int qpb200_set_rho_scale(qpb200_handle *h, const double *rho_scale);
 void qpb200_destroy(qpb200_handle *h);
 
 /* The operators of the path on their own (SparseArrays mul!, SolveQuadraticProgram.jl:85-89,

@@ -121,8 +121,20 @@ def cg(x, apply_A, b, *, abstol=0.0, reltol=math.sqrt(np.finfo(np.float64).eps),
 # --------------------------------------------------------------------------------------------
 
 def _kkt(mP, mA, rho1, sigma, n, m):
+    """rho1: the scalar 1/rho of the reference, or the vector 1 ./ (rho * rhoScale)."""
+    lower_right = -sp.diags(np.broadcast_to(np.asarray(rho1, dtype=np.float64), (m,)), format="csc")
     return sp.bmat([[mP + sigma * sp.identity(n, format="csc"), mA.T],
-                    [mA, -rho1 * sp.identity(m, format="csc")]], format="csc")
+                    [mA, lower_right]], format="csc")
+
+
+def _rho_vec(st, rho, rho1):
+    """(rho_i, 1/rho_i): the reference's scalars unless the driver stored a per-constraint scale
+    (``rhoScale``, not in the reference) in the plugin state."""
+    rs = st.get("rho_scale")
+    if rs is None:
+        return rho, rho1
+    rv = rho * rs
+    return rv, 1.0 / rv
 
 
 def la_ldl_init(vX, mP, vQ, mA, rho, rho1, sigma, n, m):
@@ -135,7 +147,8 @@ def la_ldl_init(vX, mP, vQ, mA, rho, rho1, sigma, n, m):
 
 def la_ldl(st, vXX, vZZ, vX, mP, vQ, mA, vZ, vY, rho, rho1, sigma, n, m, changedRho):
     """LaLdl! / QDLdl! / FacLdl! (LinearSystemSolvers.jl:28-44,59-75,91-107)."""
-    if changedRho:
+    rho, rho1 = _rho_vec(st, rho, rho1)
+    if changedRho or st.pop("refactor", False):
         st["hDL"] = spla.splu(_kkt(mP, mA, rho1, sigma, n, m))     # :30-32 full refactor
         st["n_factor"] += 1
     vV = st["vV"]
@@ -182,8 +195,12 @@ def _apply_K(st, vZZ, w, rho, sigma):
     """The closure at LinearSystemSolvers.jl:152-157: vZZ = A w; u = A' vZZ; u = P w + rho u;
     u += sigma w.  (It uses the plugin's vZZ as its scratch m-vector.)"""
     vZZ[:] = st["mAr"] @ w
-    u = st["mAt"] @ vZZ
-    u = st["mPr"] @ w + rho * u
+    if st.get("rho_scale") is None:
+        u = st["mAt"] @ vZZ
+        u = st["mPr"] @ w + rho * u
+    else:                                          # K = P + sigma I + A' diag(rho_i) A
+        u = st["mAt"] @ ((rho * st["rho_scale"]) * vZZ)
+        u = st["mPr"] @ w + u
     u = u + sigma * w
     return u
 
@@ -191,7 +208,7 @@ def _apply_K(st, vZZ, w, rho, sigma):
 def lin_op_cg(st, vXX, vZZ, vX, mP, vQ, mA, vZ, vY, rho, rho1, sigma, n, m, changedRho):
     """LinOpCg! / LinMapsCg! (LinearSystemSolvers.jl:164-186,207-229)."""
     vT = st["vT"]
-    vZZ[:] = rho * vZ - vY                                          # :178
+    vZZ[:] = _rho_vec(st, rho, rho1)[0] * vZ - vY                   # :178
     vT[:] = st["mAt"] @ vZZ                                         # :179
     vT[:] = sigma * vX - vQ + vT                                    # :180
     it, _ = cg(vXX, lambda w: _apply_K(st, vZZ, w, rho, sigma), vT,
@@ -212,10 +229,13 @@ def jacobi_pcg_init(vX, mP, vQ, mA, rho, rho1, sigma, n, m):
 
 def jacobi_pcg(st, vXX, vZZ, vX, mP, vQ, mA, vZ, vY, rho, rho1, sigma, n, m, changedRho):
     vT = st["vT"]
-    vZZ[:] = rho * vZ - vY
+    vZZ[:] = _rho_vec(st, rho, rho1)[0] * vZ - vY
     vT[:] = st["mAt"] @ vZZ
     vT[:] = sigma * vX - vQ + vT
-    d = st["dP"] + sigma + rho * st["dAA"]
+    if st.get("rho_scale") is not None and "dAA_scaled" not in st:
+        mAc = sp.csc_matrix(mA)
+        st["dAA_scaled"] = np.asarray(sp.diags(st["rho_scale"]).dot(mAc.multiply(mAc)).sum(axis=0)).ravel()
+    d = st["dP"] + sigma + rho * (st["dAA"] if st.get("rho_scale") is None else st["dAA_scaled"])
     it, _ = cg(vXX, lambda w: _apply_K(st, vZZ, w, rho, sigma), vT,
                abstol=st["eps_pcg"], maxiter=st["num_itr_pcg"], diag_precond=d)
     st["cg_iters"] += it
@@ -273,7 +293,8 @@ def check_convergence(vX, mP, vQ, mA, vZ, vY, vXP, vZP, rho, rhorho, adptRho, ep
 def solve_quadratic_program(vX, mP, vQ, mA, vL, vU, LinSysSolInit, LinSysSol, *,
                             numIterations=5000, epsAbs=1e-6, epsRel=1e-6, rho=1.0, sigma=1e-6, alpha=1.6,
                             delta=1e-6, adptRho=False, fctrRho=5.0, numItrConv=25, numItrPolish=10,
-                            epsMinres=1e-6, numItrMinres=500, epsPcg=None, numItrPcg=None, trace=None, scaling=None):
+                            epsMinres=1e-6, numItrMinres=500, epsPcg=None, numItrPcg=None, trace=None, scaling=None,
+                            rhoScale=None):
     """``SolveQuadraticProgram!`` (SolveQuadraticProgram.jl:14-76).  Mutates ``vX``.
 
     Returns ``(convFlag, info)``; the reference returns only the flag -- ``info`` carries the
@@ -281,6 +302,9 @@ def solve_quadratic_program(vX, mP, vQ, mA, vL, vU, LinSysSolInit, LinSysSol, *,
     ``epsPcg`` / ``numItrPcg`` override the plugin kwargs the reference driver never forwards
     (LinearSystemSolvers.jl:125 vs SolveQuadraticProgram.jl:54); None keeps 1e-6 / 1000.
     ``delta, numItrPolish, epsMinres, numItrMinres`` are accepted and unused, as in the reference.
+    ``rhoScale`` (m positive factors, not in the reference: OSQP's rho vector, README.md:71-72 TODO): constraint i
+    uses ``rho * rhoScale[i]`` wherever :56-61 and the plugin use the scalar; ``CheckConvergence`` and the
+    adaptive update keep the scalar.  Supported by modes D, M and J.
     """
     mP = sp.csc_matrix(mP)
     mA = sp.csc_matrix(mA)
@@ -297,6 +321,11 @@ def solve_quadratic_program(vX, mP, vQ, mA, vL, vU, LinSysSolInit, LinSysSol, *,
         st["eps_pcg"] = epsPcg
     if numItrPcg is not None and "num_itr_pcg" in st:
         st["num_itr_pcg"] = numItrPcg
+    if rhoScale is not None:
+        if "mL" in st:
+            raise ValueError("rhoScale is not implemented for the explicit-matrix CG plugin (mode C)")
+        st["rho_scale"] = np.asarray(rhoScale, dtype=np.float64)
+        st["refactor"] = True                      # direct plugin: the Init factor used the scalar rho
 
     vXP = np.zeros(n)                                               # :38
     vZ = np.zeros(m)
@@ -322,8 +351,9 @@ def solve_quadratic_program(vX, mP, vQ, mA, vL, vU, LinSysSolInit, LinSysSol, *,
         vXP[:] = vX                                                 # :56
         vX[:] = alpha * vXX + alpha1 * vX                           # :57
         vZP[:] = vZ                                                 # :59
-        vZ[:] = _clamp(alpha * vZZ + alpha1 * vZ + rho1 * vY, vL, vU)   # :60
-        vY[:] = vY + rho * (alpha * vZZ + alpha1 * vZP - vZ)        # :61
+        rho_v, rho1_v = _rho_vec(st, rho, rho1)
+        vZ[:] = _clamp(alpha * vZZ + alpha1 * vZ + rho1_v * vY, vL, vU)   # :60
+        vY[:] = vY + rho_v * (alpha * vZZ + alpha1 * vZP - vZ)      # :61
 
         if trace is not None:
             trace(ii, vX, vZ, vY, rho)

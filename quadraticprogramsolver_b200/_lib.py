@@ -50,7 +50,8 @@ class Info(C.Structure):
 # every symbol include/qpb200.h declares
 EXPORTS = [
     "qpb200_version", "qpb200_device_count", "qpb200_default_settings", "qpb200_last_error",
-    "qpb200_create", "qpb200_solve", "qpb200_update_vectors", "qpb200_update_settings", "qpb200_destroy",
+    "qpb200_create", "qpb200_solve", "qpb200_update_vectors", "qpb200_update_settings", "qpb200_set_rho_scale",
+    "qpb200_destroy",
     "qpb200_apply", "qpb200_time_apply", "qpb200_apply_bytes",
     "qpb200_batch_create", "qpb200_batch_solve", "qpb200_batch_destroy",
     "qpb200_dist_unique_id", "qpb200_dist_create", "qpb200_dist_solve",
@@ -80,6 +81,7 @@ def load():
     lib.qpb200_solve.argtypes = [pv, pd, pd, pd, C.POINTER(Info)]
     lib.qpb200_update_vectors.argtypes = [pv, pd, pd, pd]
     lib.qpb200_update_settings.argtypes = [pv, C.POINTER(Settings)]
+    lib.qpb200_set_rho_scale.argtypes = [pv, pd]
     lib.qpb200_destroy.argtypes = [pv]
     lib.qpb200_destroy.restype = None
     lib.qpb200_apply.argtypes = [pv, C.c_int32, pd, pd]

@@ -47,6 +47,9 @@ struct SparseProblemDev {
     // optional (Ruiz equilibration): D, 1/(c D) [n] and 1/E [m] turn the norms of CheckConvergence back into
     // those of the unscaled problem; nullptr = the problem is solved as given (the reference's behaviour)
     const double *Dv, *Dinvc, *Einv;
+    // optional per-constraint step size (qpb200_set_rho_scale; not in the reference): rho_i = rho * rs[i].
+    // nullptr = one scalar rho as in SolveQuadraticProgram.jl:16; dAA then holds sum_i rs[i] A_ij^2
+    const double *rs;
     GridSync gs;
     AdmmSettingsDev s;
     AdmmInfoDev *info;
@@ -105,6 +108,9 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) admm_kernel(SparseProblemD
     double res_prim = nan(""), res_dual = nan("");
     const double reltol = p.s.pcg_rel_eps;
     bool dinv_ready = false;
+    // rho and 1/rho of constraint i (the scalars of SolveQuadraticProgram.jl:30 unless a scale vector was set)
+    auto rho_of = [&](int i) { return p.rs ? rho * p.rs[i] : rho; };
+    auto rho1_of = [&](int i) { return p.rs ? 1.0 / (rho * p.rs[i]) : rho1; };
 
     long long ii = 0;
     for (ii = 1; ii <= p.s.max_iter; ++ii) {                        // :45
@@ -120,7 +126,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) admm_kernel(SparseProblemD
             if (PRE)
                 for (int j = gtid; j < n; j += gstride) p.dinv[j] = 1.0 / (p.dP[j] + sigma + rho * p.dAA[j]);
             if (changed)
-                for (int i = gtid; i < m; i += gstride) g[i] = rho * (p.zt[i] - p.z[i]) + y[i];
+                for (int i = gtid; i < m; i += gstride) g[i] = rho_of(i) * (p.zt[i] - p.z[i]) + y[i];
             dinv_ready = true;
             grid_barrier(p.gs, st);
         }
@@ -151,7 +157,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) admm_kernel(SparseProblemD
         while (k < p.s.pcg_max_iter && !(residual <= tol)) {
             // [S2] t = rho * A u
             {
-                auto epi = [&](int i, double s0, double) { t[i] = rho * s0; };
+                auto epi = [&](int i, double s0, double) { t[i] = rho_of(i) * s0; };
                 spmv_tiles<TMA, false>(p.A, u, sm, ps, epi);
                 ++n_a;
             }
@@ -205,12 +211,13 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) admm_kernel(SparseProblemD
                 const double zt_i = s0;
                 const double z_old = p.z[i], y_old = y[i];
                 const double zr = alpha * zt_i + alpha1 * z_old;
-                const double z_new = clamp_julia(zr + rho1 * y_old, p.l[i], p.u[i]);   // :60
-                const double y_new = y_old + rho * (zr - z_new);                       // :61
+                const double rho_i = rho_of(i);
+                const double z_new = clamp_julia(zr + rho1_of(i) * y_old, p.l[i], p.u[i]);   // :60
+                const double y_new = y_old + rho_i * (zr - z_new);                     // :61
                 p.z[i] = z_new;
                 y[i] = y_new;
                 p.zt[i] = zt_i;
-                g[i] = rho * (zt_i - z_new) + y_new;
+                g[i] = rho_i * (zt_i - z_new) + y_new;
                 const double ei = (p.Einv && do_check) ? p.Einv[i] : 1.0;
                 nrm[1] = nanmax(nrm[1], fabs(z_new - z_old) * ei);
             };

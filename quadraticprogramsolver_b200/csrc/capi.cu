@@ -80,12 +80,20 @@ int qpb200_solve(qpb200_handle *h, double *x_inout, double *z_out, double *y_out
 
 int qpb200_update_vectors(qpb200_handle *h, const double *q, const double *l, const double *u) {
     if (!h) return qpb::fail(QPB200_ERR_ARG, "qpb200_update_vectors: handle is NULL");
+    if (h->dist) return qpb::fail(QPB200_ERR_ARG, "qpb200_update_vectors: not implemented for distributed handles");
     return h->solver.update_vectors(q, l, u);
 }
 
 int qpb200_update_settings(qpb200_handle *h, const qpb200_settings *settings) {
     if (!h || !settings) return qpb::fail(QPB200_ERR_ARG, "qpb200_update_settings: NULL argument");
+    if (h->dist) return qpb::fail(QPB200_ERR_ARG, "qpb200_update_settings: not implemented for distributed handles");
     return h->solver.settings_to_dev(*settings);
+}
+
+int qpb200_set_rho_scale(qpb200_handle *h, const double *rho_scale) {
+    if (!h) return qpb::fail(QPB200_ERR_ARG, "qpb200_set_rho_scale: handle is NULL");
+    if (h->dist) return qpb::fail(QPB200_ERR_ARG, "qpb200_set_rho_scale: not implemented for distributed handles");
+    return h->solver.set_rho_scale(rho_scale);
 }
 
 void qpb200_destroy(qpb200_handle *h) {

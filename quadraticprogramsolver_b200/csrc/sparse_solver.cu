@@ -19,6 +19,14 @@ __global__ void scale_kernel(double *v, double a, int n) {
 __global__ void axpy_kernel(double *y, const double *x, double a, int n) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) y[i] += a * x[i];
 }
+// column sums of rs[i] * A_ij^2 out of H = [P A']: row j of H carries column j of A behind rowmid[j]
+__global__ void scaled_colsq_kernel(CsrTiled H, int n, const double *rs, double *out) {
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        double acc = 0.0;
+        for (int k = H.rowmid[j]; k < H.rowptr[j + 1]; ++k) acc += rs[H.col[k] - n] * (H.val[k] * H.val[k]);
+        out[j] = acc;
+    }
+}
 // L2 flush by READING a buffer larger than L2 (a writing flush would leave dirty lines whose
 // write-back is then charged to the kernel being timed)
 __global__ void flush_kernel(const double *buf, size_t n, double *sink) {
@@ -256,7 +264,8 @@ int SparseSolver::init(int64_t n64, int64_t m64, const int64_t *Pp, const int64_
     QPB_CUDA(cudaMemcpy(ddP, dP.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
     QPB_CUDA(cudaMemcpy(ddAA, dAA.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
     prob.q = dq; prob.l = dl; prob.u = du; prob.dP = ddP; prob.dAA = ddAA;
-    d_q = dq; d_l = dl; d_u = du;
+    d_q = dq; d_l = dl; d_u = du; d_dAA = ddAA;
+    prob.rs = nullptr;
     prob.Dv = prob.Dinvc = prob.Einv = nullptr;
     if (scaled) {
         std::vector<double> dinvc((size_t)n), einv((size_t)m);
@@ -391,6 +400,28 @@ int SparseSolver::solve(double *x_inout, double *z_out, double *y_out, qpb200_in
     if (getenv("QPB200_TIMING"))
         fprintf(stderr, "[qpb200_solve] device %.1f ms, wall %.1f ms\n", ms,
                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count());
+    return QPB200_OK;
+}
+
+int SparseSolver::set_rho_scale(const double *rs) {
+    QPB_CUDA(cudaSetDevice(device));
+    if (!rs) {                                      // back to the scalar rho of the reference
+        prob.rs = nullptr;
+        prob.dAA = d_dAA;
+        return QPB200_OK;
+    }
+    for (int i = 0; i < m; ++i)
+        if (!(rs[i] > 0.0) || !std::isfinite(rs[i])) return fail(QPB200_ERR_ARG, "qpb200_set_rho_scale: entry %d must be positive and finite", i);
+    if (!d_rs) {
+        QPB_CUDA(arena.alloc(&d_rs, (size_t)std::max(m, 1)));
+        QPB_CUDA(arena.alloc(&d_dAA_scaled, (size_t)n));
+    }
+    if (m) QPB_CUDA(cudaMemcpyAsync(d_rs, rs, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, stream));
+    scaled_colsq_kernel<<<std::max(1, std::min(1024, (n + 255) / 256)), 256, 0, stream>>>(prob.H, n, d_rs, d_dAA_scaled);
+    QPB_CUDA(cudaGetLastError());
+    QPB_CUDA(cudaStreamSynchronize(stream));         // rs is a borrowed host array
+    prob.rs = d_rs;
+    prob.dAA = d_dAA_scaled;
     return QPB200_OK;
 }
 

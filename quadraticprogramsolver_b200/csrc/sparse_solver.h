@@ -15,6 +15,7 @@ struct SparseSolver {
     AdmmInfoDev last_info{};
     DeviceArena arena;
     double *d_q = nullptr, *d_l = nullptr, *d_u = nullptr;
+    double *d_dAA = nullptr, *d_rs = nullptr, *d_dAA_scaled = nullptr;   // column square sums of A: plain / weighted by rs
     double *scratch = nullptr, *flush_buf = nullptr;
     unsigned long long *sync_words = nullptr;
     cudaStream_t stream = nullptr;
@@ -37,6 +38,7 @@ struct SparseSolver {
     int apply_device(int which, const double *x, double *y);
     int time_apply(int which, int reps, int flush_l2, double *ms_out);
     int update_vectors(const double *q, const double *l, const double *u);
+    int set_rho_scale(const double *rs);            // m positive factors or nullptr (scalar rho)
     int64_t spmv_bytes(int which) const;
     int64_t solve_bytes() const;
 };

@@ -89,6 +89,30 @@ def make_settings(**kw) -> Settings:
     return s
 
 
+def equality_rho_scale(vL, vU, factor=1e3):
+    """OSQP's rho vector as a scale on the scalar rho: ``factor`` on equality rows (``l == u``), 1 elsewhere
+    (Stellato et al. 2020, section 5.2: RHO_EQ_OVER_RHO_INEQ = 1e3).  Input for ``rhoScale``."""
+    vL = np.asarray(vL, dtype=np.float64)
+    vU = np.asarray(vU, dtype=np.float64)
+    return np.where(vL == vU, float(factor), 1.0)
+
+
+def _pop_rho_scale(kw, vL, vU):
+    """``rhoScale`` (m positive factors) or ``rhoEqScale`` (factor for the equality rows) -> array or None."""
+    rs = kw.pop("rhoScale", None)
+    eq = kw.pop("rhoEqScale", None)
+    if rs is not None and eq is not None:
+        raise TypeError("pass rhoScale or rhoEqScale, not both")
+    if eq is not None:
+        rs = equality_rho_scale(vL, vU, eq)
+    if rs is None:
+        return None
+    rs = np.ascontiguousarray(rs, dtype=np.float64)
+    if rs.shape != np.shape(vL):
+        raise ValueError("rhoScale must have one entry per constraint")
+    return rs
+
+
 def _pd(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
@@ -121,11 +145,24 @@ class QPB200Solver:
             raise ValueError("dimension mismatch in q, l or u")
         Pp, Pi, Pv = _csc_arrays(mP)
         Ap, Ai, Av = _csc_arrays(mA)
+        rho_scale = _pop_rho_scale(kw, vL, vU)
         self.settings = make_settings(**kw)
         self._h = C.c_void_p()
         _lib.check(lib.qpb200_create(C.byref(self._h), self.n, self.m, _p64(Pp), _p64(Pi), _pd(Pv), _p64(Ap), _p64(Ai),
                                      _pd(Av), _pd(vQ), _pd(vL), _pd(vU), C.byref(self.settings), 0))
         self.info = None
+        if rho_scale is not None:
+            self.set_rho_scale(rho_scale)
+
+    def set_rho_scale(self, rho_scale):
+        """Per-constraint step size ``rho_i = rho * rho_scale[i]`` (``None`` = the reference's scalar rho)."""
+        if rho_scale is None:
+            _lib.check(_lib.load().qpb200_set_rho_scale(self._h, None))
+            return
+        rs = np.ascontiguousarray(rho_scale, dtype=np.float64)
+        if rs.shape != (self.m,):
+            raise ValueError("rho_scale must have one entry per constraint")
+        _lib.check(_lib.load().qpb200_set_rho_scale(self._h, _pd(rs)))
 
     def solve(self, vX, want_zy: bool = False):
         """Solve from start point ``vX`` (mutated in place).  Returns the ConvergenceFlag."""

@@ -361,3 +361,63 @@ def test_scaling_is_rejected_where_it_is_not_implemented(lib):
     with pytest.raises(S.QPB200Error):
         S.QPB200Batch(P, rng.standard_normal((b, n)), A_cm, -np.ones((b, m)), np.ones((b, m)), numItrScaling=5)
 
+
+
+# ---------------------------------------------------------------------------------------------------
+# Per-constraint rho (second half): qpb200_set_rho_scale against the oracle's rhoScale
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["cfg1", "equality_n100", "svm_inf_bounds", "sparse_5k_scaled"])
+def test_rho_scale_matches_oracle(lib, case):
+    S = _solver()
+    kw = dict(rho=0.1, adptRho=True, numIterations=3000, epsPcg=1e-10)
+    if case == "cfg1":
+        P, q, A, l, u = config_cfg1(seed=1235)
+    elif case == "equality_n100":
+        P, q, A, l, u = GenerateRandomQP(ProblemClass.equalityConstrainedQp, 100, numConstraints=50, seed=3)
+        kw["adptRho"] = False                       # rho_i = 1e3 rho already; a larger rho only hurts the inner CG
+    elif case == "svm_inf_bounds":
+        P, q, A, l, u = GenerateRandomQP(ProblemClass.supportVectorMachine, 10, seed=5)
+    else:                                            # together with the equilibration, iterates compared at a cap
+        P, q, A, l, u = config_sparse(5000, 10000, 1e-3, seed=9)
+        kw.update(numIterations=50, numItrScaling=10)
+    # (the sparse case uses a milder factor: 1e3 costs ~500 CG iterations per ADMM iteration in the CPU oracle)
+    rs = S.equality_rho_scale(l, u, 10.0 if case == "sparse_5k_scaled" else 1e3)
+    rs[::3] *= 2.0
+    x_ref, flag_ref, info_ref = qp_oracle.solve(P, q, A, l, u, mode="J", rhoScale=rs, **kw)
+    x = np.zeros(P.shape[0])
+    with S.QPB200Solver(P, q, A, l, u, rhoScale=rs, **kw) as s:
+        flag = s.solve(x, want_zy=True)
+        info = dict(s.info)
+        # clearing the vector restores the scalar iteration bit for bit
+        s.set_rho_scale(None)
+        x_a = np.zeros(P.shape[0])
+        flag_a = s.solve(x_a)
+        it_a = s.info["iterations"]
+    _assert_parity(x, flag, info, x_ref, flag_ref, info_ref["iterations"])
+    assert info["rho_updates"] == info_ref["rho_updates"]
+    assert np.max(np.abs(info["y"] - info_ref["y"])) <= 1e-6 * (1.0 + np.max(np.abs(info_ref["y"])))
+    assert np.max(np.abs(info["z"] - info_ref["z"])) <= 1e-6 * (1.0 + np.max(np.abs(info_ref["z"])))
+    x_b = np.zeros(P.shape[0])
+    with S.QPB200Solver(P, q, A, l, u, **kw) as s:
+        flag_b = s.solve(x_b)
+        it_b = s.info["iterations"]
+    assert int(flag_a) == int(flag_b) and it_a == it_b and np.array_equal(x_a, x_b)
+
+
+def test_rho_eq_scale_keyword_and_argument_checks(lib):
+    S = _solver()
+    P, q, A, l, u = GenerateRandomQP(ProblemClass.equalityConstrainedQp, 100, numConstraints=50, seed=1)
+    kw = dict(rho=0.1, numIterations=20000, epsPcg=1e-10)
+    x0, x1 = np.zeros(100), np.zeros(100)
+    with S.QPB200Solver(P, q, A, l, u, **kw) as s:
+        s.solve(x0)
+        it0 = s.info["iterations"]
+        with pytest.raises(S.QPB200Error):
+            s.set_rho_scale(np.zeros(50))            # factors must be positive
+        with pytest.raises(S.QPB200Error):
+            s.set_rho_scale(np.full(50, np.inf))
+    with S.QPB200Solver(P, q, A, l, u, rhoEqScale=1e3, **kw) as s:
+        f1 = s.solve(x1, want_zy=True)
+        it1, y1 = s.info["iterations"], s.info["y"]
+    assert int(f1) != 1 and it1 < it0
+    assert max(qp_oracle.kkt_certificate(P, q, A, l, u, x1, y1).values()) < 1e-4

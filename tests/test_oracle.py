@@ -172,3 +172,44 @@ def test_scaling_rescues_a_badly_scaled_problem():
     eps_p = 1e-6 + 1e-6 * max(np.max(np.abs(A @ x1)), np.max(np.abs(i1["z"])))
     eps_d = 1e-6 + 1e-6 * max(np.max(np.abs(P @ x1)), np.max(np.abs(A.T @ i1["y"])), np.max(np.abs(q)))
     assert rp < 1.01 * eps_p and rd < 1.01 * eps_d
+
+
+# ---------------------------------------------------------------------------------------------------
+# per-constraint rho (rhoScale; OSQP's rho vector -- not in the reference)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("pc,n", [(ProblemClass.randomQp, 100), (ProblemClass.equalityConstrainedQp, 100),
+                                  (ProblemClass.supportVectorMachine, 10)])
+def test_rho_scale_modes_agree_and_solution_is_unchanged(pc, n):
+    """rho_i = rho * s_i changes the path of the iteration, not its fixed point: modes D and J agree with each
+    other, the KKT certificate holds, and the solution equals the scalar-rho one."""
+    P, q, A, l, u = GenerateRandomQP(pc, n, numConstraints=_dims(pc, n), seed=3)
+    rs = np.where(l == u, 1e3, 1.0)
+    rs[::3] *= 2.0                                     # an arbitrary positive vector, not only the equality rule
+    kw = dict(rho=0.1, adptRho=True, numIterations=20000, epsAbs=1e-8, epsRel=1e-8)
+    xd, fd, infod = qp_oracle.solve(P, q, A, l, u, mode="D", rhoScale=rs, **kw)
+    xj, fj, infoj = qp_oracle.solve(P, q, A, l, u, mode="J", rhoScale=rs, epsPcg=1e-10, **kw)
+    x0, f0, _ = qp_oracle.solve(P, q, A, l, u, mode="D", **kw)
+    assert int(fd) != 1 and int(fd) == int(fj) and infod["iterations"] == infoj["iterations"]
+    sc = 1.0 + np.max(np.abs(x0))
+    assert np.max(np.abs(xd - xj)) <= 1e-7 * sc
+    assert np.max(np.abs(xd - x0)) <= 1e-5 * sc
+    assert max(qp_oracle.kkt_certificate(P, q, A, l, u, xd, infod["y"]).values()) < 1e-5
+
+
+def test_rho_scale_of_ones_is_the_scalar_iteration():
+    P, q, A, l, u = config_cfg1(seed=1234)
+    kw = dict(rho=0.1, adptRho=True, numIterations=3000)
+    for mode in ("D", "J"):
+        x0, f0, i0 = qp_oracle.solve(P, q, A, l, u, mode=mode, **kw)
+        x1, f1, i1 = qp_oracle.solve(P, q, A, l, u, mode=mode, rhoScale=np.ones(A.shape[0]), **kw)
+        assert int(f0) == int(f1) and i0["iterations"] == i1["iterations"]
+        assert np.max(np.abs(x0 - x1)) <= 1e-8 * (1 + np.max(np.abs(x0)))   # rounding order differs, CG amplifies it
+
+
+def test_equality_rho_scale_cuts_iterations_on_an_equality_constrained_qp():
+    from quadraticprogramsolver_b200.solver import equality_rho_scale
+    P, q, A, l, u = GenerateRandomQP(ProblemClass.equalityConstrainedQp, 100, seed=1)
+    kw = dict(rho=0.1, numIterations=20000)
+    _, f0, i0 = qp_oracle.solve(P, q, A, l, u, mode="D", **kw)
+    _, f1, i1 = qp_oracle.solve(P, q, A, l, u, mode="D", rhoScale=equality_rho_scale(l, u), **kw)
+    assert int(f1) != 1 and i1["iterations"] < i0["iterations"]
