@@ -352,6 +352,7 @@ size_t cache_limit() {
 constexpr size_t kCacheMinBlock = 1 << 20;   // only blocks >= 1 MB are worth keeping
 BlockCache &dev_cache() { static BlockCache c; return c; }
 BlockCache &host_cache() { static BlockCache c; return c; }
+BlockCache &pinned_cache() { static BlockCache c; return c; }
 
 void *take(BlockCache &c, size_t bytes, size_t *cap) {
     std::lock_guard<std::mutex> g(c.mu);
@@ -438,6 +439,36 @@ void cached_host_free(void *p, size_t capacity) {
     if (!p) return;
     if (give(host_cache(), p, capacity, kCacheMinBlock)) return;
     free(p);
+}
+
+void *cached_pinned_alloc(size_t bytes, size_t *capacity, bool *pinned) {
+    *pinned = false;
+    if (bytes < kCacheMinBlock) {                    // small arrays: pinning costs more than it saves
+        *capacity = bytes;
+        return malloc(bytes);
+    }
+    if (void *q = take(pinned_cache(), bytes, capacity)) {
+        *pinned = true;
+        return q;
+    }
+    void *q = nullptr;
+    if (cudaHostAlloc(&q, bytes, cudaHostAllocPortable) == cudaSuccess) {
+        *capacity = bytes;
+        *pinned = true;
+        return q;
+    }
+    cudaGetLastError();                              // not fatal: fall back to pageable memory
+    return cached_host_alloc(bytes, capacity);
+}
+
+void cached_pinned_free(void *p, size_t capacity, bool pinned) {
+    if (!p) return;
+    if (!pinned) {
+        cached_host_free(p, capacity);
+        return;
+    }
+    if (give(pinned_cache(), p, capacity, kCacheMinBlock)) return;
+    cudaFreeHost(p);
 }
 
 namespace {

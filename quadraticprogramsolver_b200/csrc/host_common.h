@@ -37,6 +37,11 @@ cudaError_t cached_device_alloc(void **p, size_t bytes, size_t *capacity);
 void cached_device_free(void *p, size_t capacity);
 void *cached_host_alloc(size_t bytes, size_t *capacity);
 void cached_host_free(void *p, size_t capacity);
+// Page-locked flavour for the arrays that are uploaded (H2D from pinned memory runs at PCIe speed and can overlap the
+// host conversion; pageable copies measured 11 GB/s).  *pinned tells the caller what it got: when cudaHostAlloc
+// fails (or no device is present) the block is plain malloc memory.
+void *cached_pinned_alloc(size_t bytes, size_t *capacity, bool *pinned);
+void cached_pinned_free(void *p, size_t capacity, bool pinned);
 
 struct DeviceArena {
     std::vector<std::pair<void *, size_t>> ptrs;
@@ -70,13 +75,24 @@ template <class T>
 struct PodBuf {
     T *p = nullptr;
     size_t n = 0, cap = 0;
+    bool want_pinned = false;   // set before resize(): page-locked memory for buffers that get uploaded
+    bool is_pinned = false;
     PodBuf() = default;
     PodBuf(const PodBuf &) = delete;
     PodBuf &operator=(const PodBuf &) = delete;
-    ~PodBuf() { if (p) cached_host_free(p, cap); }
+    ~PodBuf() { drop(); }
+    void drop() {
+        if (!p) return;
+        if (is_pinned) cached_pinned_free(p, cap, true);
+        else cached_host_free(p, cap);
+        p = nullptr;
+    }
     void resize(size_t k) {
-        if (p) cached_host_free(p, cap);
-        p = static_cast<T *>(cached_host_alloc((k > 0 ? k : 1) * sizeof(T), &cap));
+        drop();
+        const size_t bytes = (k > 0 ? k : 1) * sizeof(T);
+        is_pinned = false;
+        if (want_pinned) p = static_cast<T *>(cached_pinned_alloc(bytes, &cap, &is_pinned));
+        else p = static_cast<T *>(cached_host_alloc(bytes, &cap));
         n = k;
     }
     T *data() { return p; }

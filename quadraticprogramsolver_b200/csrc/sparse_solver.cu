@@ -35,27 +35,25 @@ __global__ void flush_kernel(const double *buf, size_t n, double *sink) {
     if (s == 123.456) *sink = s;
 }
 
-static int upload_tiled(DeviceArena &ar, const HostCsr &M, const HostTiles &T, CsrTiled &d) {
-    int *rowptr = nullptr, *rowmid = nullptr, *col = nullptr, *cta = nullptr;
+// Bulk arrays of a tiled CSR matrix (row pointers, split points, columns, values): asynchronous on `st`, so the copy
+// of one matrix overlaps the host conversion of the next; the host arrays must stay alive until `st` is synchronised.
+static int upload_matrix(DeviceArena &ar, const HostCsr &M, CsrTiled &d, cudaStream_t st) {
+    int *rowptr = nullptr, *rowmid = nullptr, *col = nullptr;
     double *val = nullptr;
-    int4 *tiles = nullptr;
     const size_t nnz = (size_t)M.nnz();
     QPB_CUDA(ar.alloc(&rowptr, M.ptr.size()));
-    QPB_CUDA(ar.alloc(&col, nnz + 16, true));
-    QPB_CUDA(ar.alloc(&val, nnz + 16, true));
-    QPB_CUDA(ar.alloc(&tiles, T.tiles.size()));
-    QPB_CUDA(ar.alloc(&cta, T.cta_begin.size()));
-    QPB_CUDA(cudaMemcpy(rowptr, M.ptr.data(), M.ptr.size() * sizeof(int), cudaMemcpyHostToDevice));
+    QPB_CUDA(ar.alloc(&col, nnz + 16));
+    QPB_CUDA(ar.alloc(&val, nnz + 16));
+    QPB_CUDA(cudaMemcpyAsync(rowptr, M.ptr.data(), M.ptr.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     if (nnz) {
-        QPB_CUDA(cudaMemcpy(col, M.idx.data(), nnz * sizeof(int), cudaMemcpyHostToDevice));
-        QPB_CUDA(cudaMemcpy(val, M.val.data(), nnz * sizeof(double), cudaMemcpyHostToDevice));
+        QPB_CUDA(cudaMemcpyAsync(col, M.idx.data(), nnz * sizeof(int), cudaMemcpyHostToDevice, st));
+        QPB_CUDA(cudaMemcpyAsync(val, M.val.data(), nnz * sizeof(double), cudaMemcpyHostToDevice, st));
     }
-    if (!T.tiles.empty())
-        QPB_CUDA(cudaMemcpy(tiles, T.tiles.data(), T.tiles.size() * sizeof(int4), cudaMemcpyHostToDevice));
-    QPB_CUDA(cudaMemcpy(cta, T.cta_begin.data(), T.cta_begin.size() * sizeof(int), cudaMemcpyHostToDevice));
+    QPB_CUDA(cudaMemsetAsync(col + nnz, 0, 16 * sizeof(int), st));       // the tile loaders read whole 16-byte groups
+    QPB_CUDA(cudaMemsetAsync(val + nnz, 0, 16 * sizeof(double), st));
     if (!M.mid.empty()) {
         QPB_CUDA(ar.alloc(&rowmid, M.mid.size()));
-        QPB_CUDA(cudaMemcpy(rowmid, M.mid.data(), M.mid.size() * sizeof(int), cudaMemcpyHostToDevice));
+        QPB_CUDA(cudaMemcpyAsync(rowmid, M.mid.data(), M.mid.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     }
     d.rows = M.rows;
     d.cols = M.cols;
@@ -63,12 +61,31 @@ static int upload_tiled(DeviceArena &ar, const HostCsr &M, const HostTiles &T, C
     d.rowmid = rowmid;
     d.col = col;
     d.val = val;
+    return QPB200_OK;
+}
+
+// The tile plan (depends on the grid size, which is known only when both matrices have been tiled).
+static int upload_plan(DeviceArena &ar, const HostTiles &T, CsrTiled &d, cudaStream_t st) {
+    int4 *tiles = nullptr;
+    int *cta = nullptr;
+    QPB_CUDA(ar.alloc(&tiles, T.tiles.size()));
+    QPB_CUDA(ar.alloc(&cta, T.cta_begin.size()));
+    if (!T.tiles.empty())
+        QPB_CUDA(cudaMemcpyAsync(tiles, T.tiles.data(), T.tiles.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+    QPB_CUDA(cudaMemcpyAsync(cta, T.cta_begin.data(), T.cta_begin.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     d.tiles = tiles;
     d.cta_begin = cta;
     d.ntiles = (int)T.tiles.size();
     d.lpr = T.lpr;
     return QPB200_OK;
 }
+
+namespace {
+struct StreamSyncGuard {   // pending async uploads must drain before the host staging arrays are released
+    cudaStream_t &st;
+    ~StreamSyncGuard() { if (st) cudaStreamSynchronize(st); }
+};
+}  // namespace
 
 static int prep_kernel(const void *kernel, int *blocks_per_sm) {
     QPB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpmvSmem)));
@@ -136,6 +153,40 @@ int SparseSolver::init(int64_t n64, int64_t m64, const int64_t *Pp, const int64_
 
     n = (int)n64;
     m = (int)m64;
+    // ---- grid limit: co-resident CTAs of the persistent kernel
+    QPB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
+    int per_sm = 1 << 30, tmp = 0;
+    {
+        // shared-memory opt-in + occupancy of every kernel variant: once per device and process
+        static std::mutex mu;
+        static int cached_per_sm[64];
+        std::lock_guard<std::mutex> g(mu);
+        const bool cacheable = device >= 0 && device < 64;
+        if (cacheable && cached_per_sm[device] > 0) {
+            per_sm = cached_per_sm[device];
+        } else {
+            for (const void *fn : {(const void *)admm_kernel<0, false>, (const void *)admm_kernel<0, true>, (const void *)admm_kernel<1, false>,
+                                   (const void *)admm_kernel<1, true>, (const void *)admm_kernel<2, false>, (const void *)admm_kernel<2, true>}) {
+                if ((rc = prep_kernel(fn, &tmp))) return rc;
+                per_sm = std::min(per_sm, tmp);
+            }
+            for (const void *fn : {(const void *)spmv_kernel<0, false>, (const void *)spmv_kernel<0, true>, (const void *)spmv_kernel<1, false>,
+                                   (const void *)spmv_kernel<1, true>, (const void *)spmv_kernel<2, false>, (const void *)spmv_kernel<2, true>})
+                if ((rc = prep_kernel(fn, &tmp))) return rc;
+            if (cacheable) cached_per_sm[device] = per_sm;
+        }
+    }
+    if (per_sm < 1) return fail(QPB200_ERR_CUDA, "persistent kernel does not fit on an SM");
+    {
+        const char *e = getenv("QPB200_CTAS_PER_SM");   // A/B experiments only
+        per_sm = std::min(per_sm, e ? std::max(1, atoi(e)) : kMinCtas);
+    }
+    const int grid_max = num_sms * per_sm;
+
+    QPB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    QPB_CUDA(cudaEventCreate(&ev0));
+    QPB_CUDA(cudaEventCreate(&ev1));
+    lap("kernel_prep");
     // ---- host conversion: CSC(P), CSC(A) -> H = [P A'] and CSR(A)
     const int scaling_iters = s.reserved_i[QPB200_RSV_SCALING_ITERS];
     if (scaling_iters < 0 || scaling_iters > 1000) return fail(QPB200_ERR_ARG, "settings: scaling iterations must be in [0, 1000]");
@@ -144,6 +195,9 @@ int SparseSolver::init(int64_t n64, int64_t m64, const int64_t *Pp, const int64_
     if (nnzP + nnzA >= (int64_t(1) << 31) - 64)
         return fail(QPB200_ERR_ARG, "qpb200_create: nnz(P) + nnz(A) = %lld exceeds the int32 index range", (long long)(nnzP + nnzA));
     HostCsr A, H;
+    HostTiles TH, TA;
+    StreamSyncGuard drain{stream};                   // declared after H and A: runs before their buffers are released
+    H.idx.want_pinned = H.val.want_pinned = A.idx.want_pinned = A.val.want_pinned = true;
     std::vector<double> qs, ls, us;
     double nq_unscaled = 0.0;
     for (int64_t j = 0; j < n64; ++j) nq_unscaled = std::fmax(nq_unscaled, std::fabs(q[j]));
@@ -151,8 +205,11 @@ int SparseSolver::init(int64_t n64, int64_t m64, const int64_t *Pp, const int64_
     scaled = scaling_iters > 0;
     if (!scaled) {
         assemble_h_direct(n, m, Pp, Pi, Pv, Ap, Ai, Av, base, H, dP, dAA);
+        lap("assemble_H");
+        if ((rc = upload_matrix(arena, H, prob.H, stream))) return rc;   // copies while A is being transposed
+        build_tiles(H, kTileNnz, TH);
         csc_to_csr(m, n, Ap, Ai, Av, base, A);
-        lap("transposes");
+        lap("transpose_A");
     } else {
         // ---- optional Ruiz equilibration (not in the reference; off by default): from here on P, A, A', q, l, u are
         //      the scaled problem, the termination norms are brought back to the unscaled one inside the kernel
@@ -199,44 +256,14 @@ int SparseSolver::init(int64_t n64, int64_t m64, const int64_t *Pp, const int64_
                 }
             }
         }, 4096);
+        lap("assemble_H");
+        if ((rc = upload_matrix(arena, H, prob.H, stream))) return rc;
+        build_tiles(H, kTileNnz, TH);
     }
+    if ((rc = upload_matrix(arena, A, prob.A, stream))) return rc;
+    build_tiles(A, kTileNnz, TA);
     prob.normQ = nq_unscaled;
 
-    // ---- grid: co-resident CTAs of the persistent kernel, shrunk for small problems
-    lap("assemble_H");
-    QPB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
-    int per_sm = 1 << 30, tmp = 0;
-    {
-        // shared-memory opt-in + occupancy of every kernel variant: once per device and process
-        static std::mutex mu;
-        static int cached_per_sm[64];
-        std::lock_guard<std::mutex> g(mu);
-        const bool cacheable = device >= 0 && device < 64;
-        if (cacheable && cached_per_sm[device] > 0) {
-            per_sm = cached_per_sm[device];
-        } else {
-            for (const void *fn : {(const void *)admm_kernel<0, false>, (const void *)admm_kernel<0, true>, (const void *)admm_kernel<1, false>,
-                                   (const void *)admm_kernel<1, true>, (const void *)admm_kernel<2, false>, (const void *)admm_kernel<2, true>}) {
-                if ((rc = prep_kernel(fn, &tmp))) return rc;
-                per_sm = std::min(per_sm, tmp);
-            }
-            for (const void *fn : {(const void *)spmv_kernel<0, false>, (const void *)spmv_kernel<0, true>, (const void *)spmv_kernel<1, false>,
-                                   (const void *)spmv_kernel<1, true>, (const void *)spmv_kernel<2, false>, (const void *)spmv_kernel<2, true>})
-                if ((rc = prep_kernel(fn, &tmp))) return rc;
-            if (cacheable) cached_per_sm[device] = per_sm;
-        }
-    }
-    if (per_sm < 1) return fail(QPB200_ERR_CUDA, "persistent kernel does not fit on an SM");
-    {
-        const char *e = getenv("QPB200_CTAS_PER_SM");   // A/B experiments only
-        per_sm = std::min(per_sm, e ? std::max(1, atoi(e)) : kMinCtas);
-    }
-    const int grid_max = num_sms * per_sm;
-
-    lap("kernel_prep");
-    HostTiles TH, TA;
-    build_tiles(H, kTileNnz, TH);
-    build_tiles(A, kTileNnz, TA);
     int64_t want = std::max<int64_t>((int64_t)std::max(TH.tiles.size(), TA.tiles.size()),
                                      ((int64_t)std::max(n, m) + kThreads * 4 - 1) / (kThreads * 4));
     grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid_max, want));
@@ -246,8 +273,8 @@ int SparseSolver::init(int64_t n64, int64_t m64, const int64_t *Pp, const int64_
 
     lap("tiles");
     // ---- upload
-    if ((rc = upload_tiled(arena, H, TH, prob.H))) return rc;
-    if ((rc = upload_tiled(arena, A, TA, prob.A))) return rc;
+    if ((rc = upload_plan(arena, TH, prob.H, stream))) return rc;
+    if ((rc = upload_plan(arena, TA, prob.A, stream))) return rc;
     prob.n = n;
     prob.m = m;
     double *dq, *dl, *du, *ddP, *ddAA;
@@ -297,9 +324,6 @@ int SparseSolver::init(int64_t n64, int64_t m64, const int64_t *Pp, const int64_
     QPB_CUDA(arena.alloc(&prob.gs.partials[0], (size_t)grid_max * kMaxRed, true));
     QPB_CUDA(arena.alloc(&prob.gs.partials[1], (size_t)grid_max * kMaxRed, true));
     QPB_CUDA(arena.alloc(&scratch, std::max(nm, (size_t)2 * n) + 8, true));
-    QPB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    QPB_CUDA(cudaEventCreate(&ev0));
-    QPB_CUDA(cudaEventCreate(&ev1));
     QPB_CUDA(cudaDeviceSynchronize());
     lap("upload+alloc");
     setup_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
