@@ -86,6 +86,9 @@ typedef struct qpb200_settings {
                                        (SolveQuadraticProgram.jl:85-105) are evaluated on the
                                        UNSCALED residuals, x / z / y are returned unscaled.            */
 
+#define QPB200_RSV_DENSE_VARIANT 3  /* dense batch, m padded to 96: 0 = default, 1 = matrix-vector products out of
+                                       shared memory, 2 = A held in registers during the iterations (A/B runs)   */
+
 typedef struct qpb200_info {
     int32_t conv_flag;       /* QPB200_CONV_*                                                      */
     int32_t reserved;

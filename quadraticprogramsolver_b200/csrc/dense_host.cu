@@ -9,6 +9,9 @@
 
 namespace qpb {
 
+// default kernel for the mp = 96 shape: flipped by measurement (profiles/), both stay selectable
+constexpr bool kDenseRegADefault = true;   // 16 384 QPs: 68.6 -> 50.4 ms (profiles/r1d_dense_variant_ab.jsonl)
+
 struct DenseBatch {
     int64_t batch = 0;
     int n = 0, m = 0, mp = 0, device = -1, grid = 0;
@@ -19,6 +22,7 @@ struct DenseBatch {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double setup_ms = 0.0;
     size_t smem = 0;
+    bool reg_a = false;          // register-resident A variant (mp = 96)
     ~DenseBatch() {
         if (device >= 0) cudaSetDevice(device);
         if (ev0) cudaEventDestroy(ev0);
@@ -108,7 +112,15 @@ int qpb200_batch_create(qpb200_batch **out, int64_t batch, int64_t n, int64_t m,
     d.eps_abs = s.eps_abs; d.eps_rel = s.eps_rel; d.rho = s.rho; d.sigma = s.sigma; d.alpha = s.alpha;
     d.rho_factor = s.rho_factor; d.pcg_eps = 0; d.pcg_rel_eps = 0; d.adaptive_rho = s.adaptive_rho;
     B.smem = dense_smem_bytes(B.mp);
-    const void *kfn = B.mp == 96 ? (const void *)dense_batch_kernel<96> : (const void *)dense_batch_kernel<0>;
+    // reserved_i[QPB200_RSV_DENSE_VARIANT]: 0 = default, 1 = shared-memory products, 2 = register-resident A (mp = 96)
+    const int variant = s.reserved_i[QPB200_RSV_DENSE_VARIANT];
+    if (variant < 0 || variant > 2 || (variant == 2 && B.mp != 96)) {
+        delete h;
+        return fail(QPB200_ERR_ARG, "qpb200_batch_create: dense variant %d is not available for m = %lld", variant, (long long)m);
+    }
+    B.reg_a = B.mp == 96 && variant != 1 && kDenseRegADefault ? true : (variant == 2);
+    const void *kfn = B.mp == 96 ? (B.reg_a ? (const void *)dense_batch_kernel<96, true> : (const void *)dense_batch_kernel<96, false>)
+                                 : (const void *)dense_batch_kernel<0>;
     QPB_CUDA_H(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.smem));
     int per_sm = 0;
     QPB_CUDA_H(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kDThreads, B.smem));
@@ -137,7 +149,8 @@ int qpb200_batch_solve(qpb200_batch *h, double *X_inout, int32_t *flags, int64_t
     QPB_CUDA(cudaMemsetAsync(B.prm.factor_fail, 0, sizeof(int), B.stream));
     QPB_CUDA(cudaMemsetAsync(B.prm.queue, 0, 4 * sizeof(unsigned int), B.stream));
     QPB_CUDA(cudaEventRecord(B.ev0, B.stream));
-    if (B.mp == 96) dense_batch_kernel<96><<<B.grid, kDThreads, B.smem, B.stream>>>(B.prm);   // configs[2] shape: compile-time loops
+    if (B.mp == 96 && B.reg_a) dense_batch_kernel<96, true><<<B.grid, kDThreads, B.smem, B.stream>>>(B.prm);
+    else if (B.mp == 96) dense_batch_kernel<96, false><<<B.grid, kDThreads, B.smem, B.stream>>>(B.prm);   // configs[2] shape: compile-time loops
     else dense_batch_kernel<0><<<B.grid, kDThreads, B.smem, B.stream>>>(B.prm);
     QPB_CUDA(cudaGetLastError());
     QPB_CUDA(cudaEventRecord(B.ev1, B.stream));

@@ -58,6 +58,7 @@ struct DenseSmem {
     double *part;  // 128
     double *z, *y, *w, *l, *u;         // mp each
     double *red;   // 64
+    double *part4; // 4 x 64: per-warp partial sums of A'w (register-resident A variant)
 };
 
 __device__ __forceinline__ DenseSmem carve(unsigned char *raw, int mp) {
@@ -77,11 +78,12 @@ __device__ __forceinline__ DenseSmem carve(unsigned char *raw, int mp) {
     s.l = p; p += mp;
     s.u = p; p += mp;
     s.red = p; p += 64;
+    s.part4 = p; p += 4 * kDN;
     return s;
 }
 
 static size_t dense_smem_bytes(int mp) {
-    return sizeof(double) * ((size_t)(mp + 2) * kDN + kDN * kLd + 5 * kDN + 2 * kDN + 5 * (size_t)mp + 64);
+    return sizeof(double) * ((size_t)(mp + 2) * kDN + kDN * kLd + 5 * kDN + 2 * kDN + 5 * (size_t)mp + 64 + 4 * kDN);
 }
 
 // ---- K = P + sigma I + rho A'A (lower triangle) via DMMA ----------------------------------------
@@ -391,6 +393,104 @@ __device__ __forceinline__ double a_times_v_row(const double *As, int mp_rt, con
     return h == 0 ? r0 : r1;
 }
 
+// ---- register-resident A (compile-time shape mp = 96, the configs[2] shape) ---------------------------------
+// The two products with A dominate the shared-memory traffic of an iteration (2 x 48 KB of the 131 KB); here every
+// thread keeps a 6 x 8 block of A in registers for the whole solve: warp w owns rows [24 w, 24 w + 24), lane
+// 8 g + c owns rows 24 w + 6 g + (0..5) and columns 8 c + (0..7).  A x~ reduces across the 8 lanes of a row group
+// and A'w across the 4 row groups of a warp by butterfly reduce-scatters (13 FP64 shuffles per thread and
+// iteration), the 4 warps' partial sums of A'w meet in shared memory.  Fixed summation order => reproducible.
+struct RegA {
+    double a[6][8];
+};
+
+__device__ __forceinline__ void rega_load(RegA &R, const double *As) {
+    constexpr int lda = 96 + 2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 3, c = lane & 7;
+    const double *base = As + (24 * warp + 6 * g) + lda * (8 * c);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int r = 0; r < 6; r += 2) {
+            const double2 v = *reinterpret_cast<const double2 *>(base + r + lda * k);
+            R.a[r][k] = v.x;
+            R.a[r + 1][k] = v.y;
+        }
+}
+
+// part4[64 w + j] = sum over the rows of warp w of A[i, j] v_i
+__device__ __forceinline__ void rega_at_times_v(const RegA &R, const double *v, double *part4) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 3, c = lane & 7;
+    const double2 *v2 = reinterpret_cast<const double2 *>(v + 24 * warp + 6 * g);
+    double vr[6];
+#pragma unroll
+    for (int r = 0; r < 6; r += 2) {
+        const double2 t = v2[r >> 1];
+        vr[r] = t.x;
+        vr[r + 1] = t.y;
+    }
+    double cp[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        double acc = 0.0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) acc += R.a[r][k] * vr[r];
+        cp[k] = acc;
+    }
+    const bool hi2 = (g & 2) != 0, hi1 = (g & 1) != 0;
+    double v4[4], s2[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double send = hi2 ? cp[i] : cp[i + 4], keep = hi2 ? cp[i + 4] : cp[i];
+        v4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const double send = hi1 ? v4[i] : v4[i + 2], keep = hi1 ? v4[i + 2] : v4[i];
+        s2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    const int col = 8 * c + (hi2 ? 4 : 0) + (hi1 ? 2 : 0);
+    *reinterpret_cast<double2 *>(part4 + kDN * warp + col) = make_double2(s2[0], s2[1]);
+}
+
+// (A v)_row for row = 24 w + 6 g + c, valid on the lanes with c < 6
+__device__ __forceinline__ double rega_a_times_v(const RegA &R, const double *v, int &row, bool &valid) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 3, c = lane & 7;
+    const double2 *v2 = reinterpret_cast<const double2 *>(v + 8 * c);
+    double vc[8];
+#pragma unroll
+    for (int k = 0; k < 8; k += 2) {
+        const double2 t = v2[k >> 1];
+        vc[k] = t.x;
+        vc[k + 1] = t.y;
+    }
+    double rp[8];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc += R.a[r][k] * vc[k];
+        rp[r] = acc;
+    }
+    rp[6] = rp[7] = 0.0;
+    const bool b4 = (c & 4) != 0, b2 = (c & 2) != 0, b1 = (c & 1) != 0;
+    double v4[4], s2[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double send = b4 ? rp[i] : rp[i + 4], keep = b4 ? rp[i + 4] : rp[i];
+        v4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const double send = b2 ? v4[i] : v4[i + 2], keep = b2 ? v4[i + 2] : v4[i];
+        s2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    const double send = b1 ? s2[0] : s2[1], keep = b1 ? s2[1] : s2[0];
+    const double out = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+    row = 24 * warp + 6 * g + c;
+    valid = c < 6;
+    return out;
+}
+
 // block-wide max of NV values held per thread (NaN-propagating), broadcast to all threads
 template <int NV>
 __device__ __forceinline__ void block_max(double (&v)[NV], double *red) {
@@ -413,8 +513,11 @@ __device__ __forceinline__ void block_max(double (&v)[NV], double *red) {
     __syncthreads();
 }
 
-template <int MPC>
+// REGA (requires MPC == 96): A lives in registers during the iterations (see RegA above); the factorisation and
+// the convergence check keep using the shared-memory copy.
+template <int MPC, bool REGA = false>
 __global__ void __launch_bounds__(kDThreads) dense_batch_kernel(DenseBatchParams p) {
+    static_assert(!REGA || MPC == 96, "the register-resident variant is compiled for mp = 96 only");
     extern __shared__ __align__(16) unsigned char raw[];
     const DenseSmem sm = carve(raw, p.mp);
     const int n = p.n, m = p.m, mp = MPC ? MPC : p.mp, lda = mp + 2;
@@ -460,6 +563,7 @@ __global__ void __launch_bounds__(kDThreads) dense_batch_kernel(DenseBatchParams
         }
 
         double rho = p.s.rho, rho1 = 1.0 / rho, rhorho = rho;
+        RegA R;
         int conv_flag = 1;
         bool need_factor = true, fact_ok = true;
         long long ii = 0;
@@ -480,10 +584,18 @@ __global__ void __launch_bounds__(kDThreads) dense_batch_kernel(DenseBatchParams
                 trtri_lower(sm);
                 lauum_lower_and_mirror(sm);
                 need_factor = false;
+                if (REGA) rega_load(R, sm.As);   // (re)loaded here so that R is not live across the factorisation code
             }
             __syncthreads();
             // ---- rhs = sigma x - q + A' w,  w = rho z - y      (LinearSystemSolvers.jl:37-38 reduced)
-            {
+            if (REGA) {
+                rega_at_times_v(R, sm.w, sm.part4);
+                __syncthreads();
+                if (tid < kDN) {
+                    const double s = (sm.part4[tid] + sm.part4[kDN + tid]) + (sm.part4[2 * kDN + tid] + sm.part4[3 * kDN + tid]);
+                    sm.rhs[tid] = sigma * sm.x[tid] - sm.q[tid] + s;
+                }
+            } else {
                 const double s = at_times_v<MPC>(sm.As, mp, sm.w);
                 if (h == 0) sm.rhs[o] = sigma * sm.x[o] - sm.q[o] + s;
             }
@@ -504,8 +616,9 @@ __global__ void __launch_bounds__(kDThreads) dense_batch_kernel(DenseBatchParams
             // ---- z~ = A x~, then the z / y update (:59-61), one row per thread
             {
                 int row;
-                const double zt = a_times_v_row<MPC>(sm.As, mp, sm.xt, row);
-                if (row < m) {
+                bool valid = true;
+                const double zt = REGA ? rega_a_times_v(R, sm.xt, row, valid) : a_times_v_row<MPC>(sm.As, mp, sm.xt, row);
+                if (valid && row < m) {
                     const double z_old = sm.z[row], y_old = sm.y[row];
                     const double zr = alpha * zt + alpha1 * z_old;
                     const double z_new = clamp_julia(zr + rho1 * y_old, sm.l[row], sm.u[row]);   // :60

@@ -258,8 +258,11 @@ class QPB200Batch:
             raise ValueError("dimension mismatch in q, l or u")
         kw.setdefault("linSolver", "cholesky")
         unblocked = bool(kw.pop("unblockedCholesky", False))
+        # A/B switch of the n = 64, m <= 96 kernel: "smem" = products out of shared memory, "regs" = A in registers
+        variant = {"auto": 0, "smem": 1, "regs": 2}[kw.pop("denseVariant", "auto")]
         self.settings = make_settings(**kw)
         self.settings.reserved_i[0] = 1 if unblocked else 0
+        self.settings.reserved_i[3] = variant                # QPB200_RSV_DENSE_VARIANT
         self._h = C.c_void_p()
         _lib.check(lib.qpb200_batch_create(C.byref(self._h), self.batch, self.n, self.m, _pd(P), _pd(A_cm), _pd(q), _pd(l),
                                            _pd(u), C.byref(self.settings)))
