@@ -87,7 +87,8 @@ typedef struct qpb200_settings {
                                        UNSCALED residuals, x / z / y are returned unscaled.            */
 
 #define QPB200_RSV_DENSE_VARIANT 3  /* dense batch, m padded to 96: 0 = default, 1 = matrix-vector products out of
-                                       shared memory, 2 = A held in registers during the iterations (A/B runs)   */
+                                       shared memory, 2 = A held in registers during the iterations, 3 = A and
+                                       K^-1 in registers (A/B runs)                                               */
 
 typedef struct qpb200_info {
     int32_t conv_flag;       /* QPB200_CONV_*                                                      */

@@ -10,7 +10,7 @@
 namespace qpb {
 
 // default kernel for the mp = 96 shape: flipped by measurement (profiles/), both stay selectable
-constexpr bool kDenseRegADefault = true;   // 16 384 QPs: 68.6 -> 50.4 ms (profiles/r1d_dense_variant_ab.jsonl)
+constexpr int kDenseRegDefault = 2;   // A and K^-1 in registers; 16 384 QPs: 68.4 (smem) -> 50.5 (A) -> 48.1 ms (A, K^-1): profiles/r1d_dense_variant_ab2.jsonl
 
 struct DenseBatch {
     int64_t batch = 0;
@@ -22,7 +22,7 @@ struct DenseBatch {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double setup_ms = 0.0;
     size_t smem = 0;
-    bool reg_a = false;          // register-resident A variant (mp = 96)
+    int reg = 0;                 // mp = 96: 0 = products out of shared memory, 1 = A in registers, 2 = A and K^-1 in registers
     ~DenseBatch() {
         if (device >= 0) cudaSetDevice(device);
         if (ev0) cudaEventDestroy(ev0);
@@ -112,15 +112,16 @@ int qpb200_batch_create(qpb200_batch **out, int64_t batch, int64_t n, int64_t m,
     d.eps_abs = s.eps_abs; d.eps_rel = s.eps_rel; d.rho = s.rho; d.sigma = s.sigma; d.alpha = s.alpha;
     d.rho_factor = s.rho_factor; d.pcg_eps = 0; d.pcg_rel_eps = 0; d.adaptive_rho = s.adaptive_rho;
     B.smem = dense_smem_bytes(B.mp);
-    // reserved_i[QPB200_RSV_DENSE_VARIANT]: 0 = default, 1 = shared-memory products, 2 = register-resident A (mp = 96)
+    // reserved_i[QPB200_RSV_DENSE_VARIANT]: 0 = default, 1 = shared-memory products, 2 = A in registers, 3 = A and K^-1
     const int variant = s.reserved_i[QPB200_RSV_DENSE_VARIANT];
-    if (variant < 0 || variant > 2 || (variant == 2 && B.mp != 96)) {
+    if (variant < 0 || variant > 3 || (variant >= 2 && B.mp != 96)) {
         delete h;
         return fail(QPB200_ERR_ARG, "qpb200_batch_create: dense variant %d is not available for m = %lld", variant, (long long)m);
     }
-    B.reg_a = B.mp == 96 && variant != 1 && kDenseRegADefault ? true : (variant == 2);
-    const void *kfn = B.mp == 96 ? (B.reg_a ? (const void *)dense_batch_kernel<96, true> : (const void *)dense_batch_kernel<96, false>)
-                                 : (const void *)dense_batch_kernel<0>;
+    B.reg = B.mp != 96 ? 0 : (variant == 0 ? kDenseRegDefault : variant - 1);
+    const void *kfn = B.mp != 96 ? (const void *)dense_batch_kernel<0>
+                      : B.reg == 2 ? (const void *)dense_batch_kernel<96, 2>
+                      : B.reg == 1 ? (const void *)dense_batch_kernel<96, 1> : (const void *)dense_batch_kernel<96, 0>;
     QPB_CUDA_H(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.smem));
     int per_sm = 0;
     QPB_CUDA_H(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kDThreads, B.smem));
@@ -149,8 +150,9 @@ int qpb200_batch_solve(qpb200_batch *h, double *X_inout, int32_t *flags, int64_t
     QPB_CUDA(cudaMemsetAsync(B.prm.factor_fail, 0, sizeof(int), B.stream));
     QPB_CUDA(cudaMemsetAsync(B.prm.queue, 0, 4 * sizeof(unsigned int), B.stream));
     QPB_CUDA(cudaEventRecord(B.ev0, B.stream));
-    if (B.mp == 96 && B.reg_a) dense_batch_kernel<96, true><<<B.grid, kDThreads, B.smem, B.stream>>>(B.prm);
-    else if (B.mp == 96) dense_batch_kernel<96, false><<<B.grid, kDThreads, B.smem, B.stream>>>(B.prm);   // configs[2] shape: compile-time loops
+    if (B.mp == 96 && B.reg == 2) dense_batch_kernel<96, 2><<<B.grid, kDThreads, B.smem, B.stream>>>(B.prm);
+    else if (B.mp == 96 && B.reg == 1) dense_batch_kernel<96, 1><<<B.grid, kDThreads, B.smem, B.stream>>>(B.prm);
+    else if (B.mp == 96) dense_batch_kernel<96, 0><<<B.grid, kDThreads, B.smem, B.stream>>>(B.prm);   // configs[2] shape: compile-time loops
     else dense_batch_kernel<0><<<B.grid, kDThreads, B.smem, B.stream>>>(B.prm);
     QPB_CUDA(cudaGetLastError());
     QPB_CUDA(cudaEventRecord(B.ev1, B.stream));

@@ -491,6 +491,59 @@ __device__ __forceinline__ double rega_a_times_v(const RegA &R, const double *v,
     return out;
 }
 
+// K^-1 in registers as well: warp w owns rows [16 w, 16 w + 16), lane 8 g + c owns rows 16 w + 4 g + (0..3) and
+// columns 8 c + (0..7); the row sums reduce across the 8 lanes of a row group (4 FP64 shuffles per thread).
+struct RegK {
+    double k[4][8];
+};
+
+__device__ __forceinline__ void regk_load(RegK &K, const double *Kf) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 3, c = lane & 7;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const double2 *row = reinterpret_cast<const double2 *>(Kf + pidx(16 * warp + 4 * g + r, 8 * c));
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const double2 v = row[e];
+            K.k[r][2 * e] = v.x;
+            K.k[r][2 * e + 1] = v.y;
+        }
+    }
+}
+
+// (K^-1 v)_row for row = 16 w + 4 g + (c >> 1); both lanes of a pair (c, c ^ 1) return it
+__device__ __forceinline__ double regk_times_v(const RegK &K, const double *v, int &row) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 3, c = lane & 7;
+    const double2 *v2 = reinterpret_cast<const double2 *>(v + 8 * c);
+    double vc[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const double2 t = v2[e];
+        vc[2 * e] = t.x;
+        vc[2 * e + 1] = t.y;
+    }
+    double rp[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc += K.k[r][j] * vc[j];
+        rp[r] = acc;
+    }
+    const bool b4 = (c & 4) != 0, b2 = (c & 2) != 0;
+    double s2[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const double send = b4 ? rp[i] : rp[i + 2], keep = b4 ? rp[i + 2] : rp[i];
+        s2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    const double send = b2 ? s2[0] : s2[1], keep = b2 ? s2[1] : s2[0];
+    double out = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    out += __shfl_xor_sync(0xffffffffu, out, 1);
+    row = 16 * warp + 4 * g + (b4 ? 2 : 0) + (b2 ? 1 : 0);
+    return out;
+}
+
 // block-wide max of NV values held per thread (NaN-propagating), broadcast to all threads
 template <int NV>
 __device__ __forceinline__ void block_max(double (&v)[NV], double *red) {
@@ -515,9 +568,11 @@ __device__ __forceinline__ void block_max(double (&v)[NV], double *red) {
 
 // REGA (requires MPC == 96): A lives in registers during the iterations (see RegA above); the factorisation and
 // the convergence check keep using the shared-memory copy.
-template <int MPC, bool REGA = false>
+template <int MPC, int REG = 0>
 __global__ void __launch_bounds__(kDThreads) dense_batch_kernel(DenseBatchParams p) {
-    static_assert(!REGA || MPC == 96, "the register-resident variant is compiled for mp = 96 only");
+    static_assert(REG == 0 || MPC == 96, "the register-resident variants are compiled for mp = 96 only");
+    constexpr bool REGA = REG >= 1;   // A in registers
+    constexpr bool REGK = REG >= 2;   // ... and K^-1 too
     extern __shared__ __align__(16) unsigned char raw[];
     const DenseSmem sm = carve(raw, p.mp);
     const int n = p.n, m = p.m, mp = MPC ? MPC : p.mp, lda = mp + 2;
@@ -564,6 +619,7 @@ __global__ void __launch_bounds__(kDThreads) dense_batch_kernel(DenseBatchParams
 
         double rho = p.s.rho, rho1 = 1.0 / rho, rhorho = rho;
         RegA R;
+        RegK RK;
         int conv_flag = 1;
         bool need_factor = true, fact_ok = true;
         long long ii = 0;
@@ -585,6 +641,10 @@ __global__ void __launch_bounds__(kDThreads) dense_batch_kernel(DenseBatchParams
                 lauum_lower_and_mirror(sm);
                 need_factor = false;
                 if (REGA) rega_load(R, sm.As);   // (re)loaded here so that R is not live across the factorisation code
+                if (REGK) {
+                    __syncthreads();
+                    regk_load(RK, sm.Lp);
+                }
             }
             __syncthreads();
             // ---- rhs = sigma x - q + A' w,  w = rho z - y      (LinearSystemSolvers.jl:37-38 reduced)
@@ -602,7 +662,17 @@ __global__ void __launch_bounds__(kDThreads) dense_batch_kernel(DenseBatchParams
             __syncthreads();
             // ---- x~ = K^-1 rhs, then the x relaxation (:57)
             double dx = 0.0, dz = 0.0;
-            {
+            if (REGK) {
+                int row;
+                const double s = regk_times_v(RK, sm.rhs, row);
+                if ((tid & 1) == 0) {
+                    sm.xt[row] = s;
+                    const double x_old = sm.x[row];
+                    const double x_new = alpha * s + alpha1 * x_old;
+                    sm.x[row] = x_new;
+                    dx = fabs(x_new - x_old);
+                }
+            } else {
                 const double s = kinv_times_v(sm.Lp, sm.rhs);
                 if (h == 0) {
                     sm.xt[o] = s;

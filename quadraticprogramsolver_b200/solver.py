@@ -259,7 +259,7 @@ class QPB200Batch:
         kw.setdefault("linSolver", "cholesky")
         unblocked = bool(kw.pop("unblockedCholesky", False))
         # A/B switch of the n = 64, m <= 96 kernel: "smem" = products out of shared memory, "regs" = A in registers
-        variant = {"auto": 0, "smem": 1, "regs": 2}[kw.pop("denseVariant", "auto")]
+        variant = {"auto": 0, "smem": 1, "regs": 2, "regs_ak": 3}[kw.pop("denseVariant", "auto")]
         self.settings = make_settings(**kw)
         self.settings.reserved_i[0] = 1 if unblocked else 0
         self.settings.reserved_i[3] = variant                # QPB200_RSV_DENSE_VARIANT

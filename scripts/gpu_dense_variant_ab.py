@@ -1,4 +1,4 @@
-"""Dense batch kernel A/B (configs[2] shape n = 64, m = 96): shared-memory products vs A held in registers.
+"""Dense batch kernel A/B (configs[2] shape n = 64, m = 96): shared-memory products vs A (and K^-1) held in registers.
 usage: python scripts/gpu_dense_variant_ab.py [batch]"""
 import json
 import os
@@ -13,7 +13,7 @@ from quadraticprogramsolver_b200.problems import config_cfg3_batch        # noqa
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 P, q, A, l, u = config_cfg3_batch(batch, 64, 96, seed=1234)
 ref = None
-for variant in ("smem", "regs", "smem", "regs"):
+for variant in ("smem", "regs", "regs_ak", "smem", "regs", "regs_ak"):
     with S.QPB200Batch(P, q, A, l, u, denseVariant=variant) as b:
         X, flags, iters = b.solve()
         info = b.info

@@ -39,21 +39,22 @@ def test_cfg3_shape_matches_oracle(lib, kw, unblocked):
     assert info["iterations"] == int(iters.sum())
 
 
+@pytest.mark.parametrize("variant", ["regs", "regs_ak"])
 @pytest.mark.parametrize("n,m", [(64, 96), (64, 93), (40, 96), (17, 94)])
 @pytest.mark.parametrize("kw", [dict(), dict(rho=0.1, adptRho=True, epsAbs=1e-7, epsRel=1e-7, numIterations=50000)],
                          ids=["defaults", "runtests_adaptive_rho"])
-def test_register_resident_variant_matches_oracle_and_smem_variant(lib, n, m, kw):
-    """The kernel variant that keeps A in registers during the iterations (shapes padded to 64 x 96): same flags and
-    iteration counts as the oracle and as the shared-memory variant, x to 1e-6 / 1e-9."""
+def test_register_resident_variant_matches_oracle_and_smem_variant(lib, n, m, kw, variant):
+    """The kernel variants that keep A (and K^-1) in registers during the iterations (shapes padded to 64 x 96): same
+    flags and iteration counts as the oracle and as the shared-memory variant, x to 1e-6 / 1e-8."""
     P, q, A, l, u = config_cfg3_batch(160, n, m, seed=77)
     X0 = np.random.default_rng(3).standard_normal((160, n))
-    Xa, fa, ia, _ = _S().SolveQuadraticProgramBatch(P, q, A, l, u, X0=X0, denseVariant="regs", **kw)
+    Xa, fa, ia, _ = _S().SolveQuadraticProgramBatch(P, q, A, l, u, X0=X0, denseVariant=variant, **kw)
     Xb, fb, ib, _ = _S().SolveQuadraticProgramBatch(P, q, A, l, u, X0=X0, denseVariant="smem", **kw)
     Xr, fr, ir, _, rc = c_oracle.solve_dense_batch(P, q, A, l, u, x0=X0, **kw)
     assert rc == 0
     _check(Xa, fa, ia, Xr, fr, ir)
     _check(Xa, fa, ia, Xb, fb, ib, tol=1e-8)
-    Xc, fc, ic, _ = _S().SolveQuadraticProgramBatch(P, q, A, l, u, X0=X0, denseVariant="regs", **kw)
+    Xc, fc, ic, _ = _S().SolveQuadraticProgramBatch(P, q, A, l, u, X0=X0, denseVariant=variant, **kw)
     assert np.array_equal(Xa, Xc) and np.array_equal(ia, ic)          # bitwise reproducible
 
 
