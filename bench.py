@@ -409,7 +409,7 @@ def run_cfg3(args):
                 "roofline": {"bound": "fp64_fma", "achieved": flops / (tot[0] * 1e-3) / 1e12 / world, "peak": 40.0, "unit": "TFLOP/s",
                              "frac": flops / (tot[0] * 1e-3) / 1e12 / world / 40.0, "traffic": None,
                              "peak_source": "nominal B200 FP64 (no measured FP64 peak in MEASURED_PEAKS.json)",
-                             "kernel": "dense_batch_kernel (per-iteration GEMVs out of shared memory; DMMA only in the factorisation)"},
+                             "kernel": "dense_batch_kernel<96,2> (A and K^-1 register-resident during the iterations, shuffle reduce-scatters; DMMA only in the factorisation)"},
                 "admm_iters_per_s": tot[2] / (tot[0] * 1e-3)}
         if world == 1 and not args.no_cpu:
             from oracle import c_oracle

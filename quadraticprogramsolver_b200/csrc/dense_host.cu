@@ -61,10 +61,9 @@ int qpb200_batch_create(qpb200_batch **out, int64_t batch, int64_t n, int64_t m,
         return fail(QPB200_ERR_ARG, "qpb200_batch_create: the dense batch path implements lin_solver = QPB200_LINSOLVE_CHOLESKY only");
     if (s.reserved_i[QPB200_RSV_SCALING_ITERS] != 0)
         return fail(QPB200_ERR_ARG, "qpb200_batch_create: equilibration is implemented for the sparse single-GPU path only");
-    // value checks on a strided sample would miss entries: scan everything (memory-bound, ~GB/s)
+    // value checks on a strided sample would miss entries: everything is scanned -- P and A (GBs) in the same pass
+    // that stages them for the upload (staged_upload below), the small vectors here
     const size_t nP = (size_t)batch * n * n, nA = (size_t)batch * m * n;
-    if (!all_finite(P, nP)) return fail(QPB200_ERR_NONFINITE, "P has a non-finite entry");
-    if (!all_finite(A, nA)) return fail(QPB200_ERR_NONFINITE, "A has a non-finite entry");
     if (!all_finite(q, (size_t)batch * n)) return fail(QPB200_ERR_NONFINITE, "q has a non-finite entry");
     for (size_t i = 0; i < (size_t)batch * m; ++i)
         if (std::isnan(l[i]) || std::isnan(u[i]) || l[i] > u[i]) return fail(QPB200_ERR_NONFINITE, "bounds: need l <= u, not NaN (entry %zu)", i);
@@ -99,8 +98,14 @@ int qpb200_batch_create(qpb200_batch **out, int64_t batch, int64_t n, int64_t m,
     QPB_CUDA_H(cudaStreamCreateWithFlags(&B.stream, cudaStreamNonBlocking));
     QPB_CUDA_H(cudaEventCreate(&B.ev0));
     QPB_CUDA_H(cudaEventCreate(&B.ev1));
-    QPB_CUDA_H(cudaMemcpyAsync(dP, P, nP * sizeof(double), cudaMemcpyHostToDevice, B.stream));
-    QPB_CUDA_H(cudaMemcpyAsync(dA, A, nA * sizeof(double), cudaMemcpyHostToDevice, B.stream));
+    bool finiteP = true, finiteA = true;
+    QPB_CUDA_H(staged_upload(dP, P, nP, B.stream, &finiteP));
+    QPB_CUDA_H(staged_upload(dA, A, nA, B.stream, &finiteA));
+    if (!finiteP || !finiteA) {
+        cudaStreamSynchronize(B.stream);
+        delete h;
+        return fail(QPB200_ERR_NONFINITE, "%s has a non-finite entry", finiteP ? "A" : "P");
+    }
     QPB_CUDA_H(cudaMemcpyAsync(dq, q, (size_t)batch * n * sizeof(double), cudaMemcpyHostToDevice, B.stream));
     QPB_CUDA_H(cudaMemcpyAsync(dl, l, (size_t)batch * m * sizeof(double), cudaMemcpyHostToDevice, B.stream));
     QPB_CUDA_H(cudaMemcpyAsync(du, u, (size_t)batch * m * sizeof(double), cudaMemcpyHostToDevice, B.stream));

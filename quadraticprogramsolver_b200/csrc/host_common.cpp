@@ -334,6 +334,81 @@ bool all_finite(const double *v, size_t count) {
     return bad == 0;
 }
 
+// ---- staged uploads ---------------------------------------------------------------------------------
+namespace {
+struct StagingRing {
+    static constexpr int kSlots = 4;
+    static constexpr size_t kChunk = (size_t)64 << 20;   // bytes per slot
+    std::mutex mu;                                         // one upload at a time per device
+    double *slot[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t done[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+    bool ok = false, tried = false;
+    bool init() {
+        if (tried) return ok;
+        tried = true;
+        for (int i = 0; i < kSlots; ++i) {
+            if (cudaHostAlloc((void **)&slot[i], kChunk, cudaHostAllocPortable) != cudaSuccess ||
+                cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) != cudaSuccess) {
+                cudaGetLastError();
+                return ok = false;
+            }
+        }
+        return ok = true;
+    }
+};
+// events belong to a device: one ring per device ordinal (a process normally drives one GPU)
+StagingRing &staging_ring(int dev) { static StagingRing r[16]; return r[dev & 15]; }
+}  // namespace
+
+cudaError_t staged_upload(void *dst_dev, const double *src_host, size_t count, cudaStream_t st, bool *finite_out) {
+    if (finite_out) *finite_out = true;
+    const size_t bytes = count * sizeof(double);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    StagingRing &ring = staging_ring(dev);
+    std::unique_lock<std::mutex> lock(ring.mu);
+    if (bytes < 2 * StagingRing::kChunk || !ring.init()) {          // small array or no page-locked memory: plain copy
+        lock.unlock();
+        if (finite_out) *finite_out = all_finite(src_host, count);
+        return cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, st);
+    }
+    const size_t per = StagingRing::kChunk / sizeof(double);
+    std::atomic<int> bad(0);
+    size_t off = 0;
+    for (int i = 0; off < count; ++i, off += per) {
+        const int sl = i % StagingRing::kSlots;
+        const size_t cnt = std::min(per, count - off);
+        if (i >= StagingRing::kSlots) {                             // the slot's previous chunk must have left
+            cudaError_t e = cudaEventSynchronize(ring.done[sl]);
+            if (e != cudaSuccess) return e;
+        }
+        double *dst = ring.slot[sl];
+        const double *src = src_host + off;
+        parallel_chunks((int64_t)cnt, [&](int, int64_t b, int64_t e) {
+            std::memcpy(dst + b, src + b, (size_t)(e - b) * sizeof(double));
+            if (finite_out) {
+                double acc[4] = {0, 0, 0, 0};
+                int64_t k = b;
+                for (; k + 4 <= e; k += 4)
+                    for (int j = 0; j < 4; ++j) acc[j] += dst[k + j] * 0.0;
+                for (; k < e; ++k) acc[0] += dst[k] * 0.0;
+                if ((acc[0] + acc[1]) + (acc[2] + acc[3]) != 0.0) bad = 1;
+            }
+        }, 1 << 16);
+        cudaError_t e = cudaMemcpyAsync(static_cast<double *>(dst_dev) + off, dst, cnt * sizeof(double), cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) return e;
+        e = cudaEventRecord(ring.done[sl], st);
+        if (e != cudaSuccess) return e;
+    }
+    // the ring is shared: leave it drained so that the next upload (possibly on another stream) starts clean
+    for (int sl = 0; sl < StagingRing::kSlots; ++sl) {
+        cudaError_t e = cudaEventSynchronize(ring.done[sl]);
+        if (e != cudaSuccess) return e;
+    }
+    if (finite_out) *finite_out = bad == 0;
+    return cudaSuccess;
+}
+
 // ---- block caches -----------------------------------------------------------------------------------
 namespace {
 struct BlockCache {
