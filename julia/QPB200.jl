@@ -93,14 +93,16 @@ end
 Same positional arguments, keyword names, defaults and return value as the reference method
 (SolveQuadraticProgram.jl:14-17); `vX` is the start point and is overwritten with the solution.
 New keywords: `ϵPcg`, `numItrPcg` (the plugin kwargs of LinearSystemSolvers.jl:125, which the reference
-driver never forwards), `precond ∈ (:jacobi, :none)`, `device`, `numItrScaling` (Ruiz equilibration, default off).
+driver never forwards), `precond ∈ (:jacobi, :none)`, `device`, `numItrScaling` (Ruiz equilibration, default off),
+`rhoScale` (per-constraint step size ρᵢ = ρ·rhoScale[i], default `nothing` = the scalar ρ; `EqualityRhoScale(vL, vU)`
+builds OSQP's choice).
 """
 function SolveQuadraticProgram!(vX::Vector{Float64}, mP::SparseMatrixCSC{Float64, Int64}, vQ::Vector{Float64},
         mA::SparseMatrixCSC{Float64, Int64}, vL::Vector{Float64}, vU::Vector{Float64}, ::B200InitT, ::B200SolT;
         numIterations = 5000, ϵAbs = 1e-6, ϵRel = 1e-6, ρ = 1, σ = 1e-6, α = 1.6, δ = 1e-6, adptΡ::Bool = false,
         fctrΡ = 5, numItrConv = 25, numItrPolish = 10, ϵMinres = 1e-6, numItrMinres = 500,
         ϵPcg = 1e-6, numItrPcg = 1000, precond::Symbol = :jacobi, device::Integer = -1, numItrScaling::Integer = 0,
-        info::Union{Info, Nothing} = nothing)
+        rhoScale::Union{Vector{Float64}, Nothing} = nothing, info::Union{Info, Nothing} = nothing)
 
     numElements, numConstraints = length(vX), size(mA, 1);
     (size(mP) == (numElements, numElements) && size(mA, 2) == numElements && length(vQ) == numElements &&
@@ -126,6 +128,10 @@ function SolveQuadraticProgram!(vX::Vector{Float64}, mP::SparseMatrixCSC{Float64
     end
     sInfo = info === nothing ? Info() : info;
     try
+        if rhoScale !== nothing
+            length(rhoScale) == numConstraints || throw(DimensionMismatch("rhoScale"));
+            check(ccall((:qpb200_set_rho_scale, libqpb200), Cint, (Ptr{Cvoid}, Ptr{Float64}), hRef[], rhoScale));
+        end
         check(ccall((:qpb200_solve, libqpb200), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Info}),
             hRef[], vX, C_NULL, C_NULL, sInfo));
     finally
@@ -133,6 +139,13 @@ function SolveQuadraticProgram!(vX::Vector{Float64}, mP::SparseMatrixCSC{Float64
     end
     return ConvergenceFlag(sInfo.conv_flag);
 end
+
+"""
+    EqualityRhoScale(vL, vU, factor = 1e3)
+
+OSQP's rho vector as a scale on the scalar ρ: `factor` on the equality rows (`l == u`), 1 elsewhere.
+"""
+EqualityRhoScale(vL, vU, factor = 1e3) = [l == u ? Float64(factor) : 1.0 for (l, u) in zip(vL, vU)];
 
 """
     SolveQuadraticProgram(P, q, A, l, u; kw...) -> (x, convFlag, info)
