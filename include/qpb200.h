@@ -149,6 +149,9 @@ int qpb200_batch_create(qpb200_batch **out, int64_t batch, int64_t n, int64_t m,
                         const double *P, const double *A, const double *q, const double *l, const double *u,
                         const qpb200_settings *settings);
 int qpb200_batch_solve(qpb200_batch *h, double *X_inout, int32_t *flags, int64_t *iters, qpb200_info *info);
+/* MPC-style re-solve: new q[batch*n], l, u[batch*m] (any may be NULL) for the matrices already on the device;
+ * the next qpb200_batch_solve uploads nothing but the start points.                                            */
+int qpb200_batch_update_vectors(qpb200_batch *h, const double *q, const double *l, const double *u);
 void qpb200_batch_destroy(qpb200_batch *h);
 
 /* ---- one large sparse QP row-partitioned over several GPUs, one rank (process or thread) per GPU.

@@ -53,7 +53,7 @@ EXPORTS = [
     "qpb200_create", "qpb200_solve", "qpb200_update_vectors", "qpb200_update_settings", "qpb200_set_rho_scale",
     "qpb200_destroy",
     "qpb200_apply", "qpb200_time_apply", "qpb200_apply_bytes",
-    "qpb200_batch_create", "qpb200_batch_solve", "qpb200_batch_destroy",
+    "qpb200_batch_create", "qpb200_batch_solve", "qpb200_batch_update_vectors", "qpb200_batch_destroy",
     "qpb200_dist_unique_id", "qpb200_dist_create", "qpb200_dist_solve",
     "qpb200_debug_tile_plan", "qpb200_debug_tile_nnz", "qpb200_debug_equilibrate", "qpb200_debug_assemble_h",
 ]
@@ -91,6 +91,7 @@ def load():
     lib.qpb200_batch_create.argtypes = [C.POINTER(pv), C.c_int64, C.c_int64, C.c_int64, pd, pd, pd, pd, pd,
                                         C.POINTER(Settings)]
     lib.qpb200_batch_solve.argtypes = [pv, pd, C.POINTER(C.c_int32), p64, C.POINTER(Info)]
+    lib.qpb200_batch_update_vectors.argtypes = [pv, pd, pd, pd]
     lib.qpb200_batch_destroy.argtypes = [pv]
     lib.qpb200_batch_destroy.restype = None
     lib.qpb200_dist_unique_id.argtypes = [pv]

@@ -187,6 +187,28 @@ int qpb200_batch_solve(qpb200_batch *h, double *X_inout, int32_t *flags, int64_t
     return QPB200_OK;
 }
 
+int qpb200_batch_update_vectors(qpb200_batch *h, const double *q, const double *l, const double *u) {
+    if (!h) return fail(QPB200_ERR_ARG, "qpb200_batch_update_vectors: handle is NULL");
+    DenseBatch &B = h->b;
+    QPB_CUDA(cudaSetDevice(B.device));
+    const size_t nq = (size_t)B.batch * B.n, nc = (size_t)B.batch * B.m;
+    if (q && !all_finite(q, nq)) return fail(QPB200_ERR_NONFINITE, "q has a non-finite entry");
+    for (int which = 0; which < 2; ++which) {
+        const double *b = which ? u : l;
+        if (!b) continue;
+        for (size_t i = 0; i < nc; ++i)
+            if (std::isnan(b[i])) return fail(QPB200_ERR_NONFINITE, "bound %zu is NaN", i);
+    }
+    if (l && u)
+        for (size_t i = 0; i < nc; ++i)
+            if (l[i] > u[i]) return fail(QPB200_ERR_NONFINITE, "bounds: need l <= u (entry %zu)", i);
+    if (q) QPB_CUDA(cudaMemcpyAsync(const_cast<double *>(B.prm.q), q, nq * sizeof(double), cudaMemcpyHostToDevice, B.stream));
+    if (l) QPB_CUDA(cudaMemcpyAsync(const_cast<double *>(B.prm.l), l, nc * sizeof(double), cudaMemcpyHostToDevice, B.stream));
+    if (u) QPB_CUDA(cudaMemcpyAsync(const_cast<double *>(B.prm.u), u, nc * sizeof(double), cudaMemcpyHostToDevice, B.stream));
+    QPB_CUDA(cudaStreamSynchronize(B.stream));       // the host arrays are borrowed for the duration of the call only
+    return QPB200_OK;
+}
+
 void qpb200_batch_destroy(qpb200_batch *h) { delete h; }
 
 }  // extern "C"

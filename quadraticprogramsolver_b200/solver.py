@@ -282,6 +282,19 @@ class QPB200Batch:
         self.info = info.as_dict()
         return X, flags, iters
 
+    def update_vectors(self, q=None, l=None, u=None):
+        """New q [batch, n] / l, u [batch, m] for the matrices already on the device (MPC-style re-solve)."""
+        arr = []
+        for v, shape in ((q, (self.batch, self.n)), (l, (self.batch, self.m)), (u, (self.batch, self.m))):
+            if v is None:
+                arr.append(None)
+                continue
+            v = np.ascontiguousarray(v, dtype=np.float64)
+            if v.shape != shape:
+                raise ValueError(f"expected shape {shape}, got {v.shape}")
+            arr.append(v)
+        _lib.check(_lib.load().qpb200_batch_update_vectors(self._h, *[None if a is None else _pd(a) for a in arr]))
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
             _lib.load().qpb200_batch_destroy(self._h)

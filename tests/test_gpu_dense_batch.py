@@ -113,3 +113,25 @@ def test_batch_argument_validation(lib):
     assert e.value.code == _lib.ERR_NONFINITE
     with pytest.raises(ValueError):
         _S().QPB200Batch(P, q[:, :-1], A, l, u)
+
+
+def test_batch_update_vectors_resolves_without_reupload(lib):
+    """MPC-style: same P, A on the device, new q / l / u per solve -- equals a fresh handle bit for bit."""
+    from quadraticprogramsolver_b200 import _lib
+    S = _S()
+    P, q, A, l, u = config_cfg3_batch(64, 64, 96, seed=4)
+    rng = np.random.default_rng(1)
+    q2 = q + 0.1 * rng.standard_normal(q.shape)
+    l2, u2 = l - 0.05, u + 0.05
+    with S.QPB200Batch(P, q, A, l, u) as b:
+        b.solve()
+        b.update_vectors(q2, l2, u2)
+        X1, f1, i1 = b.solve()
+        with pytest.raises(_lib.QPB200Error):
+            b.update_vectors(l=u2 + 1.0, u=u2)           # l > u
+        b.update_vectors(q=q)                             # only q back: bounds stay
+        X3, f3, i3 = b.solve()
+    X2, f2, i2, _ = S.SolveQuadraticProgramBatch(P, q2, A, l2, u2)
+    assert np.array_equal(X1, X2) and np.array_equal(f1, f2) and np.array_equal(i1, i2)
+    X4, f4, i4, _ = S.SolveQuadraticProgramBatch(P, q, A, l2, u2)
+    assert np.array_equal(X3, X4) and np.array_equal(i3, i4)
