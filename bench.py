@@ -23,6 +23,8 @@ pass of the hot path over that QP: ADMM iterations 1..ITERS of SolveQuadraticPro
 from __future__ import annotations
 
 import argparse
+import contextlib
+import io
 import json
 import os
 import statistics
@@ -438,13 +440,29 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
-    if args.workload == "cfg3":
-        run_cfg3(args)
-        return
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_b200(args)
+    # The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints "NCCL version ..." from
+    # C when NCCL_DEBUG is set on the box), so file descriptor 1 points at stderr while the benchmark runs and the
+    # JSON line goes to the real stdout at the end.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    buf = io.StringIO()
+    try:
+        with contextlib.redirect_stdout(buf):
+            if args.workload == "cfg3":
+                run_cfg3(args)
+            elif args.impl == "reference":
+                run_reference(args)
+            else:
+                run_b200(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+        out = buf.getvalue()
+        if out:
+            sys.stdout.write(out)
+            sys.stdout.flush()
 
 
 if __name__ == "__main__":
