@@ -443,10 +443,17 @@ void *take(BlockCache &c, size_t bytes, size_t *cap) {
     c.blocks.erase(c.blocks.begin() + (long)bi);
     return p;
 }
-bool give(BlockCache &c, void *p, size_t cap, size_t min_block) {
+size_t pinned_cache_limit() {          // page-locked memory is a scarcer resource: its own, smaller bound
+    static size_t lim = [] {
+        const char *e = getenv("QPB200_PINNED_CACHE_MB");
+        return (size_t)(e ? atoll(e) : 1536) << 20;
+    }();
+    return std::min(lim, cache_limit());
+}
+bool give(BlockCache &c, void *p, size_t cap, size_t min_block, size_t limit = (size_t)-1) {
     if (cap < min_block) return false;
     std::lock_guard<std::mutex> g(c.mu);
-    if (c.total + cap > cache_limit()) return false;
+    if (c.total + cap > std::min(limit, cache_limit())) return false;
     c.blocks.push_back({p, cap});
     c.total += cap;
     return true;
@@ -542,7 +549,7 @@ void cached_pinned_free(void *p, size_t capacity, bool pinned) {
         cached_host_free(p, capacity);
         return;
     }
-    if (give(pinned_cache(), p, capacity, kCacheMinBlock)) return;
+    if (give(pinned_cache(), p, capacity, kCacheMinBlock, pinned_cache_limit())) return;
     cudaFreeHost(p);
 }
 

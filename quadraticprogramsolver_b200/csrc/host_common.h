@@ -39,7 +39,8 @@ void *cached_host_alloc(size_t bytes, size_t *capacity);
 void cached_host_free(void *p, size_t capacity);
 // Page-locked flavour for the arrays that are uploaded (H2D from pinned memory runs at PCIe speed and can overlap the
 // host conversion; pageable copies measured 11 GB/s).  *pinned tells the caller what it got: when cudaHostAlloc
-// fails (or no device is present) the block is plain malloc memory.
+// fails (or no device is present) the block is plain malloc memory.  At most QPB200_PINNED_CACHE_MB (default 1536)
+// of page-locked blocks are kept between handles.
 void *cached_pinned_alloc(size_t bytes, size_t *capacity, bool *pinned);
 void cached_pinned_free(void *p, size_t capacity, bool pinned);
 
