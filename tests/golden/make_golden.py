@@ -29,12 +29,29 @@ CASES = [
     ("lasso_n10_default_J", ProblemClass.lassoOptimization, 10, 0, 1234, "J", dict(epsPcg=1e-10)),
     ("svm_n10_default_J", ProblemClass.supportVectorMachine, 10, 0, 1234, "J", dict(epsPcg=1e-10)),
     ("isotonic_n100_default_J", ProblemClass.isotonicRegression, 100, 0, 1234, "J", dict(epsPcg=1e-10)),
+    # SURVEY 8(f) row 1 (not in the reference): Ruiz equilibration, per-constraint rho (1e3 on the equality rows)
+    ("randomqp_n100_scaled_J", ProblemClass.randomQp, 100, 0, 1236, "J",
+     dict(numIterations=3000, rho=0.1, adptRho=True, epsPcg=1e-11, numItrScaling=10)),
+    ("eq_n100_rhoeq_J", ProblemClass.equalityConstrainedQp, 100, 50, 3, "J",
+     dict(numIterations=3000, rho=0.1, epsPcg=1e-10, rhoEqScale=1e3)),
 ]
 
+
+def oracle_kwargs(kw, l, u):
+    """Fixture kwargs -> qp_oracle.solve kwargs (``rhoEqScale`` is the mirrors' shorthand for a ``rhoScale`` vector)."""
+    kw = dict(kw)
+    if "rhoEqScale" in kw:
+        kw["rhoScale"] = np.where(np.asarray(l) == np.asarray(u), float(kw.pop("rhoEqScale")), 1.0)
+    return kw
+
+
 if __name__ == "__main__":
+    only = set(sys.argv[1:])                     # optional: names of the fixtures to (re)generate
     for name, pc, n, m, seed, mode, kw in CASES:
+        if only and name not in only:
+            continue
         P, q, A, l, u = GenerateRandomQP(pc, n, numConstraints=m, seed=seed)
-        x, flag, info = qp_oracle.solve(P, q, A, l, u, mode=mode, **kw)
+        x, flag, info = qp_oracle.solve(P, q, A, l, u, mode=mode, **oracle_kwargs(kw, l, u))
         out = dict(P_data=P.data, P_indices=P.indices, P_indptr=P.indptr, P_shape=np.array(P.shape),
                    A_data=A.data, A_indices=A.indices, A_indptr=A.indptr, A_shape=np.array(A.shape),
                    q=q, l=l, u=u, x=x, z=info["z"], y=info["y"], flag=int(flag), iterations=info["iterations"],

@@ -114,6 +114,8 @@ def test_golden_fixtures_reproduce(path):
     P = sp.csc_matrix((g["P_data"], g["P_indices"], g["P_indptr"]), shape=tuple(g["P_shape"]))
     A = sp.csc_matrix((g["A_data"], g["A_indices"], g["A_indptr"]), shape=tuple(g["A_shape"]))
     kw = {k[3:]: g[k].item() for k in g.files if k.startswith("kw_")}
+    if "rhoEqScale" in kw:                       # the mirrors' shorthand for a rhoScale vector
+        kw["rhoScale"] = np.where(g["l"] == g["u"], float(kw.pop("rhoEqScale")), 1.0)
     mode = str(g["mode"])
     x, flag, info = qp_oracle.solve(P, g["q"], A, g["l"], g["u"], mode=mode, **kw)
     assert int(flag) == int(g["flag"])
