@@ -271,3 +271,23 @@ def test_host_operator_assembly_matches_scipy(lib, n, m, dens, base):
     assert np.array_equal(mid, H.indptr[:-1] + np.diff(sp.csr_matrix(P).indptr))
     np.testing.assert_array_equal(dP, P.diagonal())
     np.testing.assert_allclose(dAA, np.asarray(A.multiply(A).sum(axis=0)).ravel(), rtol=1e-14, atol=0)
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """The driver's contract: `bench.py --impl reference` (the CPU port of the path on the host cores; Julia is not
+    available) prints ONE JSON line on stdout with the agreed keys -- nothing else, whatever native code prints."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--scale", "0.005",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, out.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "admm_iters_per_s" and d["unit"] == "iter/s"
+    assert d["higher_is_better"] is True and d["dtype"] == "f64" and d["n_gpus"] == 1
+    assert d["value"] > 0 and d["e2e"]["value"] == d["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert "workload" in d["config"]
