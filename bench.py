@@ -314,8 +314,9 @@ def run_b200(args):
                      "kernel": "admm_kernel (persistent; 1 launch per step)" if world == 1 else
                      "admm_peer_sliced_kernel (persistent; 1 launch per GPU per step; per-GPU GB/s)", "peak_source": peak_src,
                      "spmv": spmv, "note": "cfg5's uniformly random columns make every 8-byte gather of x move a 32-byte L2 "
-                     "sector: 1.375 sectors per non-zero through the SM's L2->L1 port (1 sector/clk) bound the H pass at 0.169 ms "
-                     "= 0.42 of the HBM peak; the kernel runs at 88 % of that bound (DESIGN.md 4.2, profiles/r1d_csrvec_spmv_bench.jsonl)"},
+                     "sector: 44 B per non-zero cross the SM's L2->L1 port (ncu), which caps the H pass at 0.46 of the HBM peak; "
+                     "the kernel runs at about 80 % of the best rate measured through that port, as does a structurally different "
+                     "CSR-vector kernel (DESIGN.md 4.2, profiles/r1d_csrvec_spmv_bench.jsonl)"},
         "cg_iters_per_s": pcg / (dev_ms * 1e-3),
     }
     if world == 1 and not args.no_cpu:
