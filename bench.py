@@ -101,7 +101,7 @@ class ClockSampler:
 
 
 def make_workload(name, scale):
-    from quadraticprogramsolver_b200 import problems
+    from workloads import problems
     t0 = time.time()
     if name == "cfg5":
         P, q, A, l, u = problems.config_cfg5(seed=1234, scale=scale)
@@ -331,7 +331,7 @@ def run_cfg3(args):
     """configs[2]: 65 536 small dense QPs (n = 64, m = 96), contiguous batch slices per GPU, no collective.
     metric: QP solves/s (whole batch / slowest rank's device time)."""
     from quadraticprogramsolver_b200 import solver as S
-    from quadraticprogramsolver_b200.problems import config_cfg3_batch
+    from workloads.problems import config_cfg3_batch
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

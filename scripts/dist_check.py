@@ -12,7 +12,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from quadraticprogramsolver_b200 import solver as S  # noqa: E402
-from quadraticprogramsolver_b200.problems import config_cfg5  # noqa: E402
+from workloads.problems import config_cfg5  # noqa: E402
 
 pscale = float(sys.argv[1]) if len(sys.argv) > 1 else 0.02
 tscale = float(sys.argv[2]) if len(sys.argv) > 2 else 0.0

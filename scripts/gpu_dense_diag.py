@@ -4,7 +4,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import c_oracle
 from quadraticprogramsolver_b200 import solver as S
-from quadraticprogramsolver_b200.problems import config_cfg3_batch
+from workloads.problems import config_cfg3_batch
 kw = dict(rho=0.1, adptRho=True, epsAbs=1e-7, epsRel=1e-7, numIterations=50000)
 for n, m in [(40, 96), (64, 96), (17, 94), (64, 93)]:
     P, q, A, l, u = config_cfg3_batch(160, n, m, seed=77)

@@ -3,7 +3,7 @@ import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from quadraticprogramsolver_b200 import solver as S
-from quadraticprogramsolver_b200.problems import config_cfg5
+from workloads.problems import config_cfg5
 P, q, A, l, u = config_cfg5(seed=1234)
 n, m = P.shape[0], A.shape[0]
 Parr, Aarr = S.csc_arrays_int64(P), S.csc_arrays_int64(A)

@@ -3,7 +3,7 @@ import json, os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from quadraticprogramsolver_b200 import solver as S
-from quadraticprogramsolver_b200.problems import config_cfg3_batch
+from workloads.problems import config_cfg3_batch
 from oracle import c_oracle
 
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 65536

@@ -4,7 +4,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 if len(sys.argv) > 1 and sys.argv[1] == "child":
     from quadraticprogramsolver_b200 import solver as S
-    from quadraticprogramsolver_b200.problems import config_cfg2, config_cfg4
+    from workloads.problems import config_cfg2, config_cfg4
     out = {"grid": os.environ.get("QPB200_GRID", "auto")}
     for name, cfg, kw in (("cfg2", config_cfg2, dict(numIterations=1000)), ("cfg4", config_cfg4, dict(numIterations=300))):
         P, q, A, l, u = cfg()

@@ -3,7 +3,7 @@ import json, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from quadraticprogramsolver_b200 import solver as S, partition
-from quadraticprogramsolver_b200.problems import config_cfg5
+from workloads.problems import config_cfg5
 P, q, A, l, u = config_cfg5(seed=1234)
 for R in (1, 2, 4, 8):
     P_r, A_r, l_r, u_r, rows, cols = partition.slice_problem(P, A, l, u, 0, R)

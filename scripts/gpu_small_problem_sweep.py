@@ -8,7 +8,7 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from quadraticprogramsolver_b200 import solver as S                      # noqa: E402
-from quadraticprogramsolver_b200.problems import config_cfg1, config_cfg2, config_cfg4   # noqa: E402
+from workloads.problems import config_cfg1, config_cfg2, config_cfg4   # noqa: E402
 
 probs = {"cfg2": (config_cfg2(), dict(numIterations=500)),
          "cfg4": (config_cfg4(), dict(numIterations=200)),

@@ -4,7 +4,7 @@ import json, os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from quadraticprogramsolver_b200 import solver as S
-from quadraticprogramsolver_b200.problems import config_cfg5
+from workloads.problems import config_cfg5
 tag = sys.argv[1]
 scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 P, q, A, l, u = config_cfg5(seed=1234, scale=scale)

@@ -7,7 +7,7 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from quadraticprogramsolver_b200 import solver as S  # noqa: E402
-from quadraticprogramsolver_b200.problems import config_cfg5  # noqa: E402
+from workloads.problems import config_cfg5  # noqa: E402
 
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 2

@@ -4,7 +4,7 @@ import numpy as np
 import scipy.sparse as sp
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from quadraticprogramsolver_b200 import solver as S
-from quadraticprogramsolver_b200.problems import config_cfg1, config_cfg3_batch, config_sparse
+from workloads.problems import config_cfg1, config_cfg3_batch, config_sparse
 
 P, q, A, l, u = config_cfg1()
 for loader in ("tma", "ldg", "tma_pipe"):

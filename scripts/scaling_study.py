@@ -7,7 +7,8 @@ import sys
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from quadraticprogramsolver_b200 import problems, solver as S   # noqa: E402
+from quadraticprogramsolver_b200 import solver as S
+from workloads import problems   # noqa: E402
 
 cases = {
     "cfg1 (n=100, m=50)": problems.config_cfg1(seed=1234),

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
 from oracle import qp_oracle  # noqa: E402
-from quadraticprogramsolver_b200.problems import GenerateRandomQP, ProblemClass  # noqa: E402
+from workloads.problems import GenerateRandomQP, ProblemClass  # noqa: E402
 
 CASES = [
     # name, class, n, m, seed, mode, kwargs

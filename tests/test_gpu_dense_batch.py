@@ -5,7 +5,7 @@ import pytest
 import scipy.sparse as sp
 
 from oracle import c_oracle, qp_oracle
-from quadraticprogramsolver_b200.problems import config_cfg3_batch
+from workloads.problems import config_cfg3_batch
 
 pytestmark = pytest.mark.gpu
 

@@ -15,7 +15,7 @@ import pytest
 import scipy.sparse as sp
 
 from oracle import c_oracle, qp_oracle
-from quadraticprogramsolver_b200.problems import (GenerateRandomQP, ProblemClass, config_cfg1, config_cfg4,
+from workloads.problems import (GenerateRandomQP, ProblemClass, config_cfg1, config_cfg4,
                                                   config_cfg5, config_sparse, sprandn)
 
 pytestmark = pytest.mark.gpu
@@ -283,7 +283,7 @@ def test_dense_batch_is_bitwise_reproducible(lib):
     """Dynamic work queue, but every QP is solved by one CTA with fixed-order sums: results do not depend on
     which CTA picks which problem."""
     S = _solver()
-    from quadraticprogramsolver_b200.problems import config_cfg3_batch
+    from workloads.problems import config_cfg3_batch
     P, q, A, l, u = config_cfg3_batch(700, 64, 96, seed=4)
     X1, f1, i1, _ = S.SolveQuadraticProgramBatch(P, q, A, l, u)
     X2, f2, i2, _ = S.SolveQuadraticProgramBatch(P, q, A, l, u)
@@ -296,7 +296,7 @@ def test_dense_batch_is_bitwise_reproducible(lib):
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("case", ["cfg1", "cfg1_badly_scaled", "svm_inf_bounds", "sparse_5k"])
 def test_equilibrated_solve_matches_oracle(lib, case):
-    from quadraticprogramsolver_b200.problems import badly_scaled
+    from workloads.problems import badly_scaled
     S = _solver()
     if case == "cfg1":
         prob = config_cfg1(seed=1236)
@@ -327,7 +327,7 @@ def test_equilibrated_solve_matches_oracle(lib, case):
 
 
 def test_equilibration_rescues_a_badly_scaled_problem_and_update_vectors(lib):
-    from quadraticprogramsolver_b200.problems import badly_scaled
+    from workloads.problems import badly_scaled
     S = _solver()
     P, q, A, l, u = badly_scaled(config_cfg1(seed=1234), seed=0)
     kw = dict(rho=0.1, adptRho=True, numIterations=4000)

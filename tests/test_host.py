@@ -9,7 +9,7 @@ import pytest
 import scipy.sparse as sp
 
 from quadraticprogramsolver_b200 import _lib
-from quadraticprogramsolver_b200.problems import config_cfg1, sprandn
+from workloads.problems import config_cfg1, sprandn
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -207,7 +207,7 @@ def test_host_equilibration_matches_oracle(lib, case):
     """qpb200_create's host-side Ruiz equilibration (no GPU needed) against oracle/qp_oracle.ruiz_equilibrate."""
     import scipy.sparse as sp
     from oracle import qp_oracle
-    from quadraticprogramsolver_b200.problems import GenerateRandomQP, ProblemClass, badly_scaled, config_cfg1
+    from workloads.problems import GenerateRandomQP, ProblemClass, badly_scaled, config_cfg1
     from quadraticprogramsolver_b200.solver import _csc_arrays, _p64, _pd
     if case == "cfg1":
         P, q, A, l, u = config_cfg1(seed=1234)

@@ -8,7 +8,7 @@ import pytest
 import scipy.sparse as sp
 
 from oracle import c_oracle, qp_oracle
-from quadraticprogramsolver_b200.problems import (GenerateRandomQP, ProblemClass, config_cfg1, config_cfg3_batch,
+from workloads.problems import (GenerateRandomQP, ProblemClass, config_cfg1, config_cfg3_batch,
                                                   config_cfg4, config_cfg5)
 
 # RunTests.jl:50-56
@@ -127,7 +127,7 @@ def test_golden_fixtures_reproduce(path):
 # Ruiz equilibration (not in the reference; the oracle defines it, see ruiz_equilibrate)
 # ---------------------------------------------------------------------------------------------------
 def test_ruiz_equilibrate_balances_the_kkt_matrix():
-    from quadraticprogramsolver_b200.problems import badly_scaled
+    from workloads.problems import badly_scaled
     P, q, A, l, u = badly_scaled(config_cfg1(seed=1234), seed=3)
     Ps, qs, As, ls, us, D, E, c = qp_oracle.ruiz_equilibrate(P, q, A, l, u, 15)
     assert np.all(D > 0) and np.all(E > 0) and c > 0
@@ -161,7 +161,7 @@ def test_scaling_leaves_the_solution_unchanged(mode):
 
 
 def test_scaling_rescues_a_badly_scaled_problem():
-    from quadraticprogramsolver_b200.problems import badly_scaled
+    from workloads.problems import badly_scaled
     P, q, A, l, u = badly_scaled(config_cfg1(seed=1234), seed=0)
     kw = dict(rho=0.1, adptRho=True, numIterations=4000)
     x0, f0, i0 = qp_oracle.solve(P, q, A, l, u, mode="D", **kw)

@@ -11,7 +11,7 @@ import numpy as np
 import scipy.sparse as sp
 
 from quadraticprogramsolver_b200 import partition
-from quadraticprogramsolver_b200.problems import config_sparse
+from workloads.problems import config_sparse
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -57,7 +57,7 @@ _WORKER = textwrap.dedent('''
     import torch, torch.distributed as dist
     sys.path.insert(0, os.environ["QPB_ROOT"])
     from quadraticprogramsolver_b200 import partition
-    from quadraticprogramsolver_b200.problems import config_sparse
+    from workloads.problems import config_sparse
     from oracle import qp_oracle
 
     dist.init_process_group("gloo")
