@@ -52,6 +52,18 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def load_traffic(workload, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the timed kernel (one launch = one step), from the committed ncu
+    capture of this very launch (profiles/r2_traffic.json, written by scripts/ncu_traffic.sh); None when no capture of
+    the workload exists -- never a typed-in constant."""
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    try:
+        rec = json.load(open(path))[f"{workload}_n{world}"]
+        return float(rec["dram_bytes_per_launch"]), f"profiles/r2_traffic.json ({rec.get('git', '?')}, {rec.get('what', '')})"
+    except Exception:
+        return None, None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -110,6 +122,10 @@ def make_workload(name, scale):
         P, q, A, l, u = problems.config_cfg4(seed=1234, scale=scale)
         desc = (f"cfg4 constrained least squares (README form) as QP: n={P.shape[0]} m={A.shape[0]} nnz(P=A'A)={P.nnz} "
                 f"nnz([B;D])={A.nnz}; A_ls {4 * P.shape[0]}x{P.shape[0]}, B {P.shape[0] // 2} rows (<= c), D {P.shape[0] // 10} rows (= e), 5 nnz/row")
+    elif name == "banded":
+        P, q, A, l, u = problems.config_banded()
+        desc = (f"banded QP n={P.shape[0]} m={A.shape[0]} nnz(P)={P.nnz} nnz(A)={A.nnz}: cfg5's sizes and non-zeros per row, every "
+                "row's columns within +-256 of the diagonal (gathers with locality; separates the SpMV engine from cfg5's random columns)")
     elif name == "cfg2":
         P, q, A, l, u = problems.config_cfg2(seed=1234)
         desc = f"cfg2 sparse QP n={P.shape[0]} m={A.shape[0]} nnz(P)={P.nnz} nnz(A)={A.nnz} (d=1e-3, feasible bounds)"
@@ -124,17 +140,54 @@ def solver_kwargs():
                 numItrConv=25, epsPcg=1e-6, numItrPcg=1000)
 
 
-def cpu_sample(prob, precond, seconds):
-    """Time-bounded run of the compiled oracle on the same QP (all host threads)."""
+def bench_config(args, desc):
+    """The `config` object: identical in both arms (b200 / reference) for the same command line."""
+    world = max(1, args.gpus)
+    return {"workload": desc, "iters_per_step": ITERS,
+            "settings": "reference defaults (rho=1, sigma=1e-6, alpha=1.6, eps 1e-6, check every 25), Jacobi-PCG abstol 1e-6",
+            "parallelism": "1 GPU" if world == 1 else f"one QP row-partitioned over {world} GPUs (rows of A / columns of P per rank)",
+            "l2": "matrix streams exceed the 126 MB L2 at cfg5 size; stand-alone SpMV timings flush L2 between launches"}
+
+
+def cpu_sample(prob, precond, seconds, **over):
+    """Time-bounded run of the compiled oracle on the same QP, on ALL host cores whatever OMP_NUM_THREADS says
+    (torch.distributed.run exports OMP_NUM_THREADS=1)."""
     from oracle import c_oracle
+    c_oracle.use_all_cores()
     P, q, A, l, u = prob
     kw = solver_kwargs()
+    kw.update(over)
     x, flag, info = c_oracle.solve_sparse(P, q, A, l, u, precond=precond, time_limit_s=seconds, **kw)
     its, sec = info["iterations"], info["solve_seconds"]
     return {"value": its / sec, "unit": "iter/s", "cores": c_oracle.num_threads(), "kind": "port",
             "sample": f"ADMM iterations 1..{its} of the same QP ({sec:.1f} s wall, oracle/qp_oracle.c, "
                       f"{'Jacobi-PCG' if precond else 'un-preconditioned CG (reference)'}, OpenMP)",
-            "cg_iters_per_s": info["cg_iters_total"] / sec, "iterations": its, "host_cpus": os.cpu_count()}
+            "cg_iters_per_s": info["cg_iters_total"] / sec, "cg_iters_per_admm_iter": info["cg_iters_total"] / max(1, its),
+            "iterations": its, "host_cpus": os.cpu_count(), "x": x, "flag": int(flag), "info": info}
+
+
+def _public(cb):
+    return {k: v for k, v in cb.items() if k not in ("x", "flag", "info")}
+
+
+def parity_check(prob, solve_gpu, iters=25, eps_pcg=1e-10):
+    """north_star's criterion on the BENCHMARKED problem: the CPU port and the GPU run the same `iters` ADMM
+    iterations (tight inner solve so that the trajectory is well defined) and x, flag, iteration count are compared."""
+    over = dict(numIterations=iters, epsPcg=eps_pcg)
+    t0 = time.time()
+    ref = cpu_sample(prob, 1, 0.0, **over)
+    cpu_s = time.time() - t0
+    x_gpu, flag_gpu, info_gpu = solve_gpu(over)
+    xr = ref["x"]
+    err = float(np.max(np.abs(x_gpu - xr)) / (1.0 + np.max(np.abs(xr))))
+    return {"admm_iterations": iters, "eps_pcg": eps_pcg, "flag_gpu": int(flag_gpu), "flag_cpu_port": ref["flag"],
+            "iterations_gpu": int(info_gpu["iterations"]), "iterations_cpu_port": int(ref["iterations"]),
+            "cg_iters_gpu": int(info_gpu["pcg_iters_total"]), "cg_iters_cpu_port": int(ref["info"]["cg_iters_total"]),
+            "x_rel_err_inf": err, "tolerance": 1e-6, "pass": bool(err <= 1e-6 and int(flag_gpu) == ref["flag"]
+                                                                  and abs(int(info_gpu["iterations"]) - int(ref["iterations"])) <= 2),
+            "res_prim_gpu": float(info_gpu["res_prim"]), "res_prim_cpu_port": float(ref["info"]["res_prim"]),
+            "res_dual_gpu": float(info_gpu["res_dual"]), "res_dual_cpu_port": float(ref["info"]["res_dual"]),
+            "cpu_seconds": round(cpu_s, 1), "criterion": "|x - x_ref|inf <= 1e-6 (1 + |x_ref|inf), same flag, iterations within 2"}
 
 
 def run_reference(args):
@@ -142,9 +195,12 @@ def run_reference(args):
     if rank != 0:
         return
     prob, desc, gen_s = make_workload(args.workload, args.scale)
-    per_step = max(2.0, min(CPU_SAMPLE_SECONDS, 150.0 / max(1, args.steps + args.warmup)))
+    # warm-up steps only need to touch the matrices and spin the thread pool up: 1.5 s each; the timed steps share
+    # what is left of ~170 s.  A sample stops at ADMM iteration ITERS at the latest (the b200 arm's range 1..ITERS).
+    warm_s = 1.5
+    per_step = max(2.0, min(CPU_SAMPLE_SECONDS, (170.0 - warm_s * args.warmup) / max(1, args.steps)))
     for _ in range(args.warmup):
-        cpu_sample(prob, 1, per_step)
+        cpu_sample(prob, 1, warm_s)
     vals, samples = [], []
     t0 = time.time()
     for _ in range(args.steps):
@@ -153,11 +209,13 @@ def run_reference(args):
     wall = time.time() - t0
     its = sum(s["iterations"] for s in samples)
     value = its / sum(s["iterations"] / s["value"] for s in samples)
-    cb = dict(samples[-1]); cb["value"] = value
+    cb = _public(samples[-1]); cb["value"] = value
+    cb["cg_iters_per_admm_iter"] = sum(s["info"]["cg_iters_total"] for s in samples) / max(1, its)
+    cb["sample"] += f"; {args.steps} such samples, {warm_s} s warm-up samples"
     line = {"impl": "reference", "metric": "admm_iters_per_s", "value": value, "unit": "iter/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "iters_per_step": "time-bounded sample", "linear_solver": "jacobi-pcg eps 1e-6"},
+            "config": bench_config(args, desc),
             "cpu_baseline": cb,
             "e2e": {"value": value, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -241,6 +299,25 @@ def run_b200(args):
             ms = s.time_apply(which, reps=20, flush_l2=True)
             gb = s.apply_bytes(which) / 1e9
             spmv[name] = {"ms": ms, "GBs": gb / (ms * 1e-3), "frac": gb / (ms * 1e-3) / peak}
+    # ---- parity on the benchmarked problem (rank 0 runs the CPU port; every rank runs the GPU solve)
+    parity = None
+    if not args.no_parity:
+        def solve_gpu(over):
+            kk = dict(kw); kk.update(over)
+            if world == 1:
+                s.update_settings(**kk)
+                xx = np.zeros(n)
+                fl = s.solve(xx)
+                return xx, fl, s.info
+            with S.QPB200DistSolver(P, q, A, l, u, presliced=presliced, **kk) as ds:
+                xx = np.zeros(n)
+                fl = ds.solve(xx)
+                return xx, fl, ds.info
+        if rank == 0:
+            parity = parity_check(prob, solve_gpu)
+        else:
+            solve_gpu(dict(numIterations=25, epsPcg=1e-10))
+        barrier()
     s.close()
 
     # ---- end-to-end arm: host buffers -> create -> solve -> results on host, every step --------
@@ -264,7 +341,8 @@ def run_b200(args):
         if world == 1:
             xx = np.zeros(n)
             return S.solve_csc_arrays(n, m, Parr, q64, Aarr, l64, u64, xx, want_zy=True, **kw)[1]
-        with S.QPB200DistSolver(P, q, A, l, u, presliced=presliced, **kw) as ds:
+        # the caller holds the whole P, A on the host: cutting this rank's slice out of them is part of every call
+        with S.QPB200DistSolver(P, q, A, l, u, **kw) as ds:
             xx = np.zeros(n)
             ds.solve(xx, want_zy=True)
             return ds.info
@@ -291,15 +369,16 @@ def run_b200(args):
         if dist is not None:
             dist.destroy_process_group()
         return
+    traffic, traffic_src = load_traffic(args.workload, world)
     line = {
         "metric": "admm_iters_per_s", "value": value, "unit": "iter/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms / max(1, args.steps), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "iters_per_step": ITERS, "settings": "reference defaults (rho=1, sigma=1e-6, alpha=1.6, "
-                   "eps 1e-6, check every 25), Jacobi-PCG abstol 1e-6", "parallelism": "1 GPU" if world == 1 else
-                   f"one QP row-partitioned over {world} GPUs (rows of A / columns of P per rank; one persistent kernel per GPU, reduce-scatter / all-gather of the n-vectors in-kernel over NVLink peer memory)", "l2": "matrix streams (0.55 GB per operator application) exceed the 126 MB L2; "
-                   "stand-alone SpMV timings flush L2 between launches", "conv_flag": flag,
-                   "pcg_iters_per_step": pcg / max(1, args.steps), "gen_s": round(gen_s, 1)},
+        "config": bench_config(args, desc),
+        "run": {"conv_flag": flag, "pcg_iters_per_step": pcg / max(1, args.steps), "cg_iters_per_admm_iter": pcg / max(1, iters),
+                "gen_s": round(gen_s, 1), "collectives": None if world == 1 else
+                "one persistent kernel per GPU; reduce-scatter / all-gather of the n-vectors in-kernel over NVLink peer memory"},
+        "parity": parity,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "iter/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps, "ms_per_step": 1e3 * e2e_wall / e2e_steps,
@@ -307,10 +386,7 @@ def run_b200(args):
                                           "copies_destroy_host": 1e3 * e2e_wall / e2e_steps - (e2e_create_ms + e2e_solve_ms) / e2e_steps}},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None,
-                     "traffic_ncu": {"note": "a 100-iteration launch is too long to replay under ncu; captured instead: the same kernel "
-                                     "for 1 ADMM iteration = 48 CG iterations (profiles/r1b_ncu_full_cfg5_key_metrics.csv)",
-                                     "dram_bytes_per_launch": 32.37e9, "algorithmic_bytes_per_launch": 34.7e9, "ratio": 0.93},
+                     "traffic": traffic, "traffic_source": traffic_src,
                      "kernel": "admm_kernel (persistent; 1 launch per step)" if world == 1 else
                      "admm_peer_sliced_kernel (persistent; 1 launch per GPU per step; per-GPU GB/s)", "peak_source": peak_src,
                      "spmv": spmv, "note": "cfg5's uniformly random columns make every 8-byte gather of x move a 32-byte L2 "
@@ -320,8 +396,8 @@ def run_b200(args):
         "cg_iters_per_s": pcg / (dev_ms * 1e-3),
     }
     if world == 1 and not args.no_cpu:
-        line["cpu_baseline"] = cpu_sample(prob, 1, CPU_SAMPLE_SECONDS)
-        line["cpu_baseline_reference_cg"] = cpu_sample(prob, 0, CPU_SAMPLE_SECONDS / 2)
+        line["cpu_baseline"] = _public(cpu_sample(prob, 1, CPU_SAMPLE_SECONDS))
+        line["cpu_baseline_reference_cg"] = _public(cpu_sample(prob, 0, CPU_SAMPLE_SECONDS / 2))
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -435,10 +511,11 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg5", choices=["cfg5", "cfg2", "cfg3", "cfg4"])
+    ap.add_argument("--workload", default="cfg5", choices=["cfg5", "cfg2", "cfg3", "cfg4", "banded"])
     ap.add_argument("--batch", type=int, default=65536, help="cfg3 batch size")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink cfg5 (tests only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-bench parity check against the CPU port")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     # The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints "NCCL version ..." from

@@ -90,6 +90,15 @@ typedef struct qpb200_settings {
                                        shared memory, 2 = A held in registers during the iterations, 3 = A and
                                        K^-1 in registers (A/B runs)                                               */
 
+#define QPB200_RSV_CG_RECURRENCE 4  /* sparse single-GPU path: 1 = the recurrence exactly as IterativeSolvers' CGIterable /
+                                       PCGIterable writes it (two reductions, four grid barriers per iteration);
+                                       2 = one-reduction arrangement of the same (P)CG (Chronopoulos-Gear: same iterates
+                                       in exact arithmetic, same stopping rule at the same point, three grid barriers
+                                       per iteration); 0 = auto: 2 for problems whose iteration is barrier-latency bound
+                                       (nnz(P) + 2 nnz(A) <= 16 M: measured 14.5 vs 15.5 us per CG iteration at
+                                       configs[0], 30.2 vs 32.8 at configs[1]), 1 for larger ones (the extra vector
+                                       traffic costs more than the barrier there)                                     */
+
 typedef struct qpb200_info {
     int32_t conv_flag;       /* QPB200_CONV_*                                                      */
     int32_t reserved;

@@ -93,3 +93,12 @@ def solve_dense_batch(P, q, A_cm, l, u, x0=None, **kw):
 
 def num_threads() -> int:
     return int(lib().oracle_num_threads())
+
+
+def use_all_cores() -> int:
+    """All cores this process may run on, regardless of OMP_NUM_THREADS (torchrun sets it to 1)."""
+    try:
+        nt = len(os.sched_getaffinity(0))
+    except AttributeError:
+        nt = os.cpu_count() or 1
+    return int(lib().oracle_set_num_threads(C.c_int(nt)))

@@ -448,3 +448,15 @@ int oracle_num_threads(void) {
     return 1;
 #endif
 }
+
+/* bench.py's CPU arm: use `nt` threads whatever OMP_NUM_THREADS says (torch.distributed.run exports
+ * OMP_NUM_THREADS=1 to every rank, which would silently time a single-threaded baseline). */
+int oracle_set_num_threads(int nt) {
+#ifdef _OPENMP
+    if (nt > 0) omp_set_num_threads(nt);
+    return omp_get_max_threads();
+#else
+    (void)nt;
+    return 1;
+#endif
+}

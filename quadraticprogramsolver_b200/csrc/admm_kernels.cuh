@@ -43,6 +43,7 @@ struct SparseProblemDev {
     double *XY, *XG, *UT;       // vector pairs, n + m each
     double *z, *zt;             // m
     double *r, *c, *zp, *dinv;  // n
+    double *wv;                 // n: w = K z of the one-reduction PCG
     double normQ;
     // optional (Ruiz equilibration): D, 1/(c D) [n] and 1/E [m] turn the norms of CheckConvergence back into
     // those of the unscaled problem; nullptr = the problem is solved as given (the reference's behaviour)
@@ -53,6 +54,13 @@ struct SparseProblemDev {
     GridSync gs;
     AdmmSettingsDev s;
     AdmmInfoDev *info;
+};
+
+// Book-keeping of a solve that only thread 0 of a CTA touches: kept in shared memory, not in registers (the tile loop
+// needs them: with these as loop-carried registers ptxas spilled the epilogues' accumulators inside the tile loops).
+struct AdmmCounters {
+    long long rho_updates, pcg_total, pcg_maxed, n_h, n_a;
+    double res_prim, res_dual;
 };
 
 __device__ __forceinline__ double clamp_julia(double x, double lo, double hi) {
@@ -81,14 +89,28 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) spmv_kernel(CsrTiled M, co
 // Every scalar (rho, alpha_cg, beta, residuals, flags) is recomputed identically by every thread
 // from bit-identical all-reduced values, so control flow is uniform across the grid.
 // =============================================================================================
-template <int TMA, bool PRE>
+// CGV = false: the recurrence of IterativeSolvers' CGIterable / PCGIterable as written (two reductions and four
+//   grid barriers per iteration).
+// CGV = true (default, settings.reserved_i[QPB200_RSV_CG_RECURRENCE] = 0): the Chronopoulos-Gear arrangement of the
+//   SAME preconditioned CG -- gamma = r.z, delta = z.(K z) and |r|^2 come out of ONE reduction fused into the H pass,
+//   beta = gamma / gamma_prev, alpha = gamma / (delta - beta gamma / alpha_prev), and p = z + beta p, s = w + beta s
+//   (= K p by linearity), x~ += alpha p, r -= alpha s, z = Pl \ r are one vector pass: three grid barriers and three
+//   phases per iteration instead of four and four.  Same iterates in exact arithmetic, same stopping rule on the same
+//   recurrence residual; one more operator application per inner solve (the K z of the final residual is unused).
+template <int TMA, bool PRE, bool CGV>
 __global__ void __launch_bounds__(kThreads, kMinCtas) admm_kernel(SparseProblemDev p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SpmvSmem &sm = *reinterpret_cast<SpmvSmem *>(smem_raw);
+    __shared__ AdmmCounters ctr;
     PipeState ps;
     spmv_smem_init(sm, ps);
     SyncState st;
     st.epoch = 0;
+    if (threadIdx.x == 0) {
+        ctr.rho_updates = ctr.pcg_total = ctr.pcg_maxed = ctr.n_h = ctr.n_a = 0;
+        ctr.res_prim = ctr.res_dual = nan("");
+    }
+    auto count = [&](long long &c, long long by) { if (threadIdx.x == 0) c += by; };
 
     const int n = p.n, m = p.m;
     const int gtid = blockIdx.x * kThreads + threadIdx.x;
@@ -99,14 +121,9 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) admm_kernel(SparseProblemD
     double *const zpv = PRE ? p.zp : p.r;   // un-preconditioned: "z" of PCG is r itself
 
     double rho = p.s.rho, rho1 = 1.0 / rho;                         // SolveQuadraticProgram.jl:30
-    const double alpha = p.s.alpha, alpha1 = 1.0 - alpha;           // :31
-    const double sigma = p.s.sigma;
-    const double eps_admm = fmin(p.s.eps_abs, p.s.eps_rel) * 1e-2;  // :34
+    // p.s.alpha, 1 - p.s.alpha (:31), p.s.sigma, p.s.pcg_rel_eps are used straight out of the parameter block (constant-bank operands)
     double rhorho = rho;                                            // :43
     int conv_flag = 1;                                              // :33 convNumItr
-    long long rho_updates = 0, pcg_total = 0, pcg_maxed = 0, n_h = 0, n_a = 0;
-    double res_prim = nan(""), res_dual = nan("");
-    const double reltol = p.s.pcg_rel_eps;
     bool dinv_ready = false;
     // rho and 1/rho of constraint i (the scalars of SolveQuadraticProgram.jl:30 unless a scale vector was set)
     auto rho_of = [&](int i) { return p.rs ? rho * p.rs[i] : rho; };
@@ -120,59 +137,117 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) admm_kernel(SparseProblemD
             rho = rhorho;
             rho1 = 1.0 / rho;
             changed = true;
-            ++rho_updates;
+            count(ctr.rho_updates, 1);
         }
         if (changed || !dinv_ready) {
             if (PRE)
-                for (int j = gtid; j < n; j += gstride) p.dinv[j] = 1.0 / (p.dP[j] + sigma + rho * p.dAA[j]);
+                for (int j = gtid; j < n; j += gstride) p.dinv[j] = 1.0 / (p.dP[j] + p.s.sigma + rho * p.dAA[j]);
             if (changed)
                 for (int i = gtid; i < m; i += gstride) g[i] = rho_of(i) * (p.zt[i] - p.z[i]) + y[i];
             dinv_ready = true;
             grid_barrier(p.gs, st);
         }
 
-        // ---- [P1] r0 = b - K x~  with b = sigma x - q + A'(rho z - y)   (LinearSystemSolvers.jl:178-180
+        // ---- [P1] r0 = b - K x~  with b = p.s.sigma x - q + A'(rho z - y)   (LinearSystemSolvers.jl:178-180
         //      and the first MV product of cg!); u = Pl \ r0
         double acc[2] = {0.0, 0.0};
         {
             auto epi = [&](int j, double s0, double) {
-                const double rj = sigma * (x[j] - xt[j]) - p.q[j] - s0;
+                const double rj = p.s.sigma * (x[j] - xt[j]) - p.q[j] - s0;
                 p.r[j] = rj;
                 const double zj = PRE ? p.dinv[j] * rj : rj;
-                if (PRE) p.zp[j] = zj;
+                if (PRE && !CGV) p.zp[j] = zj;
                 u[j] = zj;
                 acc[0] += rj * rj;
                 acc[1] += rj * zj;
             };
             spmv_tiles<TMA, false>(p.H, p.XG, sm, ps, epi);
-            ++n_h;
+            count(ctr.n_h, 1);
         }
         grid_barrier_reduce<2, false>(p.gs, st, acc, sm.red, sm.bcast);
         double residual = sqrt(acc[0]);
         double rz = acc[1];
-        const double tol = fmax(reltol * residual, p.s.pcg_eps);     // cg_iterator!: max(reltol*|r0|, abstol)
+        const double tol = fmax(p.s.pcg_rel_eps * residual, p.s.pcg_eps);     // cg_iterator!: max(p.s.pcg_rel_eps*|r0|, abstol)
 
-        // ---- PCG loop (CGIterable / PCGIterable)
         long long k = 0;
+        if (CGV) {
+            // ---- one-reduction PCG: u holds z = Pl \ r (the vector A and H gather from), p.zp the search direction,
+            //      p.c holds s = K p, p.wv holds w = K z
+            double gam = 0.0, a_cg = 0.0;
+            bool first = true;
+            while (k < p.s.pcg_max_iter && !(residual <= tol)) {
+                {   // t = rho * A z
+                    auto epi = [&](int i, double s0, double) { t[i] = rho_of(i) * s0; };
+                    spmv_tiles<TMA, false>(p.A, u, sm, ps, epi);
+                    count(ctr.n_a, 1);
+                }
+                grid_barrier(p.gs, st);
+                double d3[2] = {0.0, 0.0};                             // gamma = r.z, delta = z.w
+                {   // w = P z + A' t + p.s.sigma z      (LinearSystemSolvers.jl:152-157)
+                    auto epi = [&](int j, double s0, double) {
+                        const double zj = u[j];
+                        const double wj = s0 + p.s.sigma * zj;
+                        p.wv[j] = wj;
+                        d3[0] += p.r[j] * zj;
+                        d3[1] += zj * wj;
+                    };
+                    spmv_tiles<TMA, false>(p.H, p.UT, sm, ps, epi);
+                    count(ctr.n_h, 1);
+                }
+                grid_barrier_reduce<2, false>(p.gs, st, d3, sm.red, sm.bcast);
+                double beta = 0.0;
+                if (first) {
+                    if (!(d3[1] > 0.0)) break;                         // breakdown guard (K is SPD)
+                    a_cg = d3[0] / d3[1];
+                } else {
+                    beta = d3[0] / gam;
+                    const double den = d3[1] - beta * d3[0] / a_cg;
+                    if (!(den > 0.0)) break;
+                    a_cg = d3[0] / den;
+                }
+                gam = d3[0];
+                // p = z + beta p ; s = w + beta s ; x~ += a p ; r -= a s ; z = Pl \ r ; |r|^2
+                double rr[1] = {0.0};
+                for (int j = gtid; j < n; j += gstride) {
+                    double pj = u[j], sj = p.wv[j];
+                    if (!first) {                                      // (stale p, s of the previous solve are never read)
+                        pj += beta * p.zp[j];
+                        sj += beta * p.c[j];
+                    }
+                    p.zp[j] = pj;
+                    p.c[j] = sj;
+                    xt[j] += a_cg * pj;
+                    const double rj = p.r[j] - a_cg * sj;
+                    p.r[j] = rj;
+                    u[j] = PRE ? p.dinv[j] * rj : rj;
+                    rr[0] += rj * rj;
+                }
+                first = false;
+                grid_barrier_reduce<1, false>(p.gs, st, rr, sm.red, sm.bcast);
+                residual = sqrt(rr[0]);
+                ++k;
+            }
+        } else {
+        // ---- PCG loop (CGIterable / PCGIterable)
         while (k < p.s.pcg_max_iter && !(residual <= tol)) {
             // [S2] t = rho * A u
             {
                 auto epi = [&](int i, double s0, double) { t[i] = rho_of(i) * s0; };
                 spmv_tiles<TMA, false>(p.A, u, sm, ps, epi);
-                ++n_a;
+                count(ctr.n_a, 1);
             }
             grid_barrier(p.gs, st);
-            // [S3] c = P u + rho A'(A u) + sigma u ; u.c      (LinearSystemSolvers.jl:152-157)
+            // [S3] c = P u + rho A'(A u) + p.s.sigma u ; u.c      (LinearSystemSolvers.jl:152-157)
             double uc[1] = {0.0};
             {
                 auto epi = [&](int j, double s0, double) {
                     const double uj = u[j];
-                    const double cj = s0 + sigma * uj;
+                    const double cj = s0 + p.s.sigma * uj;
                     p.c[j] = cj;
                     uc[0] += uj * cj;
                 };
                 spmv_tiles<TMA, false>(p.H, p.UT, sm, ps, epi);
-                ++n_h;
+                count(ctr.n_h, 1);
             }
             grid_barrier_reduce<1, false>(p.gs, st, uc, sm.red, sm.bcast);
             if (!(uc[0] > 0.0)) break;                               // breakdown guard (K is SPD)
@@ -200,8 +275,9 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) admm_kernel(SparseProblemD
             }
             rz = rz_new;
         }
-        pcg_total += k;
-        if (k >= p.s.pcg_max_iter && !(residual <= tol)) ++pcg_maxed;
+        }
+        count(ctr.pcg_total, k);
+        if (k >= p.s.pcg_max_iter && !(residual <= tol)) count(ctr.pcg_maxed, 1);
 
         // ---- [Upd] z~ = A x~ (LinearSystemSolvers.jl:183) fused with SolveQuadraticProgram.jl:56-61
         const bool do_check = (ii % p.s.check_every) == 0;           // :63
@@ -210,7 +286,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) admm_kernel(SparseProblemD
             auto epi = [&](int i, double s0, double) {
                 const double zt_i = s0;
                 const double z_old = p.z[i], y_old = y[i];
-                const double zr = alpha * zt_i + alpha1 * z_old;
+                const double zr = p.s.alpha * zt_i + (1.0 - p.s.alpha) * z_old;
                 const double rho_i = rho_of(i);
                 const double z_new = clamp_julia(zr + rho1_of(i) * y_old, p.l[i], p.u[i]);   // :60
                 const double y_new = y_old + rho_i * (zr - z_new);                     // :61
@@ -222,11 +298,11 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) admm_kernel(SparseProblemD
                 nrm[1] = nanmax(nrm[1], fabs(z_new - z_old) * ei);
             };
             spmv_tiles<TMA, false>(p.A, xt, sm, ps, epi);
-            ++n_a;
+            count(ctr.n_a, 1);
         }
         for (int j = gtid; j < n; j += gstride) {
             const double x_old = x[j];
-            const double x_new = alpha * xt[j] + alpha1 * x_old;      // :57
+            const double x_new = p.s.alpha * xt[j] + (1.0 - p.s.alpha) * x_old;      // :57
             x[j] = x_new;
             const double dj = (p.Dv && do_check) ? p.Dv[j] : 1.0;
             nrm[0] = nanmax(nrm[0], fabs(x_new - x_old) * dj);
@@ -245,7 +321,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) admm_kernel(SparseProblemD
                     nrm[3] = nanmax(nrm[3], fabs(zi) * ei);           // |z|   (maxNormPrim = max of both)
                 };
                 spmv_tiles<TMA, false>(p.A, x, sm, ps, epi);
-                ++n_a;
+                count(ctr.n_a, 1);
             }
             {
                 auto epi = [&](int j, double s0, double s1) {
@@ -255,12 +331,12 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) admm_kernel(SparseProblemD
                     nrm[5] = nanmax(nrm[5], fabs(s1) * dj);                 // |A'y|
                 };
                 spmv_tiles<TMA, true>(p.H, p.XY, sm, ps, epi);
-                ++n_h;
+                count(ctr.n_h, 1);
             }
             grid_barrier_reduce<7, true>(p.gs, st, nrm, sm.red, sm.bcast);
             const double dx = nrm[0], dz = nrm[1];
-            res_prim = nrm[2];
-            res_dual = nrm[4];
+            const double res_prim = nrm[2], res_dual = nrm[4];
+            if (threadIdx.x == 0) { ctr.res_prim = res_prim; ctr.res_dual = res_dual; }
             const double max_prim = nrm[3];
             const double max_dual = nanmax(nrm[5], p.normQ);
             if (p.s.adaptive_rho) {                                   // :92-96
@@ -270,6 +346,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) admm_kernel(SparseProblemD
             const double eps_prim = p.s.eps_abs + p.s.eps_rel * max_prim;   // :99
             const double eps_dual = p.s.eps_abs + p.s.eps_rel * max_dual;   // :100
             if ((res_prim < eps_prim) && (res_dual < eps_dual)) conv_flag = 3;   // :102
+            const double eps_admm = fmin(p.s.eps_abs, p.s.eps_rel) * 1e-2;       // :34
             if ((dx <= eps_admm) && (dz <= eps_admm)) conv_flag = 2;             // :105 (overrides)
             if (conv_flag != 1) break;                                // :66
         }
@@ -281,13 +358,13 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) admm_kernel(SparseProblemD
         o.conv_flag = conv_flag;
         o.iterations = ii;
         o.rho_final = rho;
-        o.res_prim = res_prim;
-        o.res_dual = res_dual;
-        o.rho_updates = rho_updates;
-        o.pcg_iters_total = pcg_total;
-        o.pcg_maxed = pcg_maxed;
-        o.n_h_passes = n_h;
-        o.n_a_passes = n_a;
+        o.res_prim = ctr.res_prim;
+        o.res_dual = ctr.res_dual;
+        o.rho_updates = ctr.rho_updates;
+        o.pcg_iters_total = ctr.pcg_total;
+        o.pcg_maxed = ctr.pcg_maxed;
+        o.n_h_passes = ctr.n_h;
+        o.n_a_passes = ctr.n_a;
     }
 }
 

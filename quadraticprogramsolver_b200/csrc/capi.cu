@@ -128,7 +128,7 @@ int64_t qpb200_debug_tile_plan(int32_t rows, const int32_t *rowptr, int32_t grid
     M.cols = 0;
     M.ptr.assign(rowptr, rowptr + rows + 1);
     qpb::HostTiles T;
-    qpb::build_tiles(M, qpb::kTileNnz, T);
+    qpb::build_tiles(M, qpb::kTileFill, qpb::kTileRows, T);
     qpb::assign_tiles(T, grid);
     const int64_t nt = (int64_t)T.tiles.size();
     if (tiles_out && nt <= tiles_cap)
@@ -144,7 +144,7 @@ int64_t qpb200_debug_tile_plan(int32_t rows, const int32_t *rowptr, int32_t grid
     return nt;
 }
 
-int32_t qpb200_debug_tile_nnz(void) { return qpb::kTileNnz; }
+int32_t qpb200_debug_tile_nnz(void) { return qpb::kTileFill; }
 
 int qpb200_debug_assemble_h(int64_t n, int64_t m, const int64_t *Pp, const int64_t *Pi, const double *Pv, const int64_t *Ap,
                             const int64_t *Ai, const double *Av, int32_t base, int32_t *rowptr_out, int32_t *rowmid_out,

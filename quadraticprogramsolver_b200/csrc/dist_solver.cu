@@ -117,10 +117,7 @@ void dist_destroy(DistContext *d) {
 
 static int launch_seg(SparseSolver &s, DistContext &d, int seg, int do_check) {
     void *args[] = {(void *)&s.prob, (void *)&d.buf, (void *)&seg, (void *)&do_check};
-    const void *fns[3][2] = {{(const void *)admm_dist_kernel<0, false>, (const void *)admm_dist_kernel<0, true>},
-                             {(const void *)admm_dist_kernel<1, false>, (const void *)admm_dist_kernel<1, true>},
-                             {(const void *)admm_dist_kernel<2, false>, (const void *)admm_dist_kernel<2, true>}};
-    const void *fn = fns[s.loader][s.use_pre ? 1 : 0];
+    const void *fn = s.use_pre ? (const void *)admm_dist_kernel<1, true> : (const void *)admm_dist_kernel<1, false>;
     QPB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(s.grid), dim3(kThreads), args, sizeof(SpmvSmem), s.stream));
     ++d.launches;
     return QPB200_OK;
@@ -263,12 +260,9 @@ int dist_init(SparseSolver &s, DistContext *&out, int rank, int nranks, const vo
     QPB_CUDA(cudaMallocHost(&d->host_state, 2 * sizeof(DistState)));
     QPB_CUDA(cudaEventCreateWithFlags(&d->ev[0], cudaEventDisableTiming));
     QPB_CUDA(cudaEventCreateWithFlags(&d->ev[1], cudaEventDisableTiming));
-    for (const void *fn : {(const void *)admm_dist_kernel<0, false>, (const void *)admm_dist_kernel<0, true>,
-                           (const void *)admm_dist_kernel<1, false>, (const void *)admm_dist_kernel<1, true>,
-                           (const void *)admm_dist_kernel<2, false>, (const void *)admm_dist_kernel<2, true>}) {
-        QPB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpmvSmem)));
+    for (const void *fn : {(const void *)admm_dist_kernel<1, false>, (const void *)admm_dist_kernel<1, true>}) {
         int per_sm = 0;
-        QPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, sizeof(SpmvSmem)));
+        if (int prc = prep_tile_kernel(fn, &per_sm)) return prc;
         if (per_sm * s.num_sms < s.grid)
             return fail(QPB200_ERR_CUDA, "segment kernel cannot be co-resident at grid %d (%d per SM)", s.grid, per_sm);
     }
@@ -399,18 +393,10 @@ static int peer_init(SparseSolver &s, DistContext &d) {
     pd.dbg = nullptr;
     if (getenv("QPB200_TIMING")) QPB_CUDA(s.arena.alloc(&pd.dbg, 16, true));
     QPB_CUDA(s.arena.alloc(&d.tiny, 2, true));
-    for (const void *fn : {(const void *)admm_peer_kernel<0, false>, (const void *)admm_peer_kernel<0, true>,
-                           (const void *)admm_peer_kernel<1, false>, (const void *)admm_peer_kernel<1, true>,
-                           (const void *)admm_peer_kernel<2, false>, (const void *)admm_peer_kernel<2, true>,
-                           (const void *)admm_peer_sliced_kernel<0, false, false>, (const void *)admm_peer_sliced_kernel<0, true, false>,
-                           (const void *)admm_peer_sliced_kernel<1, false, false>, (const void *)admm_peer_sliced_kernel<1, true, false>,
-                           (const void *)admm_peer_sliced_kernel<2, false, false>, (const void *)admm_peer_sliced_kernel<2, true, false>,
-                           (const void *)admm_peer_sliced_kernel<0, false, true>, (const void *)admm_peer_sliced_kernel<0, true, true>,
-                           (const void *)admm_peer_sliced_kernel<1, false, true>, (const void *)admm_peer_sliced_kernel<1, true, true>,
-                           (const void *)admm_peer_sliced_kernel<2, false, true>, (const void *)admm_peer_sliced_kernel<2, true, true>}) {
-        QPB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpmvSmem)));
+    for (const void *fn : {(const void *)admm_peer_sliced_kernel<1, false, false>, (const void *)admm_peer_sliced_kernel<1, true, false>,
+                           (const void *)admm_peer_sliced_kernel<1, false, true>, (const void *)admm_peer_sliced_kernel<1, true, true>}) {
         int per_sm = 0;
-        QPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, sizeof(SpmvSmem)));
+        if (int prc = prep_tile_kernel(fn, &per_sm)) return prc;
         if (per_sm * s.num_sms < s.grid)
             return fail(QPB200_ERR_CUDA, "peer kernel cannot be co-resident at grid %d (%d per SM)", s.grid, per_sm);
     }
@@ -432,24 +418,13 @@ int peer_solve(SparseSolver &s, DistContext &d, double *x_inout, double *z_out, 
     QPB_CUDA(cudaEventRecord(s.ev0, s.stream));
     {
         void *args[] = {(void *)&s.prob, (void *)&d.peer};
-        const void *fns[3][2] = {{(const void *)admm_peer_kernel<0, false>, (const void *)admm_peer_kernel<0, true>},
-                                 {(const void *)admm_peer_kernel<1, false>, (const void *)admm_peer_kernel<1, true>},
-                                 {(const void *)admm_peer_kernel<2, false>, (const void *)admm_peer_kernel<2, true>}};
-        const void *fns_sliced[3][2] = {{(const void *)admm_peer_sliced_kernel<0, false, false>, (const void *)admm_peer_sliced_kernel<0, true, false>},
-                                        {(const void *)admm_peer_sliced_kernel<1, false, false>, (const void *)admm_peer_sliced_kernel<1, true, false>},
-                                        {(const void *)admm_peer_sliced_kernel<2, false, false>, (const void *)admm_peer_sliced_kernel<2, true, false>}};
-        const void *fns_cg[3][2] = {{(const void *)admm_peer_sliced_kernel<0, false, true>, (const void *)admm_peer_sliced_kernel<0, true, true>},
-                                    {(const void *)admm_peer_sliced_kernel<1, false, true>, (const void *)admm_peer_sliced_kernel<1, true, true>},
-                                    {(const void *)admm_peer_sliced_kernel<2, false, true>, (const void *)admm_peer_sliced_kernel<2, true, true>}};
-        // default: sliced CG vectors; QPB200_PEER_SLICED=0 selects the replicated variant (A/B)
-        const char *e = getenv("QPB200_PEER_SLICED");
-        const bool sliced = !(e && atoi(e) == 0);
+        const void *fns_sliced[2] = {(const void *)admm_peer_sliced_kernel<1, false, false>, (const void *)admm_peer_sliced_kernel<1, true, false>};
+        const void *fns_cg[2] = {(const void *)admm_peer_sliced_kernel<1, false, true>, (const void *)admm_peer_sliced_kernel<1, true, true>};
         // default: Chronopoulos-Gear arrangement of the sliced kernel (one fused reduction per CG iteration);
         // QPB200_PEER_CG=0 selects the reference recurrence (three reductions per iteration) for A/B runs
         const char *ecg = getenv("QPB200_PEER_CG");
-        const bool cgv = sliced && !(ecg && atoi(ecg) == 0);
-        const void *fn = cgv ? fns_cg[s.loader][s.use_pre ? 1 : 0]
-                             : (sliced ? fns_sliced[s.loader][s.use_pre ? 1 : 0] : fns[s.loader][s.use_pre ? 1 : 0]);
+        const bool cgv = !(ecg && atoi(ecg) == 0);
+        const void *fn = cgv ? fns_cg[s.use_pre ? 1 : 0] : fns_sliced[s.use_pre ? 1 : 0];
         QPB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(s.grid), dim3(kThreads), args, sizeof(SpmvSmem), s.stream));
     }
     QPB_CUDA(cudaEventRecord(s.ev1, s.stream));

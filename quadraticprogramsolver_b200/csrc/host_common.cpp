@@ -256,15 +256,22 @@ void csc_as_csr_of_transpose(int64_t nrows, int64_t ncols, const int64_t *colptr
     }, 1 << 16);
 }
 
+// Lanes per row of the row-sum step.  One lane per row costs the fewest instructions (no shuffles, every lane of a
+// warp runs the phase epilogue) but chains `avg` dependent shared-memory adds; lpr ~ avg / 8 keeps the chain at 8-16
+// adds (two accumulators) while a 1016-nnz tile still fills at most one round of the 256 threads.
 int choose_lpr(const HostCsr &M) {
+    static const int forced = [] {
+        const char *e = getenv("QPB200_LPR");   // A/B experiments only
+        return e ? atoi(e) : 0;
+    }();
+    if (forced == 1 || forced == 2 || forced == 4 || forced == 8 || forced == 16 || forced == 32) return forced;
     const double avg = M.rows > 0 ? (double)M.nnz() / (double)M.rows : 0.0;
     int lpr = 1;
-    while (lpr < 32 && avg > 6.0 * lpr) lpr *= 2;
+    while (lpr < 32 && avg >= 16.0 * lpr) lpr *= 2;
     return lpr;
 }
 
-void build_tiles(const HostCsr &M, int tile_nnz, HostTiles &out) {
-    const int max_rows = 4096;   // bound on rows per tile (runs of empty rows)
+void build_tiles(const HostCsr &M, int tile_nnz, int max_rows, HostTiles &out) {
     out.tiles.clear();
     int r = 0;
     while (r < M.rows) {

@@ -134,7 +134,8 @@ void csc_as_csr_of_transpose(int64_t nrows, int64_t ncols, const int64_t *colptr
 // Validate a CSC triplet: monotone colptr, indices in range.  Returns 0 or an error code (message set).
 int validate_csc(const char *name, int64_t nrows, int64_t ncols, const int64_t *colptr, const int64_t *rowval,
                  const double *nzval, int64_t base);
-void build_tiles(const HostCsr &M, int tile_nnz, HostTiles &out);
+// tiles of <= tile_nnz non-zeros and <= max_rows rows (spmv_core.cuh: kTileFill, kTileRows)
+void build_tiles(const HostCsr &M, int tile_nnz, int max_rows, HostTiles &out);
 void assign_tiles(HostTiles &t, int grid);
 int choose_lpr(const HostCsr &M);
 

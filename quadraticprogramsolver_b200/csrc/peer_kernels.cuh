@@ -206,243 +206,6 @@ __device__ __forceinline__ void peer_allmax4(const GridSync &gs, SyncState &st, 
     }
 }
 
-template <int TMA, bool PRE>
-__global__ void __launch_bounds__(kThreads, kMinCtas) admm_peer_kernel(SparseProblemDev p, PeerDev pd) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    SpmvSmem &sm = *reinterpret_cast<SpmvSmem *>(smem_raw);
-    PipeState ps;
-    spmv_smem_init(sm, ps);
-    SyncState st;
-    st.epoch = 0;
-    XState xs;
-    xs.xepoch = 0;
-
-    const int n = p.n, m = p.m;
-    const int gtid = blockIdx.x * kThreads + threadIdx.x;
-    const int gstride = gridDim.x * kThreads;
-    double *const x = p.XY, *const y = p.XY + n;
-    double *const xt = p.XG, *const g = p.XG + n;
-    double *const u = p.UT, *const t = p.UT + n;
-    double *const zpv = PRE ? p.zp : p.r;
-    double *const wpart = pd.region[pd.rank] + pd.off_wpart;
-    const double *const wred = pd.region[pd.rank] + pd.off_wred;
-    double *const w2part = pd.region[pd.rank] + pd.off_w2part;
-    const double *const w2red = pd.region[pd.rank] + pd.off_w2red;
-
-    double rho = p.s.rho, rho1 = 1.0 / rho;
-    const double alpha = p.s.alpha, alpha1 = 1.0 - alpha;
-    const double sigma = p.s.sigma;
-    const double eps_admm = fmin(p.s.eps_abs, p.s.eps_rel) * 1e-2;
-    double rhorho = rho;
-    int conv_flag = 1;
-    long long rho_updates = 0, pcg_total = 0, pcg_maxed = 0, n_h = 0, n_a = 0;
-    double res_prim = nan(""), res_dual = nan("");
-    bool dinv_ready = false;
-
-    auto spmv_A_t = [&]() {      // t = rho * A_r u
-        auto epi = [&](int i, double s0, double) { t[i] = rho * s0; };
-        spmv_tiles<TMA, false>(p.A, u, sm, ps, epi);
-        ++n_a;
-    };
-    auto spmv_H_partial = [&](const double *pair) {   // wpart = H_r * pair
-        auto epi = [&](int j, double s0, double) { wpart[j] = s0; };
-        spmv_tiles<TMA, false>(p.H, pair, sm, ps, epi);
-        ++n_h;
-    };
-
-    // optional phase timers (ns, block 0 / thread 0 only): 0 A pass, 1 H pass, 2 all-reduce, 3 c + u.c, 4 x~/r update, 5 u update
-    unsigned long long t_last = gtimer();
-    auto tick = [&](int slot) {
-        if (pd.dbg && blockIdx.x == 0 && threadIdx.x == 0) {
-            const unsigned long long now = gtimer();
-            pd.dbg[slot] += now - t_last;
-            t_last = now;
-        }
-    };
-
-    if (pd.dbg) {
-        // barrier cost in isolation (QPB200_TIMING only): 200 plain grid barriers, 200 system barriers of each kind
-        grid_barrier(p.gs, st);
-        tick(15);
-        for (int i = 0; i < 200; ++i) grid_barrier(p.gs, st);
-        tick(8);
-        for (int i = 0; i < 200; ++i) sys_barrier<false>(p.gs, st, pd, xs);
-        tick(9);
-        for (int i = 0; i < 200; ++i) sys_barrier<true>(p.gs, st, pd, xs);
-        tick(10);
-        double dummy[1] = {1.0};
-        for (int i = 0; i < 200; ++i) grid_barrier_reduce<1, false>(p.gs, st, dummy, sm.red, sm.bcast);
-        tick(11);
-    }
-
-    long long ii = 0;
-    for (ii = 1; ii <= p.s.max_iter; ++ii) {
-        bool changed = false;
-        if (p.s.adaptive_rho && ((rhorho * p.s.rho_factor < rho) || (rhorho > p.s.rho_factor * rho))) {
-            rho = rhorho;
-            rho1 = 1.0 / rho;
-            changed = true;
-            ++rho_updates;
-        }
-        if (changed || !dinv_ready) {
-            if (PRE)
-                for (int j = gtid; j < n; j += gstride) p.dinv[j] = 1.0 / (p.dP[j] + sigma + rho * p.dAA[j]);
-            if (changed)
-                for (int i = gtid; i < m; i += gstride) g[i] = rho * (p.zt[i] - p.z[i]) + y[i];
-            dinv_ready = true;
-            grid_barrier(p.gs, st);
-        }
-        // ---- r0 = sigma (x - x~) - q - sum_r H_r [x~ ; g_r]
-        spmv_H_partial(p.XG);
-        peer_allreduce(p.gs, st, pd, xs, pd.off_wpart, pd.off_wred, n);
-        double acc[2] = {0.0, 0.0};
-        for (int j = gtid; j < n; j += gstride) {
-            const double rj = sigma * (x[j] - xt[j]) - p.q[j] - wred[j];
-            p.r[j] = rj;
-            const double zj = PRE ? p.dinv[j] * rj : rj;
-            if (PRE) p.zp[j] = zj;
-            u[j] = zj;
-            acc[0] += rj * rj;
-            acc[1] += rj * zj;
-        }
-        grid_barrier_reduce<2, false>(p.gs, st, acc, sm.red, sm.bcast);
-        double residual = sqrt(acc[0]);
-        double rz = acc[1];
-        const double tol = fmax(p.s.pcg_rel_eps * residual, p.s.pcg_eps);
-        long long k = 0;
-        while (k < p.s.pcg_max_iter && !(residual <= tol)) {
-            tick(6);
-            spmv_A_t();
-            grid_barrier(p.gs, st);
-            tick(0);
-            spmv_H_partial(p.UT);
-            tick(1);
-            peer_allreduce(p.gs, st, pd, xs, pd.off_wpart, pd.off_wred, n);
-            tick(2);
-            double uc[1] = {0.0};
-            for (int j = gtid; j < n; j += gstride) {
-                const double uj = u[j];
-                const double cj = wred[j] + sigma * uj;
-                p.c[j] = cj;
-                uc[0] += uj * cj;
-            }
-            grid_barrier_reduce<1, false>(p.gs, st, uc, sm.red, sm.bcast);
-            tick(3);
-            if (!(uc[0] > 0.0)) break;
-            const double a_cg = rz / uc[0];
-            double acc2[2] = {0.0, 0.0};
-            for (int j = gtid; j < n; j += gstride) {
-                xt[j] += a_cg * u[j];
-                const double rj = p.r[j] - a_cg * p.c[j];
-                p.r[j] = rj;
-                const double zj = PRE ? p.dinv[j] * rj : rj;
-                if (PRE) p.zp[j] = zj;
-                acc2[0] += rj * rj;
-                acc2[1] += rj * zj;
-            }
-            grid_barrier_reduce<2, false>(p.gs, st, acc2, sm.red, sm.bcast);
-            residual = sqrt(acc2[0]);
-            const double rz_new = acc2[1];
-            ++k;
-            tick(4);
-            if (k < p.s.pcg_max_iter && !(residual <= tol)) {
-                const double beta = rz_new / rz;
-                for (int j = gtid; j < n; j += gstride) u[j] = zpv[j] + beta * u[j];
-                grid_barrier(p.gs, st);
-            }
-            rz = rz_new;
-            tick(5);
-        }
-        pcg_total += k;
-        if (k >= p.s.pcg_max_iter && !(residual <= tol)) ++pcg_maxed;
-
-        // ---- z~ = A_r x~ with relaxation / clip / dual update on the local rows; x update (replicated)
-        const bool do_check = (ii % p.s.check_every) == 0;
-        double nrm[4] = {0.0, 0.0, 0.0, 0.0};     // dx, dz, |Ax - z|, max(|Ax|, |z|)
-        {
-            auto epi = [&](int i, double s0, double) {
-                const double zt_i = s0;
-                const double z_old = p.z[i], y_old = y[i];
-                const double zr = alpha * zt_i + alpha1 * z_old;
-                const double z_new = clamp_julia(zr + rho1 * y_old, p.l[i], p.u[i]);
-                const double y_new = y_old + rho * (zr - z_new);
-                p.z[i] = z_new;
-                y[i] = y_new;
-                p.zt[i] = zt_i;
-                g[i] = rho * (zt_i - z_new) + y_new;
-                nrm[1] = nanmax(nrm[1], fabs(z_new - z_old));
-            };
-            spmv_tiles<TMA, false>(p.A, xt, sm, ps, epi);
-            ++n_a;
-        }
-        for (int j = gtid; j < n; j += gstride) {
-            const double x_old = x[j];
-            const double x_new = alpha * xt[j] + alpha1 * x_old;
-            x[j] = x_new;
-            nrm[0] = nanmax(nrm[0], fabs(x_new - x_old));
-        }
-        grid_barrier(p.gs, st);
-        if (do_check) {
-            {
-                auto epi = [&](int i, double s0, double) {
-                    const double zi = p.z[i];
-                    nrm[2] = nanmax(nrm[2], fabs(s0 - zi));
-                    nrm[3] = nanmax(nrm[3], fabs(s0));
-                    nrm[3] = nanmax(nrm[3], fabs(zi));
-                };
-                spmv_tiles<TMA, false>(p.A, x, sm, ps, epi);
-                ++n_a;
-            }
-            {
-                auto epi = [&](int j, double s0, double s1) {
-                    w2part[j] = s0;
-                    w2part[n + j] = s1;
-                };
-                spmv_tiles<TMA, true>(p.H, p.XY, sm, ps, epi);
-                ++n_h;
-            }
-            grid_barrier_reduce<4, true>(p.gs, st, nrm, sm.red, sm.bcast);   // local maxima (identical in all CTAs)
-            peer_allmax4(p.gs, st, pd, xs, nrm);
-            peer_allreduce(p.gs, st, pd, xs, pd.off_w2part, pd.off_w2red, 2 * n);
-            double nd[2] = {0.0, 0.0};
-            for (int j = gtid; j < n; j += gstride) {
-                const double px = w2red[j], aty = w2red[n + j];
-                nd[0] = nanmax(nd[0], fabs(px + p.q[j] + aty));
-                nd[1] = nanmax(nd[1], fabs(px));
-                nd[1] = nanmax(nd[1], fabs(aty));
-            }
-            grid_barrier_reduce<2, true>(p.gs, st, nd, sm.red, sm.bcast);
-            const double dx = nrm[0], dz = nrm[1];
-            res_prim = nrm[2];
-            res_dual = nd[0];
-            const double max_prim = nrm[3];
-            const double max_dual = nanmax(nd[1], p.normQ);
-            if (p.s.adaptive_rho) {
-                const double num = res_prim * max_dual, den = res_dual * max_prim;
-                rhorho = clamp_julia(rho * sqrt(num / den), 1e-3, 1e6);
-            }
-            if ((res_prim < p.s.eps_abs + p.s.eps_rel * max_prim) && (res_dual < p.s.eps_abs + p.s.eps_rel * max_dual)) conv_flag = 3;
-            if ((dx <= eps_admm) && (dz <= eps_admm)) conv_flag = 2;
-            if (conv_flag != 1) break;
-        }
-    }
-    if (ii > p.s.max_iter) ii = p.s.max_iter;
-
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        AdmmInfoDev &o = *pd.info;
-        o.conv_flag = conv_flag;
-        o.iterations = ii;
-        o.rho_final = rho;
-        o.res_prim = res_prim;
-        o.res_dual = res_dual;
-        o.rho_updates = rho_updates;
-        o.pcg_iters_total = pcg_total;
-        o.pcg_maxed = pcg_maxed;
-        o.n_h_passes = n_h;
-        o.n_a_passes = n_a;
-    }
-}
-
 // =====================================================================================================
 // Sliced variant: the CG vectors are NOT replicated.  Rank r owns slice S_r = [n r / R, n (r+1) / R) of
 // x~, r, z, c and is the only one to update it; u (gathered by A_r and H_r) and x~ (gathered once per ADMM

@@ -41,10 +41,11 @@ static int upload_matrix(DeviceArena &ar, const HostCsr &M, CsrTiled &d, cudaStr
     int *rowptr = nullptr, *rowmid = nullptr, *col = nullptr;
     double *val = nullptr;
     const size_t nnz = (size_t)M.nnz();
-    QPB_CUDA(ar.alloc(&rowptr, M.ptr.size()));
+    QPB_CUDA(ar.alloc(&rowptr, M.ptr.size() + 16));   // the row pointers of a tile are staged in whole 16-byte groups too
     QPB_CUDA(ar.alloc(&col, nnz + 16));
     QPB_CUDA(ar.alloc(&val, nnz + 16));
     QPB_CUDA(cudaMemcpyAsync(rowptr, M.ptr.data(), M.ptr.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    QPB_CUDA(cudaMemsetAsync(rowptr + M.ptr.size(), 0, 16 * sizeof(int), st));
     if (nnz) {
         QPB_CUDA(cudaMemcpyAsync(col, M.idx.data(), nnz * sizeof(int), cudaMemcpyHostToDevice, st));
         QPB_CUDA(cudaMemcpyAsync(val, M.val.data(), nnz * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -87,11 +88,27 @@ struct StreamSyncGuard {   // pending async uploads must drain before the host s
 };
 }  // namespace
 
-static int prep_kernel(const void *kernel, int *blocks_per_sm) {
+// Shared-memory opt-in plus an explicit L1 / shared-memory split: kMinCtas CTAs of the tile engine and not a byte
+// more.  Left to itself the driver sizes the carve-out for as many CTAs as the registers allow -- a 48-register kernel
+// then gets 5 x 41 KB of shared memory and 28 KB of L1, and the x-gathers collapse (stand-alone H pass on cfg5:
+// 0.19 ms -> 0.34 ms, profiles/r2c_spmv_friendly.jsonl).
+int prep_tile_kernel(const void *kernel, int *blocks_per_sm) {
     QPB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpmvSmem)));
+    int dev = 0, max_sm_smem = 0;
+    QPB_CUDA(cudaGetDevice(&dev));
+    QPB_CUDA(cudaDeviceGetAttribute(&max_sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+    const int need = kMinCtas * ((int)sizeof(SpmvSmem) + 1024 + 256);   // + driver-reserved KB + static shared memory
+    static const int kConfigsKiB[] = {0, 8, 16, 32, 64, 100, 132, 164, 196, 228};
+    int cfg = max_sm_smem;
+    for (int c : kConfigsKiB)
+        if (c * 1024 >= need) { cfg = std::min(cfg, c * 1024); break; }
+    int pct = (int)(100.0 * cfg / max_sm_smem);   // rounded down: the driver picks the smallest split >= the request
+    if (const char *e = getenv("QPB200_CARVEOUT")) pct = atoi(e);   // A/B experiments only
+    QPB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     QPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kernel, kThreads, sizeof(SpmvSmem)));
     return QPB200_OK;
 }
+static int prep_kernel(const void *kernel, int *blocks_per_sm) { return prep_tile_kernel(kernel, blocks_per_sm); }
 
 int SparseSolver::settings_to_dev(const qpb200_settings &s) {
     if (!(s.rho > 0.0) || !(s.sigma >= 0.0) || s.max_iter < 0 || s.check_every <= 0 || s.pcg_max_iter < 0)
@@ -165,13 +182,12 @@ int SparseSolver::init(int64_t n64, int64_t m64, const int64_t *Pp, const int64_
         if (cacheable && cached_per_sm[device] > 0) {
             per_sm = cached_per_sm[device];
         } else {
-            for (const void *fn : {(const void *)admm_kernel<0, false>, (const void *)admm_kernel<0, true>, (const void *)admm_kernel<1, false>,
-                                   (const void *)admm_kernel<1, true>, (const void *)admm_kernel<2, false>, (const void *)admm_kernel<2, true>}) {
+            for (const void *fn : {(const void *)admm_kernel<1, false, false>, (const void *)admm_kernel<1, true, false>,
+                                   (const void *)admm_kernel<1, false, true>, (const void *)admm_kernel<1, true, true>}) {
                 if ((rc = prep_kernel(fn, &tmp))) return rc;
                 per_sm = std::min(per_sm, tmp);
             }
-            for (const void *fn : {(const void *)spmv_kernel<0, false>, (const void *)spmv_kernel<0, true>, (const void *)spmv_kernel<1, false>,
-                                   (const void *)spmv_kernel<1, true>, (const void *)spmv_kernel<2, false>, (const void *)spmv_kernel<2, true>})
+            for (const void *fn : {(const void *)spmv_kernel<1, false>, (const void *)spmv_kernel<1, true>})
                 if ((rc = prep_kernel(fn, &tmp))) return rc;
             if (cacheable) cached_per_sm[device] = per_sm;
         }
@@ -207,7 +223,7 @@ int SparseSolver::init(int64_t n64, int64_t m64, const int64_t *Pp, const int64_
         assemble_h_direct(n, m, Pp, Pi, Pv, Ap, Ai, Av, base, H, dP, dAA);
         lap("assemble_H");
         if ((rc = upload_matrix(arena, H, prob.H, stream))) return rc;   // copies while A is being transposed
-        build_tiles(H, kTileNnz, TH);
+        build_tiles(H, kTileFill, kTileRows, TH);
         csc_to_csr(m, n, Ap, Ai, Av, base, A);
         lap("transpose_A");
     } else {
@@ -258,10 +274,10 @@ int SparseSolver::init(int64_t n64, int64_t m64, const int64_t *Pp, const int64_
         }, 4096);
         lap("assemble_H");
         if ((rc = upload_matrix(arena, H, prob.H, stream))) return rc;
-        build_tiles(H, kTileNnz, TH);
+        build_tiles(H, kTileFill, kTileRows, TH);
     }
     if ((rc = upload_matrix(arena, A, prob.A, stream))) return rc;
-    build_tiles(A, kTileNnz, TA);
+    build_tiles(A, kTileFill, kTileRows, TA);
     prob.normQ = nq_unscaled;
 
     int64_t want = std::max<int64_t>((int64_t)std::max(TH.tiles.size(), TA.tiles.size()),
@@ -317,6 +333,7 @@ int SparseSolver::init(int64_t n64, int64_t m64, const int64_t *Pp, const int64_
     QPB_CUDA(arena.alloc(&prob.c, (size_t)n + 8, true));
     QPB_CUDA(arena.alloc(&prob.zp, (size_t)n + 8, true));
     QPB_CUDA(arena.alloc(&prob.dinv, (size_t)n + 8, true));
+    QPB_CUDA(arena.alloc(&prob.wv, (size_t)n + 8, true));
     QPB_CUDA(arena.alloc(&prob.info, 1, true));
     QPB_CUDA(arena.alloc(&sync_words, 64, true));   // count @0, flag @32 (separate 128-B lines)
     prob.gs.count = sync_words;
@@ -367,12 +384,16 @@ int SparseSolver::reset_state(const double *x0_host) {
     return QPB200_OK;
 }
 
+bool SparseSolver::one_reduction() const {
+    const int r = settings.reserved_i[QPB200_RSV_CG_RECURRENCE];
+    return r == 2 || (r == 0 && nnzP + 2 * nnzA <= (int64_t)16 << 20);
+}
+
 int SparseSolver::launch_admm() {
     void *args[] = {(void *)&prob};
-    const void *fns[3][2] = {{(const void *)admm_kernel<0, false>, (const void *)admm_kernel<0, true>},
-                             {(const void *)admm_kernel<1, false>, (const void *)admm_kernel<1, true>},
-                             {(const void *)admm_kernel<2, false>, (const void *)admm_kernel<2, true>}};
-    const void *fn = fns[loader][use_pre ? 1 : 0];
+    const void *fns[2][2] = {{(const void *)admm_kernel<1, false, true>, (const void *)admm_kernel<1, true, true>},
+                             {(const void *)admm_kernel<1, false, false>, (const void *)admm_kernel<1, true, false>}};
+    const void *fn = fns[one_reduction() ? 0 : 1][use_pre ? 1 : 0];
     QPB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, sizeof(SpmvSmem), stream));
     return QPB200_OK;
 }
@@ -466,16 +487,17 @@ int64_t SparseSolver::solve_bytes() const {
     // algorithmic bytes moved by the last solve: matrix passes + the element-wise vector passes
     const AdmmInfoDev &i = last_info;
     const int64_t bH = spmv_bytes(4), bA = spmv_bytes(1);
-    const int64_t pcg_vec = 8LL * 11 * n;   // S4: x~,u,r,c,(dinv) reads + x~,r,(zp) writes; S1: zp,u reads + u write
+    // standard recurrence: S4 x~,u,r,c,(dinv) reads + x~,r,(zp) writes; S1 zp,u reads + u write = 11 n-vectors;
+    // one-reduction arrangement: z,w,p,s,x~,r,(dinv) reads + p,s,x~,r,z writes = 12 (12 n-vector passes)
+    const int64_t pcg_vec = 8LL * (one_reduction() ? 12 : 11) * n;
     const int64_t upd_vec = 8LL * (3 * (int64_t)n + 8 * (int64_t)m);
     return i.n_h_passes * bH + i.n_a_passes * bA + i.pcg_iters_total * pcg_vec + i.iterations * upd_vec;
 }
 
 template <bool SPLIT>
 static void launch_spmv(int loader, const CsrTiled &M, int grid, const double *x, double *y0, double *y1, cudaStream_t st) {
-    if (loader == 2) spmv_kernel<2, SPLIT><<<grid, kThreads, sizeof(SpmvSmem), st>>>(M, x, y0, y1);
-    else if (loader == 1) spmv_kernel<1, SPLIT><<<grid, kThreads, sizeof(SpmvSmem), st>>>(M, x, y0, y1);
-    else spmv_kernel<0, SPLIT><<<grid, kThreads, sizeof(SpmvSmem), st>>>(M, x, y0, y1);
+    (void)loader;   // one tile loader since round 2 (TMA bulk copies); settings.spmv_loader is accepted and ignored
+    spmv_kernel<1, SPLIT><<<grid, kThreads, sizeof(SpmvSmem), st>>>(M, x, y0, y1);
 }
 
 int SparseSolver::apply_device(int which, const double *x, double *y) {

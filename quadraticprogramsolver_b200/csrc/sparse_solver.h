@@ -33,6 +33,7 @@ struct SparseSolver {
     int settings_to_dev(const qpb200_settings &s);
     int reset_state(const double *x0_host);
     int launch_admm();
+    bool one_reduction() const;   // which arrangement of the (P)CG recurrence admm_kernel runs (QPB200_RSV_CG_RECURRENCE)
     int solve(double *x_inout, double *z_out, double *y_out, qpb200_info *info);
     int apply(int which, const double *x_host, double *y_host);
     int apply_device(int which, const double *x, double *y);
@@ -42,6 +43,8 @@ struct SparseSolver {
     int64_t spmv_bytes(int which) const;
     int64_t solve_bytes() const;
 };
+
+int prep_tile_kernel(const void *kernel, int *blocks_per_sm);   // shared-memory opt-in + L1 split of a tile-engine kernel
 
 struct DistContext;                       // dist_solver.cu
 void dist_destroy(DistContext *d);

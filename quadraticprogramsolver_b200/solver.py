@@ -59,7 +59,10 @@ _DEFAULTS = dict(numIterations=5000, epsAbs=1e-6, epsRel=1e-6, rho=1.0, sigma=1e
                  epsPcg=1e-6, numItrPcg=1000, relPcg=-1.0, linSolver="pcg", precond="jacobi", device=-1,
                  spmvLoader="auto",
                  # Ruiz equilibration iterations (0 = off = the reference's behaviour)
-                 numItrScaling=0)
+                 numItrScaling=0,
+                 # arrangement of the (P)CG recurrence: "standard" (IterativeSolvers' CGIterable / PCGIterable statement
+                 # order), "one_reduction" (three grid barriers per CG iteration), "auto" (by problem size)
+                 cgRecurrence="auto")
 
 
 def make_settings(**kw) -> Settings:
@@ -86,6 +89,7 @@ def make_settings(**kw) -> Settings:
     s.device = int(opts["device"])
     s.spmv_loader = {"auto": 0, "ldg": 1, "tma": 2, "tma_pipe": 3}[str(opts["spmvLoader"])]
     s.reserved_i[2] = int(opts["numItrScaling"])          # QPB200_RSV_SCALING_ITERS
+    s.reserved_i[4] = {"auto": 0, "standard": 1, "one_reduction": 2}[str(opts["cgRecurrence"])]   # QPB200_RSV_CG_RECURRENCE
     return s
 
 
@@ -146,6 +150,7 @@ class QPB200Solver:
         Pp, Pi, Pv = _csc_arrays(mP)
         Ap, Ai, Av = _csc_arrays(mA)
         rho_scale = _pop_rho_scale(kw, vL, vU)
+        self._kw = {_ALIASES.get(k, k): v for k, v in kw.items()}
         self.settings = make_settings(**kw)
         self._h = C.c_void_p()
         _lib.check(lib.qpb200_create(C.byref(self._h), self.n, self.m, _p64(Pp), _p64(Pi), _pd(Pv), _p64(Ap), _p64(Ai),
@@ -183,9 +188,20 @@ class QPB200Solver:
         arr = [None if v is None else np.ascontiguousarray(v, dtype=np.float64) for v in (vQ, vL, vU)]
         _lib.check(_lib.load().qpb200_update_vectors(self._h, *[None if a is None else _pd(a) for a in arr]))
 
+    #: keyword arguments that are fixed when the handle is created
+    _IMMUTABLE = ("numItrScaling", "device", "linSolver")
+
     def update_settings(self, **kw):
-        self.settings = make_settings(**kw)
-        _lib.check(_lib.load().qpb200_update_settings(self._h, C.byref(self.settings)))
+        """Change keyword arguments of the handle; the ones not named keep the values given at creation."""
+        kw = {_ALIASES.get(k, k): v for k, v in kw.items()}
+        for k in self._IMMUTABLE:
+            if k in kw and kw[k] != self._kw.get(k, _DEFAULTS[k]):
+                raise ValueError(f"{k} cannot change after the handle is created")
+        merged = dict(self._kw)
+        merged.update(kw)
+        settings = make_settings(**merged)
+        _lib.check(_lib.load().qpb200_update_settings(self._h, C.byref(settings)))
+        self._kw, self.settings = merged, settings
 
     def apply(self, which: int, x):
         """Operators of the path: 0: P x, 1: A x, 2: A' x, 3: (P + sigma I + rho A'A) x."""

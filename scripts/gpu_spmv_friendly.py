@@ -55,7 +55,8 @@ for name in workloads:
     for loader in loaders:
         out = {"tag": tag, "workload": name, "loader": loader, "n": P.shape[0], "m": A.shape[0], "nnzP": int(P.nnz),
                "nnzA": int(A.nnz)}
-        with S.QPB200Solver(P, q, A, l, u, spmvLoader=loader, numIterations=25) as s:
+        out["recur"] = os.environ.get("QPB_RECUR", "auto")
+        with S.QPB200Solver(P, q, A, l, u, spmvLoader=loader, numIterations=25, cgRecurrence=out["recur"]) as s:
             for which, nm in ((1, "A"), (4, "H")):
                 ms = min(s.time_apply(which, reps=20, flush_l2=True) for _ in range(2))
                 gb = s.apply_bytes(which) / 1e9
