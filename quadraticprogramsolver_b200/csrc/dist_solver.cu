@@ -508,6 +508,10 @@ int qpb200_dist_create(qpb200_handle **out, int32_t rank, int32_t nranks, const 
 
 int qpb200_dist_solve(qpb200_handle *h, double *x_inout, double *z_out, double *y_out, qpb200_info *info) {
     if (!h || !h->dist) return fail(QPB200_ERR_ARG, "qpb200_dist_solve: not a distributed handle");
+    // (a start point that differs between the ranks, or is non-finite on some only, would desynchronise the collective:
+    //  x_inout is documented as replicated, so every rank takes the same branch here)
+    if (x_inout && !all_finite(x_inout, (size_t)h->solver.n))
+        return fail(QPB200_ERR_NONFINITE, "qpb200_dist_solve: the start point holds NaN or Inf");
     if (h->dist->peer_ok) return peer_solve(h->solver, *h->dist, x_inout, z_out, y_out, info);
     return dist_solve(h->solver, *h->dist, x_inout, z_out, y_out, info);
 }

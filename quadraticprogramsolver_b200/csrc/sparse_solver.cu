@@ -115,6 +115,9 @@ int SparseSolver::settings_to_dev(const qpb200_settings &s) {
         return fail(QPB200_ERR_ARG, "settings: need rho > 0, sigma >= 0, max_iter >= 0, check_every > 0, pcg_max_iter >= 0");
     if (s.lin_solver != QPB200_LINSOLVE_PCG)
         return fail(QPB200_ERR_ARG, "qpb200_create: the sparse path implements lin_solver = QPB200_LINSOLVE_PCG only");
+    if (created && (s.device != settings.device || s.reserved_i[QPB200_RSV_SCALING_ITERS] != settings.reserved_i[QPB200_RSV_SCALING_ITERS] ||
+                    s.reserved_i[QPB200_RSV_DIST_MODE] != settings.reserved_i[QPB200_RSV_DIST_MODE]))
+        return fail(QPB200_ERR_ARG, "qpb200_update_settings: device, scaling iterations and the multi-GPU mode are fixed at create");
     settings = s;
     AdmmSettingsDev &d = prob.s;
     d.max_iter = s.max_iter;
@@ -343,6 +346,9 @@ int SparseSolver::init(int64_t n64, int64_t m64, const int64_t *Pp, const int64_
     QPB_CUDA(arena.alloc(&scratch, std::max(nm, (size_t)2 * n) + 8, true));
     QPB_CUDA(cudaDeviceSynchronize());
     lap("upload+alloc");
+    h_l.assign(l, l + m);   // host copies of the (scaled) bounds: qpb200_update_vectors re-checks l <= u against them
+    h_u.assign(u, u + m);
+    created = true;
     setup_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (getenv("QPB200_TIMING")) fprintf(stderr, "[qpb200_create] total %.1f ms:%s\n", setup_ms, laps.c_str());
     return QPB200_OK;
@@ -400,6 +406,7 @@ int SparseSolver::launch_admm() {
 
 int SparseSolver::solve(double *x_inout, double *z_out, double *y_out, qpb200_info *info) {
     if (!x_inout) return fail(QPB200_ERR_ARG, "qpb200_solve: x_inout is NULL");
+    if (!all_finite(x_inout, (size_t)n)) return fail(QPB200_ERR_NONFINITE, "qpb200_solve: the start point holds NaN or Inf");
     const auto wall0 = std::chrono::steady_clock::now();
     QPB_CUDA(cudaSetDevice(device));
     std::vector<double> x0s;
@@ -608,17 +615,25 @@ int SparseSolver::update_vectors(const double *q, const double *l, const double 
         }
         QPB_CUDA(cudaMemcpy(d_q, q, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
     }
-    for (int which = 0; which < 2; ++which) {
-        const double *b = which ? u : l;
-        if (!b || !m) continue;
-        for (int i = 0; i < m; ++i)
-            if (std::isnan(b[i])) return fail(QPB200_ERR_NONFINITE, "bound %d is NaN", i);
-        if (scaled) {
-            tmp.resize((size_t)m);
-            for (int i = 0; i < m; ++i) tmp[(size_t)i] = scaling.E[(size_t)i] * b[i];
-            b = tmp.data();
+    // bounds: validated as a pair against the stored counterpart (create checks l <= u, so must every update)
+    if (m && (l || u)) {
+        std::vector<double> nl(h_l), nu(h_u);
+        for (int which = 0; which < 2; ++which) {
+            const double *b = which ? u : l;
+            if (!b) continue;
+            std::vector<double> &dst = which ? nu : nl;
+            for (int i = 0; i < m; ++i) {
+                if (std::isnan(b[i])) return fail(QPB200_ERR_NONFINITE, "bound %d is NaN", i);
+                dst[(size_t)i] = scaled ? scaling.E[(size_t)i] * b[i] : b[i];
+            }
         }
-        QPB_CUDA(cudaMemcpy(which ? d_u : d_l, b, (size_t)m * sizeof(double), cudaMemcpyHostToDevice));
+        for (int i = 0; i < m; ++i)
+            if (nl[(size_t)i] > nu[(size_t)i])
+                return fail(QPB200_ERR_NONFINITE, "bounds: need l[i] <= u[i] (row %d) after the update", i);
+        if (l) QPB_CUDA(cudaMemcpy(d_l, nl.data(), (size_t)m * sizeof(double), cudaMemcpyHostToDevice));
+        if (u) QPB_CUDA(cudaMemcpy(d_u, nu.data(), (size_t)m * sizeof(double), cudaMemcpyHostToDevice));
+        h_l.swap(nl);
+        h_u.swap(nu);
     }
     return QPB200_OK;
 }

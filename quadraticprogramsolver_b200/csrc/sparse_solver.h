@@ -25,6 +25,8 @@ struct SparseSolver {
     // x = D x_s, z = z_s / E, y = E y_s / c; the kernel tests convergence on the unscaled residuals
     RuizScaling scaling;
     bool scaled = false;
+    bool created = false;                  // settings_to_dev: later calls may not change what create fixed
+    std::vector<double> h_l, h_u;          // the bounds as uploaded (scaled if the problem is), for update_vectors
 
     ~SparseSolver();
     int init(int64_t n, int64_t m, const int64_t *Pp, const int64_t *Pi, const double *Pv, const int64_t *Ap,

@@ -96,10 +96,13 @@ __device__ __forceinline__ void tma_issue_tile(const CsrTiled &M, const int4 td,
 // bank conflicts, measured as 2.3 of 5.1 M store wavefronts per H pass).  All gathers of x are issued before the
 // first use.  x is mutable between phases: plain loads, never ld.global.nc.  Slots past the staged range keep stale
 // data and are not touched: every slot that is multiplied holds a column index of this matrix.
-__device__ __forceinline__ void tile_products(double *val, const int *col, int cnt, const double *x) {
-    constexpr int kPairs = 2 * kSlotGroups;
-    int2 c[kPairs];
+constexpr int kPairs = 2 * kSlotGroups;
+struct Gathered {          // the x values of one tile's slots owned by this thread, in flight or landed
     double xa[kPairs], xb[kPairs];
+};
+
+__device__ __forceinline__ void tile_gather(const int *col, int cnt, const double *x, Gathered &g) {
+    int2 c[kPairs];
 #pragma unroll
     for (int h = 0; h < kPairs; ++h) {
         const int s2 = (h * kThreads + threadIdx.x) * 2;
@@ -108,19 +111,22 @@ __device__ __forceinline__ void tile_products(double *val, const int *col, int c
 #pragma unroll
     for (int h = 0; h < kPairs; ++h) {
         const int s2 = (h * kThreads + threadIdx.x) * 2;
-        xa[h] = xb[h] = 0.0;   // (defined on every path: otherwise the values are loop carried and get spilled)
+        g.xa[h] = g.xb[h] = 0.0;   // (defined on every path: otherwise the values are loop carried and get spilled)
         if (s2 < cnt) {
-            xa[h] = x[static_cast<unsigned>(c[h].x)];
-            xb[h] = x[static_cast<unsigned>(c[h].y)];
+            g.xa[h] = x[static_cast<unsigned>(c[h].x)];
+            g.xb[h] = x[static_cast<unsigned>(c[h].y)];
         }
     }
+}
+
+__device__ __forceinline__ void tile_multiply(double *val, int cnt, const Gathered &g) {
 #pragma unroll
     for (int h = 0; h < kPairs; ++h) {
         const int s2 = (h * kThreads + threadIdx.x) * 2;
         if (s2 < cnt) {
             double2 v = *reinterpret_cast<const double2 *>(val + s2);
-            v.x *= xa[h];
-            v.y *= xb[h];
+            v.x *= g.xa[h];
+            v.y *= g.xb[h];
             *reinterpret_cast<double2 *>(val + s2) = v;
         }
     }
@@ -222,7 +228,9 @@ __device__ __forceinline__ void spmv_tiles(const CsrTiled &M, const double *x, S
         const int4 td = sm.tdq[s];
         const int k0a = td.z & ~3;
         const int cnt = ((td.z + (td.w & kTileNkMask) - k0a) + 3) & ~3;
-        tile_products(sm.val[s], sm.col[s], cnt, x);
+        Gathered g;
+        tile_gather(sm.col[s], cnt, x, g);
+        tile_multiply(sm.val[s], cnt, g);
         fence_proxy_async_smem();   // our generic accesses to the stages (incl. tile i-1's reads) before the refill
         __syncthreads();
         if (threadIdx.x == 0 && i + kAhead < nt) {
@@ -232,6 +240,9 @@ __device__ __forceinline__ void spmv_tiles(const CsrTiled &M, const double *x, S
         tile_row_sums<SPLIT>(M, td, sm.val[s], sm.rp[s] + (td.x & 3), k0a, lsh, sm, epi);
         s = (s + 1 == kStages) ? 0 : s + 1;
     }
+    // (Issuing the gathers of tile i+1 before the row sums of tile i was measured twice, round 1 and round 2
+    //  (profiles/r2e_spmv_variants.jsonl: cfg5 H pass 0.176 -> 0.201 ms): the L2 -> SM return path is already at
+    //  ~90 % of the best rate measured on this GPU, extra loads in flight only block the warps' row sums.)
     __syncthreads();
 }
 

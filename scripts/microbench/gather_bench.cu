@@ -80,5 +80,16 @@ int main(int argc, char **argv) {
         printf("%-28s %8d %10.4f %12.1f %14.3f\n", "ld.global ILP=4", kb, m4, n / m4 / 1e6, n / (m4 * 1e-3) / (sms * (double)p.clockRate * 1e3));
         printf("%-28s %8d %10.4f %12.1f %14.3f\n", "ld.global ILP=8", kb, m8, n / m8 / 1e6, n / (m8 * 1e-3) / (sms * (double)p.clockRate * 1e3));
     }
+    // the same sweep for loads that should not need an L1 line per miss in flight
+    printf("\n%-28s %8s %10s %12s %14s\n", "1024 thr/SM, smem/CTA", "KB", "ms", "Ggather/s", "gathers/clk/SM");
+    for (int kb : {0, 50, 100}) {
+        const int threads = 512, blocks = sms * 2;
+        float a = run<8, 1>(idx, x, out, n, blocks, threads, 10, (size_t)kb * 1024);
+        float b = run<8, 3>(idx, x, out, n, blocks, threads, 10, (size_t)kb * 1024);
+        float c = run<8, 2>(idx, x, out, n, blocks, threads, 10, (size_t)kb * 1024);
+        printf("%-28s %8d %10.4f %12.1f %14.3f\n", "ld.global.cg ILP=8", kb, a, n / a / 1e6, n / (a * 1e-3) / (sms * (double)p.clockRate * 1e3));
+        printf("%-28s %8d %10.4f %12.1f %14.3f\n", "L1::no_allocate ILP=8", kb, b, n / b / 1e6, n / (b * 1e-3) / (sms * (double)p.clockRate * 1e3));
+        printf("%-28s %8d %10.4f %12.1f %14.3f\n", "ld.global.nc ILP=8", kb, c, n / c / 1e6, n / (c * 1e-3) / (sms * (double)p.clockRate * 1e3));
+    }
     return 0;
 }
