@@ -505,3 +505,24 @@ def test_cg_recurrences_agree_with_oracle(lib, recur):
     xc, fc, ic = c_oracle.solve_sparse(P, q, A, l, u, precond=1, **kw)
     _assert_parity(x, flag, info, xc, fc, ic["iterations"])
     assert abs(info["pcg_iters_total"] - ic["cg_iters_total"]) <= max(3, ic["cg_iters_total"] // 200)
+
+
+def test_validation_of_updates_and_start_point(lib):
+    """qpb200_update_vectors re-checks l <= u against the stored counterpart, qpb200_solve rejects a non-finite start
+    point, qpb200_update_settings keeps the creation keywords that are not named and refuses the immutable ones."""
+    S = _solver()
+    P, q, A, l, u = config_cfg1(1234)
+    with S.QPB200Solver(P, q, A, l, u, numIterations=50, adptRho=True, epsPcg=1e-10) as s:
+        with pytest.raises(S.QPB200Error):
+            s.update_vectors(vL=u + 1.0)                     # l > stored u
+        with pytest.raises(S.QPB200Error):
+            s.update_vectors(vU=l - 1.0)                     # u < stored l
+        s.update_vectors(vL=l - 1.0, vU=u + 1.0)            # a consistent pair is accepted
+        x = np.full(P.shape[0], np.nan)
+        with pytest.raises(S.QPB200Error):
+            s.solve(x)
+        s.update_settings(rho=0.1)
+        assert s.settings.max_iter == 50 and s.settings.adaptive_rho == 1 and s.settings.pcg_eps == 1e-10
+        assert s.settings.rho == 0.1
+        with pytest.raises(ValueError):
+            s.update_settings(numItrScaling=5)
