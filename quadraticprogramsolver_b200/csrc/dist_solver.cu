@@ -302,8 +302,10 @@ static int peer_init(SparseSolver &s, DistContext &d) {
     size_t off = 0;
     pd.off_flags = (long long)off; off += 16;
     pd.off_lmax = (long long)off; off += up(4 * (size_t)kMaxPeers);
-    pd.off_wpart = (long long)off; off += up(n);
-    pd.off_wred = (long long)off; off += up(n);
+    for (int q = 0; q <= d.nranks; ++q) pd.sb[q] = (int)((long long)s.n * q / d.nranks);
+    for (int q = d.nranks + 1; q <= kMaxPeers; ++q) pd.sb[q] = s.n;
+    pd.sstride = (long long)up(n / (size_t)d.nranks + 1);
+    pd.off_wrecv = (long long)off; off += (size_t)pd.sstride * (size_t)d.nranks;
     pd.off_w2part = (long long)off; off += up(2 * n);
     pd.off_w2red = (long long)off; off += up(2 * n);
     // sliced variant: per-CTA dot partials of every rank, and the gathered vector pairs [u ; t], [x~ ; g]
@@ -389,12 +391,10 @@ static int peer_init(SparseSolver &s, DistContext &d) {
     s.prob.UT = d.region + off_UT;
     s.prob.XG = d.region + off_XG;
     pd.info = s.prob.info;
-    pd.wslice = d.buf.wbuf;
     pd.dbg = nullptr;
     if (getenv("QPB200_TIMING")) QPB_CUDA(s.arena.alloc(&pd.dbg, 16, true));
     QPB_CUDA(s.arena.alloc(&d.tiny, 2, true));
-    for (const void *fn : {(const void *)admm_peer_sliced_kernel<1, false, false>, (const void *)admm_peer_sliced_kernel<1, true, false>,
-                           (const void *)admm_peer_sliced_kernel<1, false, true>, (const void *)admm_peer_sliced_kernel<1, true, true>}) {
+    for (const void *fn : {(const void *)admm_peer_sliced_kernel<1, false>, (const void *)admm_peer_sliced_kernel<1, true>}) {
         int per_sm = 0;
         if (int prc = prep_tile_kernel(fn, &per_sm)) return prc;
         if (per_sm * s.num_sms < s.grid)
@@ -412,19 +412,13 @@ int peer_solve(SparseSolver &s, DistContext &d, double *x_inout, double *z_out, 
     int rc = s.reset_state(x_inout);
     if (rc) return rc;
     // epoch flags back to zero, then a host-level rendezvous: nobody launches before everybody has reset
-    QPB_CUDA(cudaMemsetAsync(d.region, 0, (size_t)(d.peer.off_wpart) * sizeof(double), s.stream));
+    QPB_CUDA(cudaMemsetAsync(d.region, 0, (size_t)(d.peer.off_wrecv) * sizeof(double), s.stream));
     QPB_NCCL(api->AllReduce(d.tiny, d.tiny, 1, ncclDouble, ncclSum, d.comm, s.stream));
     QPB_CUDA(cudaStreamSynchronize(s.stream));
     QPB_CUDA(cudaEventRecord(s.ev0, s.stream));
     {
         void *args[] = {(void *)&s.prob, (void *)&d.peer};
-        const void *fns_sliced[2] = {(const void *)admm_peer_sliced_kernel<1, false, false>, (const void *)admm_peer_sliced_kernel<1, true, false>};
-        const void *fns_cg[2] = {(const void *)admm_peer_sliced_kernel<1, false, true>, (const void *)admm_peer_sliced_kernel<1, true, true>};
-        // default: Chronopoulos-Gear arrangement of the sliced kernel (one fused reduction per CG iteration);
-        // QPB200_PEER_CG=0 selects the reference recurrence (three reductions per iteration) for A/B runs
-        const char *ecg = getenv("QPB200_PEER_CG");
-        const bool cgv = !(ecg && atoi(ecg) == 0);
-        const void *fn = cgv ? fns_cg[s.use_pre ? 1 : 0] : fns_sliced[s.use_pre ? 1 : 0];
+        const void *fn = s.use_pre ? (const void *)admm_peer_sliced_kernel<1, true> : (const void *)admm_peer_sliced_kernel<1, false>;
         QPB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(s.grid), dim3(kThreads), args, sizeof(SpmvSmem), s.stream));
     }
     QPB_CUDA(cudaEventRecord(s.ev1, s.stream));
@@ -445,10 +439,9 @@ int peer_solve(SparseSolver &s, DistContext &d, double *x_inout, double *z_out, 
         QPB_CUDA(cudaMemcpy(t, d.peer.dbg, sizeof(t), cudaMemcpyDeviceToHost));
         QPB_CUDA(cudaMemset(d.peer.dbg, 0, sizeof(t)));
         const double k = hi.pcg_iters_total > 0 ? 1e-3 / (double)hi.pcg_iters_total : 0.0;
-        fprintf(stderr, "[qpb200 peer rank %d] us per CG iteration: A pass %.1f, H pass %.1f, all-reduce %.1f, c+u.c %.1f, x~/r %.1f, u %.1f, other %.1f (solve %.1f ms, %lld CG its)\n",
-                d.rank, t[0] * k, t[1] * k, t[2] * k, t[3] * k, t[4] * k, t[5] * k, t[6] * k, ms, (long long)hi.pcg_iters_total);
-        fprintf(stderr, "[qpb200 peer rank %d] barrier cost in isolation (us): grid %.2f, system(local writes) %.2f, system(remote writes) %.2f, grid+reduce %.2f\n",
-                d.rank, t[8] / 200e3, t[9] / 200e3, t[10] / 200e3, t[11] / 200e3);
+        fprintf(stderr, "[qpb200 peer rank %d] us per CG iteration: A pass + grid barrier %.1f, H pass with push %.1f, system barrier + z.w sum %.1f, "
+                        "slice update + z push %.1f, system barrier + 3 sums %.1f, loop head %.1f (solve %.1f ms, %lld CG its)\n",
+                d.rank, t[0] * k, t[1] * k, t[2] * k, t[3] * k, t[4] * k, t[5] * k, ms, (long long)hi.pcg_iters_total);
     }
     if (info) {
         std::memset(info, 0, sizeof(*info));

@@ -25,7 +25,9 @@ struct PeerDev {
     int rank, nranks;
     double *region[kMaxPeers];       // peer-visible region of every rank (own entry = local pointer)
     // offsets in doubles inside a region
-    long long off_wpart, off_wred;   // n each
+    long long off_wrecv;             // nranks * sstride: receive buffer of the push-style reduce-scatter
+    long long sstride;               // doubles between the partials of two source ranks (>= longest slice)
+    int sb[kMaxPeers + 1];           // slice bounds: rank q owns [sb[q], sb[q+1]) of the n-vectors
     long long off_w2part, off_w2red; // 2n each
     long long off_lmax;              // nranks * 4
     long long off_flags;             // kMaxPeers unsigned long long
@@ -33,7 +35,6 @@ struct PeerDev {
     int grid_max;
     AdmmInfoDev *info;
     unsigned long long *dbg;         // 16 phase timers in ns (block 0 / thread 0), printed with QPB200_TIMING
-    double *wslice;                  // n doubles (local): w = K z of the Chronopoulos-Gear variant
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
@@ -207,13 +208,24 @@ __device__ __forceinline__ void peer_allmax4(const GridSync &gs, SyncState &st, 
 }
 
 // =====================================================================================================
-// Sliced variant: the CG vectors are NOT replicated.  Rank r owns slice S_r = [n r / R, n (r+1) / R) of
-// x~, r, z, c and is the only one to update it; u (gathered by A_r and H_r) and x~ (gathered once per ADMM
-// iteration) are kept coherent by pushing the owner's slice into every rank's copy (all-gather by remote
-// stores).  The reduce-scatter of H_r [u ; rho A_r u] is fused with c = w + sigma u and the u.c partial sums;
-// dot products are reduced across GPUs by pushing every CTA's partial into every rank's slot table and
-// summing the R x G partials in the same fixed order everywhere after ONE system barrier.
-// Per CG iteration: 1 grid barrier + 4 system barriers, vector traffic 1/R of the replicated variant.
+// The kernel.  The CG vectors are NOT replicated: rank r owns slice S_r = [sb[r], sb[r+1]) of x~, r, p, s and is
+// the only one to update it; z = Pl \ r (the one vector A_r and H_r gather from) and x~ (gathered once per ADMM
+// iteration) are kept coherent by pushing the owner's slice into every rank's copy (all-gather by remote stores).
+//
+// One CG iteration (one-reduction arrangement of the PCG, see admm_kernels.cuh) costs ONE grid barrier and TWO
+// system barriers:
+//   A pass    t = rho A_r z                                   (rows of this rank)          | grid barrier
+//   H pass    w_r = H_r [z ; t]; the epilogue PUSHES row j of w_r straight into the receive buffer of the rank that
+//             owns j (push-style reduce-scatter riding on the pass: the 7/8 n remote stores are on the wire while the
+//             next tiles are computed) and accumulates z . w_r over ALL rows               | system barrier + sum<1>
+//             => delta = z . K z = sum_r z . w_r + sigma z . z is known to everybody without the reduced w
+//   slice     w = sum_q recv[q][j] + sigma z (R LOCAL reads, rank order => deterministic), p = z + beta p,
+//             s = w + beta s, x~ += alpha p, r -= alpha s, z' = Pl \ r pushed into every rank's copy,
+//             gamma' = r . z', |r|^2, z' . z' on the slice                                 | system barrier + sum<3>
+// (round 1: pull-style reduce-scatter -- R dependent remote loads per element, pure NVLink latency -- and three
+//  system barriers per iteration: 59 + 21 of the 122 us of an iteration on 8 GPUs, profiles/r1c_dist8_cg.txt.)
+// Scalars are summed in rank order from per-GPU totals that every rank holds bit-identically, so all ranks branch
+// identically.
 // =====================================================================================================
 template <int NV>
 __device__ __forceinline__ void peer_barrier_sum(const GridSync &gs, SyncState &st, const PeerDev &pd, XState &xs,
@@ -222,12 +234,11 @@ __device__ __forceinline__ void peer_barrier_sum(const GridSync &gs, SyncState &
     sys_barrier_impl<NV>(gs, st, pd, xs, v, sm, parity);
 }
 
-// CGV = true: Chronopoulos-Gear arrangement of the same PCG (one fused reduction per iteration, no all-gather of
-// the search direction): see the loop below.
-template <int TMA, bool PRE, bool CGV>
+template <int TMA, bool PRE>
 __global__ void __launch_bounds__(kThreads, kMinCtas) admm_peer_sliced_kernel(SparseProblemDev p, PeerDev pd) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SpmvSmem &sm = *reinterpret_cast<SpmvSmem *>(smem_raw);
+    __shared__ AdmmCounters ctr;
     PipeState ps;
     spmv_smem_init(sm, ps);
     SyncState st;
@@ -235,37 +246,28 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) admm_peer_sliced_kernel(Sp
     XState xs;
     xs.xepoch = 0;
     unsigned parity = 0;
+    if (threadIdx.x == 0) {
+        ctr.rho_updates = ctr.pcg_total = ctr.pcg_maxed = ctr.n_h = ctr.n_a = 0;
+        ctr.res_prim = ctr.res_dual = nan("");
+    }
+    auto count = [&](long long &c, long long by) { if (threadIdx.x == 0) c += by; };
 
     const int n = p.n, m = p.m, R = pd.nranks;
     const int gtid = blockIdx.x * kThreads + threadIdx.x;
     const int gstride = gridDim.x * kThreads;
-    const int s0 = (int)((long long)n * pd.rank / R), s1 = (int)((long long)n * (pd.rank + 1) / R);   // my slice
+    const int s0 = pd.sb[pd.rank], s1 = pd.sb[pd.rank + 1];   // my slice
     double *const x = p.XY, *const y = p.XY + n;
     double *const xt = p.XG, *const g = p.XG + n;          // p.XG / p.UT live in the peer-visible region
     double *const u = p.UT, *const t = p.UT + n;
-    double *const zpv = PRE ? p.zp : p.r;
-    double *const wpart = pd.region[pd.rank] + pd.off_wpart;
     double *const w2part = pd.region[pd.rank] + pd.off_w2part;
     const double *const w2red = pd.region[pd.rank] + pd.off_w2red;
-    // remote views of u and x~ (same offset in every region)
+    const double *const recv = pd.region[pd.rank] + pd.off_wrecv;   // [R][sstride]: row j of rank q's partial at q sstride + j - s0
+    // remote views of z (= u) and x~: same offset in every region
     const long long off_u = (long long)(p.UT - pd.region[pd.rank]), off_xt = (long long)(p.XG - pd.region[pd.rank]);
-    const double *wsrc[kMaxPeers];
-    double *udst[kMaxPeers], *xtdst[kMaxPeers];
-#pragma unroll
-    for (int q = 0; q < kMaxPeers; ++q) {
-        wsrc[q] = pd.region[q < R ? q : 0] + pd.off_wpart;
-        udst[q] = pd.region[q < R ? q : 0] + off_u;
-        xtdst[q] = pd.region[q < R ? q : 0] + off_xt;
-    }
 
     double rho = p.s.rho, rho1 = 1.0 / rho;
-    const double alpha = p.s.alpha, alpha1 = 1.0 - alpha;
-    const double sigma = p.s.sigma;
-    const double eps_admm = fmin(p.s.eps_abs, p.s.eps_rel) * 1e-2;
     double rhorho = rho;
     int conv_flag = 1;
-    long long rho_updates = 0, pcg_total = 0, pcg_maxed = 0, n_h = 0, n_a = 0;
-    double res_prim = nan(""), res_dual = nan("");
     bool dinv_ready = false;
 
     unsigned long long t_last = gtimer();
@@ -276,22 +278,29 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) admm_peer_sliced_kernel(Sp
             t_last = now;
         }
     };
-    auto spmv_A_t = [&]() {
-        auto epi = [&](int i, double s0_, double) { t[i] = rho * s0_; };
-        spmv_tiles<TMA, false>(p.A, u, sm, ps, epi);
-        ++n_a;
-    };
-    auto spmv_H_partial = [&](const double *pair) {
-        auto epi = [&](int j, double s0_, double) { wpart[j] = s0_; };
+    // H pass with the push-style reduce-scatter in its epilogue; returns this thread's share of sum_j pair[j] * (H_r pair)_j
+    auto spmv_H_push = [&](const double *pair, double &zw) {
+        auto epi = [&](int j, double sum, double) {
+            int q = 0;
+#pragma unroll
+            for (int b = 1; b < kMaxPeers; ++b) q += (b < R && j >= pd.sb[b]) ? 1 : 0;
+            pd.region[q][pd.off_wrecv + (long long)pd.rank * pd.sstride + (j - pd.sb[q])] = sum;
+            zw += pair[j] * sum;
+        };
         spmv_tiles<TMA, false>(p.H, pair, sm, ps, epi);
-        ++n_h;
+        count(ctr.n_h, 1);
     };
-    auto reduced_w = [&](int j) {          // sum of all ranks' partials in rank order (deterministic)
+    auto reduced_w = [&](int j) {          // sum of all ranks' partials in rank order (deterministic); local reads
         double w = 0.0;
 #pragma unroll
         for (int q = 0; q < kMaxPeers; ++q)
-            if (q < R) w += __ldcg(wsrc[q] + j);
+            if (q < R) w += __ldcg(recv + (long long)q * pd.sstride + (j - s0));
         return w;
+    };
+    auto push_all = [&](long long off, int j, double v) {   // element j of a replicated vector, into every rank's copy
+#pragma unroll
+        for (int q = 0; q < kMaxPeers; ++q)
+            if (q < R) pd.region[q][off + j] = v;
     };
 
     long long ii = 0;
@@ -301,165 +310,107 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) admm_peer_sliced_kernel(Sp
             rho = rhorho;
             rho1 = 1.0 / rho;
             changed = true;
-            ++rho_updates;
+            count(ctr.rho_updates, 1);
         }
         if (changed || !dinv_ready) {
             if (PRE)
-                for (int j = s0 + gtid; j < s1; j += gstride) p.dinv[j] = 1.0 / (p.dP[j] + sigma + rho * p.dAA[j]);
+                for (int j = s0 + gtid; j < s1; j += gstride) p.dinv[j] = 1.0 / (p.dP[j] + p.s.sigma + rho * p.dAA[j]);
             if (changed)
                 for (int i = gtid; i < m; i += gstride) g[i] = rho * (p.zt[i] - p.z[i]) + y[i];
             dinv_ready = true;
             grid_barrier(p.gs, st);
         }
-        // ---- r0 on my slice: r = sigma (x - x~) - q - sum_q H_q [x~ ; g_q];  u = z = Pl \ r, pushed to everyone
-        spmv_H_partial(p.XG);
-        sys_barrier<false>(p.gs, st, pd, xs);
-        double acc[2] = {0.0, 0.0};
+        // ---- r0 on my slice: r = sigma (x - x~) - q - sum_q H_q [x~ ; g_q];  z = Pl \ r pushed to everyone
+        double unused = 0.0;
+        spmv_H_push(p.XG, unused);
+        sys_barrier<true>(p.gs, st, pd, xs);
+        double d3[3] = {0.0, 0.0, 0.0};                                // gamma = r.z, |r|^2, z.z on my slice
         for (int j = s0 + gtid; j < s1; j += gstride) {
-            const double rj = sigma * (x[j] - xt[j]) - p.q[j] - reduced_w(j);
+            const double rj = p.s.sigma * (x[j] - xt[j]) - p.q[j] - reduced_w(j);
             p.r[j] = rj;
             const double zj = PRE ? p.dinv[j] * rj : rj;
-            if (PRE && !CGV) p.zp[j] = zj;
-#pragma unroll
-            for (int q = 0; q < kMaxPeers; ++q)
-                if (q < R) udst[q][j] = zj;
-            acc[0] += rj * rj;
-            acc[1] += rj * zj;
+            push_all(off_u, j, zj);
+            d3[0] += rj * zj;
+            d3[1] += rj * rj;
+            d3[2] += zj * zj;
         }
-        double residual, tol;
+        peer_barrier_sum<3>(p.gs, st, pd, xs, d3, sm, parity);         // also publishes the z slices
+        double residual = sqrt(d3[1]);
+        const double tol = fmax(p.s.pcg_rel_eps * residual, p.s.pcg_eps);
         long long k = 0;
-        if (CGV) {
-            // ---- Chronopoulos-Gear PCG: u holds z = Pl \ r (the only gathered CG vector), p.zp holds the search
-            //      direction, p.c holds s = K p, pd.wslice holds w = K z; gamma = r.z, delta = z.w and |r|^2 come out of
-            //      ONE reduction per iteration.  Same iterates as the standard recurrence in exact arithmetic; one
-            //      extra operator application per solve (the w of the converged residual is not used).
-            sys_barrier<true>(p.gs, st, pd, xs);                       // z slices published
-            double gam = 0.0, a_cg = 0.0;
-            bool first = true;
-            for (;;) {
-                tick(6);
-                spmv_A_t();
-                grid_barrier(p.gs, st);
-                tick(0);
-                spmv_H_partial(p.UT);
-                tick(1);
-                sys_barrier<false>(p.gs, st, pd, xs);
-                double d3[3] = {0.0, 0.0, 0.0};                        // r.z, z.w, r.r on my slice
-                for (int j = s0 + gtid; j < s1; j += gstride) {
-                    const double zj = u[j], rj = p.r[j];
-                    const double wj = reduced_w(j) + sigma * zj;
-                    pd.wslice[j] = wj;
-                    d3[0] += rj * zj;
-                    d3[1] += zj * wj;
-                    d3[2] += rj * rj;
-                }
-                peer_barrier_sum<3>(p.gs, st, pd, xs, d3, sm, parity);
-                tick(2);
-                residual = sqrt(d3[2]);
-                if (first) tol = fmax(p.s.pcg_rel_eps * residual, p.s.pcg_eps);
-                if (!first) ++k;
-                if (!(k < p.s.pcg_max_iter && !(residual <= tol))) break;
-                double beta = 0.0;
-                if (first) {
-                    a_cg = d3[0] / d3[1];
-                } else {
-                    beta = d3[0] / gam;
-                    const double den = d3[1] - beta * d3[0] / a_cg;
-                    if (!(den > 0.0)) break;
-                    a_cg = d3[0] / den;
-                }
-                if (first && !(d3[1] > 0.0)) break;
-                gam = d3[0];
-                first = false;
-                // p = z + beta p ; s = w + beta s ; x~ += a p ; r -= a s ; z = Pl \ r -> pushed to everyone
-                for (int j = s0 + gtid; j < s1; j += gstride) {
-                    const double pj = u[j] + beta * p.zp[j];
-                    const double sj = pd.wslice[j] + beta * p.c[j];
-                    p.zp[j] = pj;
-                    p.c[j] = sj;
-                    xt[j] += a_cg * pj;
-                    const double rj = p.r[j] - a_cg * sj;
-                    p.r[j] = rj;
-                    const double zj = PRE ? p.dinv[j] * rj : rj;
-#pragma unroll
-                    for (int q = 0; q < kMaxPeers; ++q)
-                        if (q < R) udst[q][j] = zj;
-                }
-                sys_barrier<true>(p.gs, st, pd, xs);
-                tick(4);
-            }
-        } else {
-        peer_barrier_sum<2>(p.gs, st, pd, xs, acc, sm, parity);      // also publishes the u slices
-        residual = sqrt(acc[0]);
-        double rz = acc[1];
-        tol = fmax(p.s.pcg_rel_eps * residual, p.s.pcg_eps);
+        double gam_prev = 0.0, a_cg = 0.0;
+        bool first = true;
         while (k < p.s.pcg_max_iter && !(residual <= tol)) {
-            tick(6);
-            spmv_A_t();
+            tick(5);
+            {   // t = rho A_r z
+                auto epi = [&](int i, double sum, double) { t[i] = rho * sum; };
+                spmv_tiles<TMA, false>(p.A, u, sm, ps, epi);
+                count(ctr.n_a, 1);
+            }
             grid_barrier(p.gs, st);
             tick(0);
-            spmv_H_partial(p.UT);
+            double zw[1] = {0.0};
+            spmv_H_push(p.UT, zw[0]);
             tick(1);
-            sys_barrier<false>(p.gs, st, pd, xs);
-            // reduce-scatter fused with c = w + sigma u and u.c (my slice only)
-            double uc[1] = {0.0};
-            for (int j = s0 + gtid; j < s1; j += gstride) {
-                const double uj = u[j];
-                const double cj = reduced_w(j) + sigma * uj;
-                p.c[j] = cj;
-                uc[0] += uj * cj;
-            }
-            peer_barrier_sum<1>(p.gs, st, pd, xs, uc, sm, parity);
+            peer_barrier_sum<1>(p.gs, st, pd, xs, zw, sm, parity);     // partials delivered; z . sum_r w_r known
             tick(2);
-            if (!(uc[0] > 0.0)) break;
-            const double a_cg = rz / uc[0];
-            double acc2[2] = {0.0, 0.0};
+            const double gam = d3[0];
+            const double delta = zw[0] + p.s.sigma * d3[2];            // z . (P + rho A'A + sigma I) z
+            double beta = 0.0;
+            if (first) {
+                if (!(delta > 0.0)) break;                             // breakdown guard (K is SPD)
+                a_cg = gam / delta;
+            } else {
+                beta = gam / gam_prev;
+                const double den = delta - beta * gam / a_cg;
+                if (!(den > 0.0)) break;
+                a_cg = gam / den;
+            }
+            gam_prev = gam;
+            d3[0] = d3[1] = d3[2] = 0.0;
             for (int j = s0 + gtid; j < s1; j += gstride) {
-                xt[j] += a_cg * u[j];
-                const double rj = p.r[j] - a_cg * p.c[j];
-                p.r[j] = rj;
-                const double zj = PRE ? p.dinv[j] * rj : rj;
-                if (PRE) p.zp[j] = zj;
-                acc2[0] += rj * rj;
-                acc2[1] += rj * zj;
-            }
-            peer_barrier_sum<2>(p.gs, st, pd, xs, acc2, sm, parity);
-            residual = sqrt(acc2[0]);
-            const double rz_new = acc2[1];
-            ++k;
-            tick(4);
-            if (k < p.s.pcg_max_iter && !(residual <= tol)) {
-                const double beta = rz_new / rz;
-                for (int j = s0 + gtid; j < s1; j += gstride) {
-                    const double un = zpv[j] + beta * u[j];
-#pragma unroll
-                    for (int q = 0; q < kMaxPeers; ++q)
-                        if (q < R) udst[q][j] = un;
+                const double zj = u[j];
+                double pj = zj, sj = reduced_w(j) + p.s.sigma * zj;
+                if (!first) {                                          // (stale p, s of the previous solve are never read)
+                    pj += beta * p.zp[j];
+                    sj += beta * p.c[j];
                 }
-                sys_barrier<true>(p.gs, st, pd, xs);
+                p.zp[j] = pj;
+                p.c[j] = sj;
+                xt[j] += a_cg * pj;
+                const double rj = p.r[j] - a_cg * sj;
+                p.r[j] = rj;
+                const double zn = PRE ? p.dinv[j] * rj : rj;
+                push_all(off_u, j, zn);
+                d3[0] += rj * zn;
+                d3[1] += rj * rj;
+                d3[2] += zn * zn;
             }
-            rz = rz_new;
-            tick(5);
+            first = false;
+            tick(3);
+            peer_barrier_sum<3>(p.gs, st, pd, xs, d3, sm, parity);
+            tick(4);
+            residual = sqrt(d3[1]);
+            ++k;
         }
-        }
-        pcg_total += k;
-        if (k >= p.s.pcg_max_iter && !(residual <= tol)) ++pcg_maxed;
+        count(ctr.pcg_total, k);
+        if (k >= p.s.pcg_max_iter && !(residual <= tol)) count(ctr.pcg_maxed, 1);
         // ---- all-gather x~ (every rank pushes its slice), then the row-local update
         for (int j = s0 + gtid; j < s1; j += gstride) {
             const double v = xt[j];
 #pragma unroll
             for (int q = 0; q < kMaxPeers; ++q)
-                if (q < R && q != pd.rank) xtdst[q][j] = v;
+                if (q < R && q != pd.rank) pd.region[q][off_xt + j] = v;
         }
         sys_barrier<true>(p.gs, st, pd, xs);
 
         const bool do_check = (ii % p.s.check_every) == 0;
         double nrm[4] = {0.0, 0.0, 0.0, 0.0};
         {
-            auto epi = [&](int i, double s0_, double) {
-                const double zt_i = s0_;
+            auto epi = [&](int i, double sum, double) {
+                const double zt_i = sum;
                 const double z_old = p.z[i], y_old = y[i];
-                const double zr = alpha * zt_i + alpha1 * z_old;
+                const double zr = p.s.alpha * zt_i + (1.0 - p.s.alpha) * z_old;
                 const double z_new = clamp_julia(zr + rho1 * y_old, p.l[i], p.u[i]);
                 const double y_new = y_old + rho * (zr - z_new);
                 p.z[i] = z_new;
@@ -469,33 +420,33 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) admm_peer_sliced_kernel(Sp
                 nrm[1] = nanmax(nrm[1], fabs(z_new - z_old));
             };
             spmv_tiles<TMA, false>(p.A, xt, sm, ps, epi);
-            ++n_a;
+            count(ctr.n_a, 1);
         }
         for (int j = gtid; j < n; j += gstride) {
             const double x_old = x[j];
-            const double x_new = alpha * xt[j] + alpha1 * x_old;
+            const double x_new = p.s.alpha * xt[j] + (1.0 - p.s.alpha) * x_old;
             x[j] = x_new;
             nrm[0] = nanmax(nrm[0], fabs(x_new - x_old));
         }
         grid_barrier(p.gs, st);
         if (do_check) {
             {
-                auto epi = [&](int i, double s0_, double) {
+                auto epi = [&](int i, double sum, double) {
                     const double zi = p.z[i];
-                    nrm[2] = nanmax(nrm[2], fabs(s0_ - zi));
-                    nrm[3] = nanmax(nrm[3], fabs(s0_));
+                    nrm[2] = nanmax(nrm[2], fabs(sum - zi));
+                    nrm[3] = nanmax(nrm[3], fabs(sum));
                     nrm[3] = nanmax(nrm[3], fabs(zi));
                 };
                 spmv_tiles<TMA, false>(p.A, x, sm, ps, epi);
-                ++n_a;
+                count(ctr.n_a, 1);
             }
             {
-                auto epi = [&](int j, double s0_, double s1_) {
-                    w2part[j] = s0_;
-                    w2part[n + j] = s1_;
+                auto epi = [&](int j, double sum0, double sum1) {
+                    w2part[j] = sum0;
+                    w2part[n + j] = sum1;
                 };
                 spmv_tiles<TMA, true>(p.H, p.XY, sm, ps, epi);
-                ++n_h;
+                count(ctr.n_h, 1);
             }
             grid_barrier_reduce<4, true>(p.gs, st, nrm, sm.red, sm.bcast);
             peer_allmax4(p.gs, st, pd, xs, nrm);
@@ -509,14 +460,15 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) admm_peer_sliced_kernel(Sp
             }
             grid_barrier_reduce<2, true>(p.gs, st, nd, sm.red, sm.bcast);
             const double dx = nrm[0], dz = nrm[1];
-            res_prim = nrm[2];
-            res_dual = nd[0];
+            const double res_prim = nrm[2], res_dual = nd[0];
+            if (threadIdx.x == 0) { ctr.res_prim = res_prim; ctr.res_dual = res_dual; }
             const double max_prim = nrm[3];
             const double max_dual = nanmax(nd[1], p.normQ);
             if (p.s.adaptive_rho) {
                 const double num = res_prim * max_dual, den = res_dual * max_prim;
                 rhorho = clamp_julia(rho * sqrt(num / den), 1e-3, 1e6);
             }
+            const double eps_admm = fmin(p.s.eps_abs, p.s.eps_rel) * 1e-2;
             if ((res_prim < p.s.eps_abs + p.s.eps_rel * max_prim) && (res_dual < p.s.eps_abs + p.s.eps_rel * max_dual)) conv_flag = 3;
             if ((dx <= eps_admm) && (dz <= eps_admm)) conv_flag = 2;
             if (conv_flag != 1) break;
@@ -529,13 +481,13 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) admm_peer_sliced_kernel(Sp
         o.conv_flag = conv_flag;
         o.iterations = ii;
         o.rho_final = rho;
-        o.res_prim = res_prim;
-        o.res_dual = res_dual;
-        o.rho_updates = rho_updates;
-        o.pcg_iters_total = pcg_total;
-        o.pcg_maxed = pcg_maxed;
-        o.n_h_passes = n_h;
-        o.n_a_passes = n_a;
+        o.res_prim = ctr.res_prim;
+        o.res_dual = ctr.res_dual;
+        o.rho_updates = ctr.rho_updates;
+        o.pcg_iters_total = ctr.pcg_total;
+        o.pcg_maxed = ctr.pcg_maxed;
+        o.n_h_passes = ctr.n_h;
+        o.n_a_passes = ctr.n_a;
     }
 }
 

@@ -13,6 +13,7 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from quadraticprogramsolver_b200 import solver as S  # noqa: E402
 from workloads.problems import config_cfg5  # noqa: E402
+from oracle import c_oracle  # noqa: E402  (the checker: this script is test infrastructure, tests/test_gpu_dist.py runs it)
 
 pscale = float(sys.argv[1]) if len(sys.argv) > 1 else 0.02
 tscale = float(sys.argv[2]) if len(sys.argv) > 2 else 0.0
@@ -37,10 +38,16 @@ for mode, precond, adapt in [(mo, pc, ad) for mo in modes for pc, ad in (("jacob
         x1 = np.zeros(n)
         flag1 = s1.solve(x1, want_zy=True)
         info1 = dict(s1.info)
+    # the oracle (compiled restatement of the reference), same linear-solver mode and settings
+    okw = {k: v for k, v in kw.items() if k != "precond"}
+    xo, fo, io = c_oracle.solve_sparse(P, q, A, l, u, precond=1 if precond == "jacobi" else 0, **okw)
+    err_o = float(np.max(np.abs(x - xo)) / (1 + np.max(np.abs(xo))))
+    ok_o = int(flag) == int(fo) and abs(info["iterations"] - io["iterations"]) <= 2 and err_o <= 1e-6
     err = float(np.max(np.abs(x - x1)) / (1 + np.max(np.abs(x1))))
     zerr = float(np.max(np.abs(info["z_local"] - info1["z"][rows[0]:rows[1]]), initial=0.0) / (1 + np.max(np.abs(info1["z"]))))
-    ok = (int(flag) == int(flag1) and abs(info["iterations"] - info1["iterations"]) <= 2 and err <= 1e-6 and zerr <= 1e-6)
-    res = dict(ok=bool(ok), flag=int(flag), flag1=int(flag1), it=info["iterations"], it1=info1["iterations"], err=err, zerr=zerr,
+    ok = (int(flag) == int(flag1) and abs(info["iterations"] - info1["iterations"]) <= 2 and err <= 1e-6 and zerr <= 1e-6
+          and ok_o)
+    res = dict(ok=bool(ok), err_vs_oracle=err_o, flag_oracle=int(fo), it_oracle=int(io["iterations"]), flag=int(flag), flag1=int(flag1), it=info["iterations"], it1=info1["iterations"], err=err, zerr=zerr,
                pcg=info["pcg_iters_total"], pcg1=info1["pcg_iters_total"], rho_updates=info["rho_updates"],
                ms=info["solve_ms"], ms1=info1["solve_ms"], launches=info["kernel_launches"])
     out[f"parity_{mode}_{precond}_{'adapt' if adapt else 'fixed'}"] = res

@@ -1,5 +1,5 @@
 """Multi-GPU parity (needs >= 2 B200s, e.g. `gpurun --gpus 2`; skipped on a single-GPU box): the row-partitioned
-path -- both the in-kernel peer-memory variant and the NCCL baseline -- against the single-GPU kernel.
+path -- both the in-kernel peer-memory variant and the NCCL baseline -- against the single-GPU kernel AND the compiled oracle.
 The host-side partition logic and data flow are covered on CPU by tests/test_partition_gloo.py."""
 import os
 import subprocess
