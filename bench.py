@@ -54,7 +54,7 @@ def load_peaks():
 
 def load_traffic(workload, world):
     """dram__bytes_read.sum + dram__bytes_write.sum of the timed kernel (one launch = one step), from the committed ncu
-    capture of this very launch (profiles/r2_traffic.json, written by scripts/ncu_traffic.sh); None when no capture of
+    capture of this very launch (profiles/r2_traffic.json, written by scripts/ncu_traffic.py); None when no capture of
     the workload exists -- never a typed-in constant."""
     path = os.path.join(ROOT, "profiles", "r2_traffic.json")
     try:

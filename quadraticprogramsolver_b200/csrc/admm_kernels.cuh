@@ -15,6 +15,7 @@
 // so that  K u = H*UT + sigma u,   b - K x~ = sigma (x - x~) - q - H*XG,   [Px ; A'y] = split sums of H*XY.
 #pragma once
 #include "spmv_core.cuh"
+#include "direct_kernels.cuh"
 
 namespace qpb {
 
@@ -51,6 +52,16 @@ struct SparseProblemDev {
     // optional per-constraint step size (qpb200_set_rho_scale; not in the reference): rho_i = rho * rs[i].
     // nullptr = one scalar rho as in SolveQuadraticProgram.jl:16; dAA then holds sum_i rs[i] A_ij^2
     const double *rs;
+    // direct x~ step (settings.lin_solver = QPB200_LINSOLVE_CHOLESKY, direct_kernels.cuh): Kneg = -(P + sigma I +
+    // A' diag(rho_i) A)^-1 for the rho in rho0, dense row-major, leading dimension ldk; nullptr on the CG path
+    const double *Kneg;
+    int ldk;
+    // where this launch starts: a fresh solve has iter0 = 0, rho0 = rhorho0 = settings.rho, resume_changed = 0.  The
+    // direct path leaves the kernel when the rho trigger fires (conv_flag 0 = "refactorise"), the host rebuilds Kneg
+    // and re-enters with the iteration count, the adopted rho and resume_changed = 1 (g depends on rho)
+    long long iter0;
+    double rho0, rhorho0;
+    int resume_changed;
     GridSync gs;
     AdmmSettingsDev s;
     AdmmInfoDev *info;
@@ -97,7 +108,9 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) spmv_kernel(CsrTiled M, co
 //   (= K p by linearity), x~ += alpha p, r -= alpha s, z = Pl \ r are one vector pass: three grid barriers and three
 //   phases per iteration instead of four and four.  Same iterates in exact arithmetic, same stopping rule on the same
 //   recurrence residual; one more operator application per inner solve (the K z of the final residual is unused).
-template <int TMA, bool PRE, bool CGV>
+// DIRECT = true: the x~ step is exact (the reference's LaLdl!/QDLdl!/FacLdl! plugins, LinearSystemSolvers.jl:16-107):
+//   x~ += K^-1 (b - K x~) with the dense inverse of direct_kernels.cuh; a rho change ends the launch (see iter0 above).
+template <int TMA, bool PRE, bool CGV, bool DIRECT = false>
 __global__ void __launch_bounds__(kThreads, kMinCtas) admm_kernel(SparseProblemDev p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SpmvSmem &sm = *reinterpret_cast<SpmvSmem *>(smem_raw);
@@ -120,9 +133,9 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) admm_kernel(SparseProblemD
     double *const u = p.UT, *const t = p.UT + n;
     double *const zpv = PRE ? p.zp : p.r;   // un-preconditioned: "z" of PCG is r itself
 
-    double rho = p.s.rho, rho1 = 1.0 / rho;                         // SolveQuadraticProgram.jl:30
+    double rho = p.rho0, rho1 = 1.0 / rho;                          // SolveQuadraticProgram.jl:30 (rho0 = settings.rho on a fresh solve)
     // p.s.alpha, 1 - p.s.alpha (:31), p.s.sigma, p.s.pcg_rel_eps are used straight out of the parameter block (constant-bank operands)
-    double rhorho = rho;                                            // :43
+    double rhorho = p.rhorho0;                                      // :43
     int conv_flag = 1;                                              // :33 convNumItr
     bool dinv_ready = false;
     // rho and 1/rho of constraint i (the scalars of SolveQuadraticProgram.jl:30 unless a scale vector was set)
@@ -130,10 +143,15 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) admm_kernel(SparseProblemD
     auto rho1_of = [&](int i) { return p.rs ? 1.0 / (rho * p.rs[i]) : rho1; };
 
     long long ii = 0;
-    for (ii = 1; ii <= p.s.max_iter; ++ii) {                        // :45
+    bool refactor = false;
+    for (ii = p.iter0 + 1; ii <= p.s.max_iter; ++ii) {              // :45
         // ---- rho trigger (:46-52) -> "refactorisation": Jacobi diagonal and g depend on rho
-        bool changed = false;
+        bool changed = DIRECT && ii == p.iter0 + 1 && p.resume_changed;
         if (p.s.adaptive_rho && ((rhorho * p.s.rho_factor < rho) || (rhorho > p.s.rho_factor * rho))) {
+            if (DIRECT) {                                           // the host refactorises K for rhorho and re-enters at ii
+                refactor = true;
+                break;
+            }
             rho = rhorho;
             rho1 = 1.0 / rho;
             changed = true;
@@ -170,7 +188,11 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) admm_kernel(SparseProblemD
         const double tol = fmax(p.s.pcg_rel_eps * residual, p.s.pcg_eps);     // cg_iterator!: max(p.s.pcg_rel_eps*|r0|, abstol)
 
         long long k = 0;
-        if (CGV) {
+        if (DIRECT) {
+            // ---- exact solve as one refinement step from the previous x~: x~ += K^-1 r0 (r0 from [P1])
+            dense_symv_sub(p.Kneg, p.ldk, n, p.r, xt);
+            grid_barrier(p.gs, st);
+        } else if (CGV) {
             // ---- one-reduction PCG: u holds z = Pl \ r (the vector A and H gather from), p.zp the search direction,
             //      p.c holds s = K p, p.wv holds w = K z
             double gam = 0.0, a_cg = 0.0;
@@ -352,6 +374,11 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) admm_kernel(SparseProblemD
         }
     }
     if (ii > p.s.max_iter) ii = p.s.max_iter;
+    if (refactor) {                                                 // iterations completed so far; rho to adopt
+        conv_flag = 0;
+        ii -= 1;
+        rho = rhorho;
+    }
 
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         AdmmInfoDev &o = *p.info;

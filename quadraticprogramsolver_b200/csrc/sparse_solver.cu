@@ -113,12 +113,16 @@ static int prep_kernel(const void *kernel, int *blocks_per_sm) { return prep_til
 int SparseSolver::settings_to_dev(const qpb200_settings &s) {
     if (!(s.rho > 0.0) || !(s.sigma >= 0.0) || s.max_iter < 0 || s.check_every <= 0 || s.pcg_max_iter < 0)
         return fail(QPB200_ERR_ARG, "settings: need rho > 0, sigma >= 0, max_iter >= 0, check_every > 0, pcg_max_iter >= 0");
-    if (s.lin_solver != QPB200_LINSOLVE_PCG)
-        return fail(QPB200_ERR_ARG, "qpb200_create: the sparse path implements lin_solver = QPB200_LINSOLVE_PCG only");
+    if (s.lin_solver != QPB200_LINSOLVE_PCG && s.lin_solver != QPB200_LINSOLVE_CHOLESKY)
+        return fail(QPB200_ERR_ARG, "settings: lin_solver must be QPB200_LINSOLVE_PCG or QPB200_LINSOLVE_CHOLESKY");
+    if (created && (s.lin_solver == QPB200_LINSOLVE_CHOLESKY) != direct)
+        return fail(QPB200_ERR_ARG, "qpb200_update_settings: lin_solver is fixed at create (the dense factor is allocated there)");
     if (created && (s.device != settings.device || s.reserved_i[QPB200_RSV_SCALING_ITERS] != settings.reserved_i[QPB200_RSV_SCALING_ITERS] ||
                     s.reserved_i[QPB200_RSV_DIST_MODE] != settings.reserved_i[QPB200_RSV_DIST_MODE]))
         return fail(QPB200_ERR_ARG, "qpb200_update_settings: device, scaling iterations and the multi-GPU mode are fixed at create");
+    if (created && s.sigma != settings.sigma) k_valid = false;   // the dense inverse was built for the old sigma
     settings = s;
+    direct = s.lin_solver == QPB200_LINSOLVE_CHOLESKY;
     AdmmSettingsDev &d = prob.s;
     d.max_iter = s.max_iter;
     d.check_every = s.check_every;
@@ -173,6 +177,9 @@ int SparseSolver::init(int64_t n64, int64_t m64, const int64_t *Pp, const int64_
 
     n = (int)n64;
     m = (int)m64;
+    if (direct && n > kDirectMaxN)
+        return fail(QPB200_ERR_ARG, "qpb200_create: lin_solver = CHOLESKY keeps a dense n x n inverse: n = %d exceeds %d, use PCG", n,
+                    kDirectMaxN);
     // ---- grid limit: co-resident CTAs of the persistent kernel
     QPB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
     int per_sm = 1 << 30, tmp = 0;
@@ -186,7 +193,8 @@ int SparseSolver::init(int64_t n64, int64_t m64, const int64_t *Pp, const int64_
             per_sm = cached_per_sm[device];
         } else {
             for (const void *fn : {(const void *)admm_kernel<1, false, false>, (const void *)admm_kernel<1, true, false>,
-                                   (const void *)admm_kernel<1, false, true>, (const void *)admm_kernel<1, true, true>}) {
+                                   (const void *)admm_kernel<1, false, true>, (const void *)admm_kernel<1, true, true>,
+                                   (const void *)admm_kernel<1, false, false, true>}) {
                 if ((rc = prep_kernel(fn, &tmp))) return rc;
                 per_sm = std::min(per_sm, tmp);
             }
@@ -344,6 +352,19 @@ int SparseSolver::init(int64_t n64, int64_t m64, const int64_t *Pp, const int64_
     QPB_CUDA(arena.alloc(&prob.gs.partials[0], (size_t)grid_max * kMaxRed, true));
     QPB_CUDA(arena.alloc(&prob.gs.partials[1], (size_t)grid_max * kMaxRed, true));
     QPB_CUDA(arena.alloc(&scratch, std::max(nm, (size_t)2 * n) + 8, true));
+    prob.Kneg = nullptr;
+    prob.ldk = 0;
+    if (direct) {
+        ldk = (n + kGjTile - 1) / kGjTile * kGjTile;
+        QPB_CUDA(arena.alloc(&d_K, (size_t)ldk * ldk));
+        QPB_CUDA(arena.alloc(&d_gjD, (size_t)kGjNb * kGjNb));
+        QPB_CUDA(arena.alloc(&d_gjW, (size_t)ldk * kGjNb));
+        QPB_CUDA(arena.alloc(&d_gjC, (size_t)ldk * kGjNb));
+        QPB_CUDA(arena.alloc(&d_gjStatus, 1, true));
+        prob.Kneg = d_K;
+        prob.ldk = ldk;
+        k_valid = false;
+    }
     QPB_CUDA(cudaDeviceSynchronize());
     lap("upload+alloc");
     h_l.assign(l, l + m);   // host copies of the (scaled) bounds: qpb200_update_vectors re-checks l <= u against them
@@ -399,7 +420,7 @@ int SparseSolver::launch_admm() {
     void *args[] = {(void *)&prob};
     const void *fns[2][2] = {{(const void *)admm_kernel<1, false, true>, (const void *)admm_kernel<1, true, true>},
                              {(const void *)admm_kernel<1, false, false>, (const void *)admm_kernel<1, true, false>}};
-    const void *fn = fns[one_reduction() ? 0 : 1][use_pre ? 1 : 0];
+    const void *fn = direct ? (const void *)admm_kernel<1, false, false, true> : fns[one_reduction() ? 0 : 1][use_pre ? 1 : 0];
     QPB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, sizeof(SpmvSmem), stream));
     return QPB200_OK;
 }
@@ -416,8 +437,35 @@ int SparseSolver::solve(double *x_inout, double *z_out, double *y_out, qpb200_in
     }
     int rc = reset_state(scaled ? x0s.data() : x_inout);
     if (rc) return rc;
+    prob.iter0 = 0;
+    prob.rho0 = prob.rhorho0 = settings.rho;
+    prob.resume_changed = 0;
+    int64_t launches = 0;
+    AdmmInfoDev seg{};                              // direct path: totals over the launches of this solve
+    seg.res_prim = seg.res_dual = std::nan("");
     QPB_CUDA(cudaEventRecord(ev0, stream));
-    if ((rc = launch_admm())) return rc;
+    if (direct && (!k_valid || k_rho != settings.rho)) {
+        if ((rc = refactor(settings.rho, &launches))) return rc;
+    }
+    for (;;) {
+        if ((rc = launch_admm())) return rc;
+        ++launches;
+        if (!direct) break;
+        // the exact-solve path leaves the kernel when the rho trigger fires (SolveQuadraticProgram.jl:46-52): refactorise
+        // K for the new rho (LinearSystemSolvers.jl:93-95) and re-enter at the same iteration
+        AdmmInfoDev part;
+        QPB_CUDA(cudaMemcpyAsync(&part, prob.info, sizeof(part), cudaMemcpyDeviceToHost, stream));
+        QPB_CUDA(cudaStreamSynchronize(stream));
+        seg.n_h_passes += part.n_h_passes;
+        seg.n_a_passes += part.n_a_passes;
+        if (!std::isnan(part.res_prim)) { seg.res_prim = part.res_prim; seg.res_dual = part.res_dual; }
+        if (part.conv_flag != 0) break;
+        seg.rho_updates += 1;
+        prob.iter0 = part.iterations;
+        prob.rho0 = prob.rhorho0 = part.rho_final;
+        prob.resume_changed = 1;
+        if ((rc = refactor(part.rho_final, &launches))) return rc;
+    }
     QPB_CUDA(cudaEventRecord(ev1, stream));
     QPB_CUDA(cudaMemcpyAsync(x_inout, prob.XY, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, stream));
     if (z_out && m) QPB_CUDA(cudaMemcpyAsync(z_out, prob.z, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, stream));
@@ -434,6 +482,12 @@ int SparseSolver::solve(double *x_inout, double *z_out, double *y_out, qpb200_in
     }
     float ms = 0.f;
     QPB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+    if (direct) {
+        hi.n_h_passes = seg.n_h_passes;
+        hi.n_a_passes = seg.n_a_passes;
+        hi.rho_updates = seg.rho_updates;
+        if (std::isnan(hi.res_prim)) { hi.res_prim = seg.res_prim; hi.res_dual = seg.res_dual; }
+    }
     last_info = hi;
     if (info) {
         std::memset(info, 0, sizeof(*info));
@@ -447,7 +501,7 @@ int SparseSolver::solve(double *x_inout, double *z_out, double *y_out, qpb200_in
         info->pcg_maxed = hi.pcg_maxed;
         info->solve_ms = ms;
         info->setup_ms = setup_ms;
-        info->kernel_launches = 1;
+        info->kernel_launches = launches;
     }
     if (getenv("QPB200_TIMING"))
         fprintf(stderr, "[qpb200_solve] device %.1f ms, wall %.1f ms\n", ms,
@@ -457,6 +511,7 @@ int SparseSolver::solve(double *x_inout, double *z_out, double *y_out, qpb200_in
 
 int SparseSolver::set_rho_scale(const double *rs) {
     QPB_CUDA(cudaSetDevice(device));
+    k_valid = false;                                // K = P + sigma I + A' diag(rho_i) A changes with the scale
     if (!rs) {                                      // back to the scalar rho of the reference
         prob.rs = nullptr;
         prob.dAA = d_dAA;
@@ -498,7 +553,8 @@ int64_t SparseSolver::solve_bytes() const {
     // one-reduction arrangement: z,w,p,s,x~,r,(dinv) reads + p,s,x~,r,z writes = 12 (12 n-vector passes)
     const int64_t pcg_vec = 8LL * (one_reduction() ? 12 : 11) * n;
     const int64_t upd_vec = 8LL * (3 * (int64_t)n + 8 * (int64_t)m);
-    return i.n_h_passes * bH + i.n_a_passes * bA + i.pcg_iters_total * pcg_vec + i.iterations * upd_vec;
+    const int64_t dense = direct ? 8LL * n * (int64_t)ldk + 24LL * n : 0;   // one pass over -K^-1 per ADMM iteration
+    return i.n_h_passes * bH + i.n_a_passes * bA + i.pcg_iters_total * pcg_vec + i.iterations * (upd_vec + dense);
 }
 
 template <bool SPLIT>

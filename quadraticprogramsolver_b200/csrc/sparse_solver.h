@@ -5,11 +5,19 @@
 
 namespace qpb {
 
+constexpr int kDirectMaxN = 32768;        // dense n x n inverse: 8.6 GB at the limit
+
 struct SparseSolver {
     int n = 0, m = 0, device = -1, num_sms = 0, grid = 0;
     int64_t nnzP = 0, nnzA = 0;
     int loader = 1;          // 0 LDG, 1 TMA (default), 2 TMA + software-pipelined gathers
     bool use_pre = true;
+    // exact x~ step (settings.lin_solver = QPB200_LINSOLVE_CHOLESKY): dense -K^-1 [ldk x ldk] + sweep scratch
+    bool direct = false, k_valid = false;
+    double k_rho = 0.0;
+    int ldk = 0;
+    double *d_K = nullptr, *d_gjD = nullptr, *d_gjW = nullptr, *d_gjC = nullptr;
+    int *d_gjStatus = nullptr;
     qpb200_settings settings{};
     SparseProblemDev prob{};
     AdmmInfoDev last_info{};
@@ -35,6 +43,7 @@ struct SparseSolver {
     int settings_to_dev(const qpb200_settings &s);
     int reset_state(const double *x0_host);
     int launch_admm();
+    int refactor(double rho, int64_t *launches);   // build K for rho and invert it in place
     bool one_reduction() const;   // which arrangement of the (P)CG recurrence admm_kernel runs (QPB200_RSV_CG_RECURRENCE)
     int solve(double *x_inout, double *z_out, double *y_out, qpb200_info *info);
     int apply(int which, const double *x_host, double *y_host);
