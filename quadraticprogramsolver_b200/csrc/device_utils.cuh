@@ -108,7 +108,15 @@ __device__ __forceinline__ void grid_barrier(const GridSync &gs, SyncState &st) 
             fence_acq_rel_gpu();
             st_release_gpu(gs.flag, st.epoch);
         } else {
+            // a CTA that never arrives (a launch that is not co-resident, counters left over from another launch) must
+            // fail loudly, not hang the GPU: trap after ~20 s of polling
+            long long t0 = 0;
+            unsigned spins = 0;
             while (ld_acquire_gpu(gs.flag) < st.epoch) {
+                if ((++spins & 0xfffffu) == 0) {
+                    if (t0 == 0) t0 = clock64();
+                    else if (clock64() - t0 > 40000000000LL) __trap();
+                }
             }
         }
         // acquire + L1 invalidate (SASS: MEMBAR ; CCTL.IVALL): the phase that follows reads vectors other CTAs

@@ -464,6 +464,7 @@ int SparseSolver::solve(double *x_inout, double *z_out, double *y_out, qpb200_in
         prob.iter0 = part.iterations;
         prob.rho0 = prob.rhorho0 = part.rho_final;
         prob.resume_changed = 1;
+        QPB_CUDA(cudaMemsetAsync(sync_words, 0, 64 * sizeof(unsigned long long), stream));   // the barrier epochs restart with the launch
         if ((rc = refactor(part.rho_final, &launches))) return rc;
     }
     QPB_CUDA(cudaEventRecord(ev1, stream));
