@@ -44,8 +44,11 @@ extern "C" {
 /* ---- linear-system solver for the x~ step (replaces the (Init, Sol!) pair) ----------------- */
 #define QPB200_LINSOLVE_PCG 0      /* matrix-free (P)CG on K = P + sigma I + rho A'A
                                       (LinOpCg!/LinMapsCg!, LinearSystemSolvers.jl:145-229)       */
-#define QPB200_LINSOLVE_CHOLESKY 1 /* dense Cholesky of K (batched path; the reduced form of the
-                                      direct plugins LaLdl/QDLdl/FacLdl, :16-107)                 */
+#define QPB200_LINSOLVE_CHOLESKY 1 /* exact solve, the reduced form of the direct plugins LaLdl/QDLdl/FacLdl
+                                      (:16-107; FacLdl is what RunTests.jl:55-56 runs).  qpb200_batch_*: dense
+                                      Cholesky of K per QP in shared memory.  qpb200_create (n <= 32768): dense K in
+                                      HBM inverted in place by a blocked symmetric sweep (FP64 tensor-pipe trailing
+                                      updates), refactorised on every rho change, applied as x~ += K^-1 (b - K x~)   */
 #define QPB200_PRECOND_NONE 0      /* IterativeSolvers.cg! exactly as the reference calls it      */
 #define QPB200_PRECOND_JACOBI 1    /* Pl = Diagonal(diag(P) + sigma + rho colsumsq(A))            */
 
@@ -58,14 +61,15 @@ typedef struct qpb200_settings {
     double rho;           /* ρ = 1                                                                */
     double sigma;         /* σ = 1e-6                                                             */
     double alpha;         /* α = 1.6                                                              */
-    double delta;         /* δ = 1e-6        accepted, unused (as in the reference)               */
+    double delta;         /* δ = 1e-6        regularisation of the polish KKT system (unused unless
+                             reserved_i[QPB200_RSV_POLISH] is set; the reference never uses it)    */
     int32_t adaptive_rho; /* adptΡ = false                                                        */
     int32_t lin_solver;   /* QPB200_LINSOLVE_*                                                    */
     double rho_factor;    /* fctrΡ = 5                                                            */
     int64_t check_every;  /* numItrConv = 25                                                      */
-    int64_t polish_iter;  /* numItrPolish = 10   accepted, unused                                 */
-    double minres_eps;    /* ϵMinres = 1e-6      accepted, unused                                 */
-    int64_t minres_iter;  /* numItrMinres = 500  accepted, unused                                 */
+    int64_t polish_iter;  /* numItrPolish = 10   refinement rounds of the polish (see QPB200_RSV_POLISH)  */
+    double minres_eps;    /* ϵMinres = 1e-6      relative residual of each MINRES solve of the polish     */
+    int64_t minres_iter;  /* numItrMinres = 500  iteration cap of each MINRES solve                       */
     double pcg_eps;       /* ϵPcg = 1e-6  (abstol of cg!)                                         */
     int64_t pcg_max_iter; /* numItrPcg = 1000                                                     */
     double pcg_rel_eps;   /* reltol of cg!; <0 means the library default sqrt(eps(Float64))       */
@@ -99,9 +103,18 @@ typedef struct qpb200_settings {
                                        configs[0], 30.2 vs 32.8 at configs[1]), 1 for larger ones (the extra vector
                                        traffic costs more than the barrier there)                                     */
 
+#define QPB200_RSV_POLISH 5         /* sparse single-GPU path: 1 = polish the solution after the ADMM loop.  The Julia
+                                       driver accepts numItrPolish, delta, eps_minres, numItrMinres and never uses them
+                                       (SolveQuadraticProgram.jl:16-17), so 0 (default) is the reference's behaviour; 1 runs
+                                       the MATLAB twin's polish (SolveQuadraticProgram.m:289-325): numItrPolish rounds of
+                                       iterative refinement of the delta-regularised KKT system of the active constraints,
+                                       each solved by MINRES (eps_minres, numItrMinres) on the device; x is replaced only if
+                                       the last MINRES solve converged.  Active rows: z_i - l_i < -y_i (lower),
+                                       u_i - z_i < y_i (upper) instead of MATLAB's sign(y_i) -- see polish_kernels.cuh.     */
+
 typedef struct qpb200_info {
     int32_t conv_flag;       /* QPB200_CONV_*                                                      */
-    int32_t reserved;
+    int32_t polish_status;   /* 0 = polish not requested, 1 = applied, 2 = MINRES did not converge (x untouched) */
     int64_t iterations;      /* ADMM iterations executed (a multiple of check_every unless capped) */
     double rho_final;
     double res_prim;         /* ||Ax - z||inf at the last check                                    */
@@ -112,6 +125,8 @@ typedef struct qpb200_info {
     double solve_ms;         /* device time of the solve, CUDA events                              */
     double setup_ms;         /* host wall time of create (conversion + upload)                     */
     int64_t kernel_launches; /* kernels launched by the last solve                                 */
+    int64_t polish_minres_iters; /* MINRES iterations summed over the polish rounds                */
+    int64_t polish_active;   /* constraints in the polish's active set                             */
 } qpb200_info;
 
 typedef struct qpb200_handle qpb200_handle;             /* one sparse QP on one GPU               */

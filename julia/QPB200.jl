@@ -64,10 +64,10 @@ mutable struct Settings
     Settings() = new()
 end
 
-# qpb200_info (88 bytes)
+# qpb200_info (104 bytes)
 mutable struct Info
     conv_flag::Int32
-    reserved::Int32
+    polish_status::Int32
     iterations::Int64
     rho_final::Float64
     res_prim::Float64
@@ -78,6 +78,8 @@ mutable struct Info
     solve_ms::Float64
     setup_ms::Float64
     kernel_launches::Int64
+    polish_minres_iters::Int64
+    polish_active::Int64
     Info() = new()
 end
 

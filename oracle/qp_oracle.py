@@ -294,14 +294,15 @@ def solve_quadratic_program(vX, mP, vQ, mA, vL, vU, LinSysSolInit, LinSysSol, *,
                             numIterations=5000, epsAbs=1e-6, epsRel=1e-6, rho=1.0, sigma=1e-6, alpha=1.6,
                             delta=1e-6, adptRho=False, fctrRho=5.0, numItrConv=25, numItrPolish=10,
                             epsMinres=1e-6, numItrMinres=500, epsPcg=None, numItrPcg=None, trace=None, scaling=None,
-                            rhoScale=None):
+                            rhoScale=None, polish=False):
     """``SolveQuadraticProgram!`` (SolveQuadraticProgram.jl:14-76).  Mutates ``vX``.
 
     Returns ``(convFlag, info)``; the reference returns only the flag -- ``info`` carries the
     iteration count, final rho, residuals and CG iteration total for the parity tests.
     ``epsPcg`` / ``numItrPcg`` override the plugin kwargs the reference driver never forwards
     (LinearSystemSolvers.jl:125 vs SolveQuadraticProgram.jl:54); None keeps 1e-6 / 1000.
-    ``delta, numItrPolish, epsMinres, numItrMinres`` are accepted and unused, as in the reference.
+    ``delta, numItrPolish, epsMinres, numItrMinres`` are accepted and unused, as in the reference, unless
+    ``polish=True`` (not a reference keyword): then ``polish_solution`` below runs after the loop.
     ``rhoScale`` (m positive factors, not in the reference: OSQP's rho vector, README.md:71-72 TODO): constraint i
     uses ``rho * rhoScale[i]`` wherever :56-61 and the plugin use the scalar; ``CheckConvergence`` and the
     adaptive update keep the scalar.  Supported by modes D, M and J.
@@ -366,7 +367,101 @@ def solve_quadratic_program(vX, mP, vQ, mA, vL, vU, LinSysSolInit, LinSysSol, *,
 
     info = {"iterations": ii, "rho": rho, "res_prim": norms[0], "res_dual": norms[1],
             "rho_updates": n_rho_updates, "cg_iters": st.get("cg_iters", 0), "z": vZ, "y": vY}
+    if polish:
+        info["polish"] = polish_solution(vX, mPr, vQ, mAr, vL, vU, vZ, vY, delta, numItrPolish, epsMinres, numItrMinres)
     return convFlag, info
+
+
+# --------------------------------------------------------------------------------------------
+# Solution polish.  The Julia function reserves the keyword arguments and never uses them
+# (SolveQuadraticProgram.jl:16-17); the algorithm is the MATLAB twin's, SolveQuadraticProgram.m:289-325:
+#   active sets from the multipliers, g = [-q; l_L; u_U], K = [P A_L' A_U'; A_L 0 0; A_U 0 0],
+#   KK = K + blkdiag(delta I, -delta I); numPolishItr rounds of iterative refinement
+#       tt = minres(KK, g - K t, tol, maxit, x0 = tt);  stop at the first failure;  t += tt
+#   and x = t[1:n] only if the last minres call converged.
+# One deliberate change: the MATLAB code picks the active rows by the SIGN of y, which puts rows whose
+# multiplier is rounding noise around 0 into an active set with whichever bound the noise points at; here a row is
+# active only if its multiplier exceeds its distance to the bound (OSQP's rule, Stellato et al. 2020, section 5.4):
+#   lower active  <=>  z_i - l_i < -y_i        upper active  <=>  u_i - z_i < y_i .
+# The reduced system is kept at full size: inactive rows carry the equation -delta nu_i = 0, so their entries stay
+# exactly zero and the operator is two masked passes over A and H = [P A'].
+# --------------------------------------------------------------------------------------------
+
+def minres(op, b, tol, maxit, x0):
+    """MINRES (Paige & Saunders 1975) without preconditioner, stopping rule of MATLAB's ``minres``: estimated
+    ``||b - A x|| <= tol ||b||``.  Returns ``(x, flag, iterations)`` with flag 0 = converged, 1 = maxit reached."""
+    x = np.array(x0, dtype=np.float64)
+    bnorm = float(np.sqrt(np.dot(b, b)))
+    Y = [None, None, None]
+    Y[0] = b - op(x)
+    beta1 = float(np.sqrt(np.dot(Y[0], Y[0])))
+    tolb = tol * bnorm
+    if beta1 <= tolb:
+        return x, 0, 0
+    W = [np.zeros_like(x), np.zeros_like(x), np.zeros_like(x)]
+    oldb, beta, dbar, epsln, phibar, cs, sn = 0.0, beta1, 0.0, 0.0, beta1, -1.0, 0.0
+    v = Y[0] / beta
+    for k in range(1, int(maxit) + 1):
+        y = op(v)
+        if k >= 2:
+            y = y - (beta / oldb) * Y[(k - 2) % 3]
+        alfa = float(np.dot(v, y))
+        y = y - (alfa / beta) * Y[(k - 1) % 3]
+        Y[k % 3] = y
+        oldb = beta
+        beta = float(np.sqrt(np.dot(y, y)))
+        oldeps = epsln
+        delta = cs * dbar + sn * alfa
+        gbar = sn * dbar - cs * alfa
+        epsln = sn * beta
+        dbar = -cs * beta
+        gamma = max(float(np.sqrt(gbar * gbar + beta * beta)), np.finfo(np.float64).eps)
+        cs = gbar / gamma
+        sn = beta / gamma
+        phi = cs * phibar
+        phibar = sn * phibar
+        W[k % 3] = (v - oldeps * W[(k - 2) % 3] - delta * W[(k - 1) % 3]) * (1.0 / gamma)
+        x = x + phi * W[k % 3]
+        if phibar <= tolb or beta == 0.0:
+            return x, 0, k
+        v = y / beta
+    return x, 1, int(maxit)
+
+
+def polish_active_sets(vL, vU, vZ, vY):
+    """0 = inactive, 1 = lower bound active, 2 = upper bound active."""
+    lower = (vZ - vL) < -vY
+    upper = ~lower & ((vU - vZ) < vY)
+    return np.where(lower, 1, np.where(upper, 2, 0))
+
+
+def polish_solution(vX, mP, vQ, mA, vL, vU, vZ, vY, delta, numItrPolish, epsMinres, numItrMinres):
+    """Polish ``vX`` in place; returns ``{"applied", "minres_iters", "n_active"}``."""
+    n, m = mP.shape[0], mA.shape[0]
+    act = polish_active_sets(vL, vU, vZ, vY)
+    mask = (act != 0).astype(np.float64)
+    g = np.concatenate([-np.asarray(vQ, dtype=np.float64),
+                        np.where(act == 1, vL, np.where(act == 2, vU, 0.0))])
+    mAt = sp.csr_matrix(mA.T)
+
+    def K(t, reg):
+        top = mP @ t[:n] + mAt @ t[n:] + reg * t[:n]
+        bot = mask * (mA @ t[:n]) - reg * t[n:]
+        return np.concatenate([top, bot])
+
+    t = np.zeros(n + m)
+    tt = np.zeros(n + m)
+    flag, total = -1, 0
+    for _ in range(int(numItrPolish)):
+        tt, flag, its = minres(lambda v: K(v, delta), g - K(t, 0.0), epsMinres, numItrMinres, tt)
+        total += its
+        if flag:
+            break
+        t = t + tt
+    applied = flag == 0
+    if applied:
+        vX[:] = t[:n]
+    return {"applied": bool(applied), "minres_iters": total, "n_active": int(np.count_nonzero(act)), "nu": t[n:]}
 
 
 def _limit_scaling(v):

@@ -38,13 +38,14 @@ class Settings(C.Structure):
 
 class Info(C.Structure):
     """``qpb200_info`` (include/qpb200.h)."""
-    _fields_ = [("conv_flag", C.c_int32), ("reserved", C.c_int32), ("iterations", C.c_int64),
+    _fields_ = [("conv_flag", C.c_int32), ("polish_status", C.c_int32), ("iterations", C.c_int64),
                 ("rho_final", C.c_double), ("res_prim", C.c_double), ("res_dual", C.c_double),
                 ("rho_updates", C.c_int64), ("pcg_iters_total", C.c_int64), ("pcg_maxed", C.c_int64),
-                ("solve_ms", C.c_double), ("setup_ms", C.c_double), ("kernel_launches", C.c_int64)]
+                ("solve_ms", C.c_double), ("setup_ms", C.c_double), ("kernel_launches", C.c_int64),
+                ("polish_minres_iters", C.c_int64), ("polish_active", C.c_int64)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 # every symbol include/qpb200.h declares

@@ -194,7 +194,7 @@ int SparseSolver::init(int64_t n64, int64_t m64, const int64_t *Pp, const int64_
         } else {
             for (const void *fn : {(const void *)admm_kernel<1, false, false>, (const void *)admm_kernel<1, true, false>,
                                    (const void *)admm_kernel<1, false, true>, (const void *)admm_kernel<1, true, true>,
-                                   (const void *)admm_kernel<1, false, false, true>}) {
+                                   (const void *)admm_kernel<1, false, false, true>, (const void *)polish_kernel<1>}) {
                 if ((rc = prep_kernel(fn, &tmp))) return rc;
                 per_sm = std::min(per_sm, tmp);
             }
@@ -467,8 +467,14 @@ int SparseSolver::solve(double *x_inout, double *z_out, double *y_out, qpb200_in
         QPB_CUDA(cudaMemsetAsync(sync_words, 0, 64 * sizeof(unsigned long long), stream));   // the barrier epochs restart with the launch
         if ((rc = refactor(part.rho_final, &launches))) return rc;
     }
+    const bool do_polish = settings.reserved_i[QPB200_RSV_POLISH] != 0;
+    if (do_polish) {
+        if ((rc = polish())) return rc;
+        ++launches;
+    }
     QPB_CUDA(cudaEventRecord(ev1, stream));
     QPB_CUDA(cudaMemcpyAsync(x_inout, prob.XY, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    if (do_polish) QPB_CUDA(cudaMemcpyAsync(pol_out, pol.out, sizeof(pol_out), cudaMemcpyDeviceToHost, stream));
     if (z_out && m) QPB_CUDA(cudaMemcpyAsync(z_out, prob.z, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, stream));
     if (y_out && m) QPB_CUDA(cudaMemcpyAsync(y_out, prob.XY + n, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, stream));
     AdmmInfoDev hi;
@@ -503,10 +509,36 @@ int SparseSolver::solve(double *x_inout, double *z_out, double *y_out, qpb200_in
         info->solve_ms = ms;
         info->setup_ms = setup_ms;
         info->kernel_launches = launches;
+        if (do_polish) {
+            info->polish_status = (int32_t)pol_out[0];
+            info->polish_minres_iters = pol_out[1];
+            info->polish_active = pol_out[2];
+        }
     }
     if (getenv("QPB200_TIMING"))
         fprintf(stderr, "[qpb200_solve] device %.1f ms, wall %.1f ms\n", ms,
                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count());
+    return QPB200_OK;
+}
+
+// Polish (polish_kernels.cuh): active sets, numItrPolish refinement rounds, MINRES on the masked KKT operator -- one
+// cooperative launch behind the ADMM kernel on the same stream; x (the n-part of XY) is replaced on success.
+int SparseSolver::polish() {
+    const size_t N = (size_t)n + (size_t)m;
+    if (!pol_ready) {
+        double **bufs[] = {&pol.T, &pol.TT, &pol.G, &pol.B, &pol.V, &pol.Y[0], &pol.Y[1], &pol.Y[2], &pol.W[0], &pol.W[1], &pol.W[2]};
+        for (double **b : bufs) QPB_CUDA(arena.alloc(b, N + 8, true));
+        QPB_CUDA(arena.alloc(&pol.mask, (size_t)m + 8, true));
+        QPB_CUDA(arena.alloc(&pol.out, 4, true));
+        pol_ready = true;
+    }
+    pol.delta = settings.delta;
+    pol.tol = settings.minres_eps;
+    pol.polish_iter = settings.polish_iter;
+    pol.minres_iter = settings.minres_iter;
+    QPB_CUDA(cudaMemsetAsync(sync_words, 0, 64 * sizeof(unsigned long long), stream));   // barrier epochs restart with the launch
+    void *args[] = {(void *)&prob, (void *)&pol};
+    QPB_CUDA(cudaLaunchCooperativeKernel((const void *)polish_kernel<1>, dim3(grid), dim3(kThreads), args, sizeof(SpmvSmem), stream));
     return QPB200_OK;
 }
 

@@ -1,6 +1,7 @@
 // sparse_solver.h -- the object behind a qpb200_handle (single GPU, sparse QP).
 #pragma once
 #include "admm_kernels.cuh"
+#include "polish_kernels.cuh"
 #include "host_common.h"
 
 namespace qpb {
@@ -43,6 +44,11 @@ struct SparseSolver {
     int settings_to_dev(const qpb200_settings &s);
     int reset_state(const double *x0_host);
     int launch_admm();
+    // solution polish (settings.reserved_i[QPB200_RSV_POLISH]): buffers allocated at the first use
+    PolishDev pol{};
+    bool pol_ready = false;
+    long long pol_out[3] = {0, 0, 0};
+    int polish();                                  // one cooperative launch on `stream` after the ADMM loop
     int refactor(double rho, int64_t *launches);   // build K for rho and invert it in place
     bool one_reduction() const;   // which arrangement of the (P)CG recurrence admm_kernel runs (QPB200_RSV_CG_RECURRENCE)
     int solve(double *x_inout, double *z_out, double *y_out, qpb200_info *info);

@@ -62,7 +62,10 @@ _DEFAULTS = dict(numIterations=5000, epsAbs=1e-6, epsRel=1e-6, rho=1.0, sigma=1e
                  numItrScaling=0,
                  # arrangement of the (P)CG recurrence: "standard" (IterativeSolvers' CGIterable / PCGIterable statement
                  # order), "one_reduction" (three grid barriers per CG iteration), "auto" (by problem size)
-                 cgRecurrence="auto")
+                 cgRecurrence="auto",
+                 # polish after the ADMM loop (SolveQuadraticProgram.m:289-325; the Julia driver ignores its polish
+                 # keywords, so False is the reference's behaviour): uses numItrPolish, delta, epsMinres, numItrMinres
+                 polish=False)
 
 
 def make_settings(**kw) -> Settings:
@@ -90,6 +93,7 @@ def make_settings(**kw) -> Settings:
     s.spmv_loader = {"auto": 0, "ldg": 1, "tma": 2, "tma_pipe": 3}[str(opts["spmvLoader"])]
     s.reserved_i[2] = int(opts["numItrScaling"])          # QPB200_RSV_SCALING_ITERS
     s.reserved_i[4] = {"auto": 0, "standard": 1, "one_reduction": 2}[str(opts["cgRecurrence"])]   # QPB200_RSV_CG_RECURRENCE
+    s.reserved_i[5] = int(bool(opts["polish"]))           # QPB200_RSV_POLISH
     return s
 
 
