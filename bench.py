@@ -52,6 +52,23 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def load_fp64_peak():
+    """FP64 FMA peak for the dense-batch roofline: measured live by scripts/microbench/fp64_peak_bench (built by
+    scripts/microbench/Makefile, travels to the GPU box) when present, else the committed measurement, else nominal."""
+    exe = os.path.join(ROOT, "scripts", "microbench", "fp64_peak_bench")
+    try:
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=60, check=True).stdout
+        rec = json.loads(out.strip().splitlines()[-1])
+        return float(rec["dfma_tflops"]), f"measured in this run (scripts/microbench/fp64_peak_bench: DFMA {rec['dfma_tflops']} TF/s, DMMA {rec['dmma_tflops']} TF/s)"
+    except Exception:
+        pass
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "r2_fp64_peak.json")))
+        return float(rec["dfma_tflops"]), "profiles/r2_fp64_peak.json (scripts/microbench/fp64_peak_bench on a B200 of this pool)"
+    except Exception:
+        return 40.0, "nominal B200 FP64 (no measurement available)"
+
+
 def load_traffic(workload, world):
     """dram__bytes_read.sum + dram__bytes_write.sum of the timed kernel (one launch = one step), from the committed ncu
     capture of this very launch (profiles/r2_traffic.json, written by scripts/ncu_traffic.py); None when no capture of
@@ -258,11 +275,8 @@ def run_b200(args):
     # (rows of A / columns of P per rank, n-vector partial sums reduced in-kernel over NVLink) -> strong scaling.
     if world == 1:
         s = S.QPB200Solver(P, q, A, l, u, **kw)
-        presliced = None
     else:
-        from quadraticprogramsolver_b200 import partition
-        presliced = partition.slice_problem(P, A, l, u, rank, world)
-        s = S.QPB200DistSolver(P, q, A, l, u, presliced=presliced, **kw)
+        s = S.QPB200DistSolver(P, q, A, l, u, **kw)          # qpb200_dist_create_full: the library partitions the QP
     x = np.zeros(n)
     for _ in range(args.warmup):
         x[:] = 0.0
@@ -309,7 +323,7 @@ def run_b200(args):
                 xx = np.zeros(n)
                 fl = s.solve(xx)
                 return xx, fl, s.info
-            with S.QPB200DistSolver(P, q, A, l, u, presliced=presliced, **kk) as ds:
+            with S.QPB200DistSolver(P, q, A, l, u, **kk) as ds:
                 xx = np.zeros(n)
                 fl = ds.solve(xx)
                 return xx, fl, ds.info
@@ -321,15 +335,20 @@ def run_b200(args):
     s.close()
 
     # ---- end-to-end arm: host buffers -> create -> solve -> results on host, every step --------
+    Pp, Pi, Pv = S._csc_arrays(P)
+    Ap, Ai, Av = S._csc_arrays(A)
     if world == 1:
-        Pp, Pi, Pv = S._csc_arrays(P)
-        Ap, Ai, Av = S._csc_arrays(A)
         m_loc = m
+        h2d = Pp.nbytes + Pi.nbytes + Pv.nbytes + Ap.nbytes + Ai.nbytes + Av.nbytes + 8 * (2 * n + 2 * m_loc)
     else:
-        Pp, Pi, Pv = S._csc_arrays(presliced[0])
-        Ap, Ai, Av = S._csc_arrays(presliced[1])
-        m_loc = presliced[1].shape[0]
-    h2d = Pp.nbytes + Pi.nbytes + Pv.nbytes + Ap.nbytes + Ai.nbytes + Av.nbytes + 8 * (2 * n + 2 * m_loc)
+        # what this rank uploads: its slice (rows of A, columns of P) as the library cuts it; counted from the partition
+        from quadraticprogramsolver_b200 import partition
+        rb, cb = partition.plan(P, A, world)
+        i0, i1, j0, j1 = int(rb[rank]), int(rb[rank + 1]), int(cb[rank]), int(cb[rank + 1])
+        m_loc = i1 - i0
+        nnz_p = int(Pp[j1] - Pp[j0])
+        nnz_a = int(np.count_nonzero((Ai >= i0) & (Ai < i1)))
+        h2d = 16 * (nnz_p + nnz_a) + 8 * 2 * (n + 1) + 8 * (2 * n + 2 * m_loc)
     d2h = 8 * (n + 2 * m_loc)
 
     # The host buffers are what the reference caller owns: SparseMatrixCSC arrays (Int64 indices), q, l, u.
@@ -341,8 +360,9 @@ def run_b200(args):
         if world == 1:
             xx = np.zeros(n)
             return S.solve_csc_arrays(n, m, Parr, q64, Aarr, l64, u64, xx, want_zy=True, **kw)[1]
-        # the caller holds the whole P, A on the host: cutting this rank's slice out of them is part of every call
-        with S.QPB200DistSolver(P, q, A, l, u, **kw) as ds:
+        # the caller holds the whole P, A on the host (SparseMatrixCSC arrays): cutting this rank's slice out of them is
+        # part of every call (qpb200_dist_create_full)
+        with S.QPB200DistSolver(None, q64, None, l64, u64, arrays=(Parr, Aarr), **kw) as ds:
             xx = np.zeros(n)
             ds.solve(xx, want_zy=True)
             return ds.info
@@ -474,6 +494,7 @@ def run_cfg3(args):
         dist.all_reduce(t2, op=dist.ReduceOp.SUM)
         tot = [float(t[0]), float(t[1]), float(t2[0])]
     if rank == 0:
+        fp64_peak, fp64_src = load_fp64_peak()
         value = batch * args.steps / (tot[0] * 1e-3)
         flops = 2.0 * 16448.0 * tot[2]     # FMAs per ADMM iteration: 2 * 96 * 64 (A, A') + 2 * 2080 (L^-1, L^-T)
         line = {"metric": "qp_solves_per_s", "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
@@ -486,9 +507,9 @@ def run_cfg3(args):
                 "e2e": {"value": batch * e2e_steps / tot[1], "unit": "solves/s", "h2d_bytes_per_step": int(8 * (P.size + A.size + q.size + l.size + u.size + q.size)) * world,
                         "d2h_bytes_per_step": int(8 * q.size + 12 * len(q)) * world},
                 "gpu_launches": args.steps,
-                "roofline": {"bound": "fp64_fma", "achieved": flops / (tot[0] * 1e-3) / 1e12 / world, "peak": 40.0, "unit": "TFLOP/s",
-                             "frac": flops / (tot[0] * 1e-3) / 1e12 / world / 40.0, "traffic": None,
-                             "peak_source": "nominal B200 FP64 (no measured FP64 peak in MEASURED_PEAKS.json)",
+                "roofline": {"bound": "fp64_fma", "achieved": flops / (tot[0] * 1e-3) / 1e12 / world, "peak": fp64_peak, "unit": "TFLOP/s",
+                             "frac": flops / (tot[0] * 1e-3) / 1e12 / world / fp64_peak, "traffic": None,
+                             "peak_source": fp64_src,
                              "kernel": "dense_batch_kernel<96,2> (A and K^-1 register-resident during the iterations, shuffle reduce-scatters; DMMA only in the factorisation)"},
                 "admm_iters_per_s": tot[2] / (tot[0] * 1e-3)}
         if world == 1 and not args.no_cpu:

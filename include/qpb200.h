@@ -112,6 +112,8 @@ typedef struct qpb200_settings {
                                        the last MINRES solve converged.  Active rows: z_i - l_i < -y_i (lower),
                                        u_i - z_i < y_i (upper) instead of MATLAB's sign(y_i) -- see polish_kernels.cuh.     */
 
+#define QPB200_RSV_BATCH_CHUNK 6    /* qpb200_batch_solve_once: problems per pipeline chunk (0 = 4096)                */
+
 typedef struct qpb200_info {
     int32_t conv_flag;       /* QPB200_CONV_*                                                      */
     int32_t polish_status;   /* 0 = polish not requested, 1 = applied, 2 = MINRES did not converge (x untouched) */
@@ -177,6 +179,13 @@ int qpb200_batch_solve(qpb200_batch *h, double *X_inout, int32_t *flags, int64_t
  * the next qpb200_batch_solve uploads nothing but the start points.                                            */
 int qpb200_batch_update_vectors(qpb200_batch *h, const double *q, const double *l, const double *u);
 void qpb200_batch_destroy(qpb200_batch *h);
+/* A batch that is solved once (create + solve + destroy in one call, what SolveQuadraticProgramBatch does): the batch
+ * is cut into chunks of settings.reserved_i[QPB200_RSV_BATCH_CHUNK] problems (0 = 4096) and chunk c + 1 is uploaded
+ * while the kernel of chunk c runs; only two chunks are resident.  Same results as create + solve, bit for bit.
+ * info->solve_ms = sum of the chunks' kernel times, info->setup_ms = wall time of the whole call.                 */
+int qpb200_batch_solve_once(int64_t batch, int64_t n, int64_t m, const double *P, const double *A, const double *q,
+                            const double *l, const double *u, const qpb200_settings *settings, double *X_inout,
+                            int32_t *flags, int64_t *iters, qpb200_info *info);
 
 /* ---- one large sparse QP row-partitioned over several GPUs, one rank (process or thread) per GPU.
  * Rank r owns rows [row_begin, row_end) of A (and of l, u, z, y) and the same-numbered share of P's
@@ -195,6 +204,17 @@ int qpb200_dist_create(qpb200_handle **out, int32_t rank, int32_t nranks, const 
                        const int64_t *A_colptr, const int64_t *A_rowval, const double *A_nzval,
                        const double *q, const double *l_local, const double *u_local,
                        const qpb200_settings *settings, int32_t index_base);
+/* The same with the partition done inside: every rank passes the WHOLE QP as the caller holds it
+ * (P n x n, A m x n, q[n], l[m], u[m]); the library computes the nnz-balanced row blocks of A / column blocks of P,
+ * cuts this rank's slice out on all host threads (P's columns without a copy) and proceeds as qpb200_dist_create.
+ * qpb200_dist_rows returns the rows [row_begin, row_end) of A whose z, y this rank's qpb200_dist_solve returns.   */
+int qpb200_dist_create_full(qpb200_handle **out, int32_t rank, int32_t nranks, const void *nccl_unique_id,
+                            int64_t n, int64_t m,
+                            const int64_t *P_colptr, const int64_t *P_rowval, const double *P_nzval,
+                            const int64_t *A_colptr, const int64_t *A_rowval, const double *A_nzval,
+                            const double *q, const double *l, const double *u,
+                            const qpb200_settings *settings, int32_t index_base);
+int qpb200_dist_rows(qpb200_handle *h, int64_t *row_begin, int64_t *row_end);
 /* Collective: every rank calls it.  x_inout[n] (replicated), z_out/y_out[m_local] or NULL.        */
 int qpb200_dist_solve(qpb200_handle *h, double *x_inout, double *z_out, double *y_out, qpb200_info *info);
 
@@ -222,6 +242,18 @@ int qpb200_debug_equilibrate(int64_t n, int64_t m, const int64_t *P_colptr, cons
                              const double *A_nzval, const double *q, int32_t iters, int32_t index_base,
                              double *D_out, double *E_out, double *c_out, double *q_out, double *Pnzval_out,
                              double *Anzval_out);
+
+/* The partition qpb200_dist_create_full uses, without a device: row_bounds_out[nranks+1] (rows of A),
+ * col_bounds_out[nranks+1] (columns of P); returns nranks or an error < 0.  qpb200_debug_slice additionally cuts the
+ * slice of `rank`: bounds4_out = {row_begin, row_end, pcol_begin, pcol_end}, *p_off_out = first non-zero of P used,
+ * Pcolptr_out[n+1] relative to it, the row slice of A as CSC with local row indices (a_cap = capacity of the A arrays). */
+int64_t qpb200_debug_partition(int64_t n, int64_t m, const int64_t *P_colptr, const int64_t *A_colptr,
+                               const int64_t *A_rowval, int32_t index_base, int32_t nranks,
+                               int64_t *row_bounds_out, int64_t *col_bounds_out);
+int qpb200_debug_slice(int64_t n, int64_t m, const int64_t *P_colptr, const int64_t *A_colptr, const int64_t *A_rowval,
+                       const double *A_nzval, int32_t index_base, int32_t rank, int32_t nranks, int64_t *bounds4_out,
+                       int64_t *p_off_out, int64_t *Pcolptr_out, int64_t *Acolptr_out, int64_t *Arowval_out,
+                       double *Anzval_out, int64_t a_cap);
 
 #ifdef __cplusplus
 }

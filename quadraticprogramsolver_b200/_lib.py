@@ -55,8 +55,10 @@ EXPORTS = [
     "qpb200_destroy",
     "qpb200_apply", "qpb200_time_apply", "qpb200_apply_bytes",
     "qpb200_batch_create", "qpb200_batch_solve", "qpb200_batch_update_vectors", "qpb200_batch_destroy",
-    "qpb200_dist_unique_id", "qpb200_dist_create", "qpb200_dist_solve",
+    "qpb200_batch_solve_once",
+    "qpb200_dist_unique_id", "qpb200_dist_create", "qpb200_dist_create_full", "qpb200_dist_rows", "qpb200_dist_solve",
     "qpb200_debug_tile_plan", "qpb200_debug_tile_nnz", "qpb200_debug_equilibrate", "qpb200_debug_assemble_h",
+    "qpb200_debug_partition", "qpb200_debug_slice",
 ]
 
 _lib = None
@@ -92,12 +94,17 @@ def load():
     lib.qpb200_batch_create.argtypes = [C.POINTER(pv), C.c_int64, C.c_int64, C.c_int64, pd, pd, pd, pd, pd,
                                         C.POINTER(Settings)]
     lib.qpb200_batch_solve.argtypes = [pv, pd, C.POINTER(C.c_int32), p64, C.POINTER(Info)]
+    lib.qpb200_batch_solve_once.argtypes = [C.c_int64, C.c_int64, C.c_int64, pd, pd, pd, pd, pd, C.POINTER(Settings), pd,
+                                            C.POINTER(C.c_int32), p64, C.POINTER(Info)]
     lib.qpb200_batch_update_vectors.argtypes = [pv, pd, pd, pd]
     lib.qpb200_batch_destroy.argtypes = [pv]
     lib.qpb200_batch_destroy.restype = None
     lib.qpb200_dist_unique_id.argtypes = [pv]
     lib.qpb200_dist_create.argtypes = [C.POINTER(pv), C.c_int32, C.c_int32, pv, C.c_int64, C.c_int64,
                                        p64, p64, pd, p64, p64, pd, pd, pd, pd, C.POINTER(Settings), C.c_int32]
+    lib.qpb200_dist_create_full.argtypes = [C.POINTER(pv), C.c_int32, C.c_int32, pv, C.c_int64, C.c_int64,
+                                            p64, p64, pd, p64, p64, pd, pd, pd, pd, C.POINTER(Settings), C.c_int32]
+    lib.qpb200_dist_rows.argtypes = [pv, p64, p64]
     lib.qpb200_dist_solve.argtypes = [pv, pd, pd, pd, C.POINTER(Info)]
     p32 = C.POINTER(C.c_int32)
     lib.qpb200_debug_tile_plan.argtypes = [C.c_int32, p32, C.c_int32, p32, C.c_int64, p32, p32]
@@ -108,6 +115,11 @@ def load():
     lib.qpb200_debug_equilibrate.restype = C.c_int
     lib.qpb200_debug_assemble_h.argtypes = [C.c_int64, C.c_int64, p64, p64, pd, p64, p64, pd, C.c_int32, p32, p32, p32, pd, pd, pd]
     lib.qpb200_debug_assemble_h.restype = C.c_int
+    lib.qpb200_debug_partition.argtypes = [C.c_int64, C.c_int64, p64, p64, p64, C.c_int32, C.c_int32, p64, p64]
+    lib.qpb200_debug_partition.restype = C.c_int64
+    lib.qpb200_debug_slice.argtypes = [C.c_int64, C.c_int64, p64, p64, p64, pd, C.c_int32, C.c_int32, C.c_int32, p64, p64, p64,
+                                       p64, p64, pd, C.c_int64]
+    lib.qpb200_debug_slice.restype = C.c_int
     _lib = lib
     return lib
 

@@ -7,6 +7,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -58,33 +59,44 @@ static NcclApi *nccl_api() {
             return ::qpb::fail(QPB200_ERR_NCCL, "%s failed: %s (%s:%d)", #call, api->GetErrorString(r_), __FILE__, __LINE__); \
     } while (0)
 
+// Process-wide caches, one entry per device (one rank per GPU, whether the ranks are processes or threads of one
+// process), guarded by a mutex and reference counted: an entry that a live handle uses is never destroyed or
+// replaced -- a handle that cannot take the entry gets private resources it owns and frees itself.
+constexpr int kMaxDevices = 64;
+static std::mutex &cache_mutex() {
+    static std::mutex m;
+    return m;
+}
 struct CommCacheEntry {
     ncclComm_t comm = nullptr;
-    int rank = -1, nranks = 0, device = -1;
+    int rank = -1, nranks = 0, users = 0;
 };
-static CommCacheEntry &comm_cache() {
-    static CommCacheEntry e;
-    return e;
+static CommCacheEntry &comm_cache(int device) {
+    static CommCacheEntry e[kMaxDevices];
+    return e[device];
 }
 
 // Peer-visible region of this process, kept across handles like the communicator: cudaMalloc + IPC export +
 // (R-1) cudaIpcOpenMemHandle at create and the matching close/free at destroy cost 100-500 ms per handle --
-// as much as a whole solve on 8 GPUs.  One entry; a handle created while another one owns it allocates privately.
+// as much as a whole solve on 8 GPUs.  One entry per device; a handle created while another one owns it allocates
+// privately.
 struct PeerRegionCache {
     bool in_use = false;
-    int device = -1, rank = -1, nranks = 0;
+    int rank = -1, nranks = 0;
     double *region = nullptr;
     size_t doubles = 0;
     void *opened[kMaxPeers] = {nullptr};
 };
-static PeerRegionCache &region_cache() {
-    static PeerRegionCache c;
-    return c;
+static PeerRegionCache &region_cache(int device) {
+    static PeerRegionCache c[kMaxDevices];
+    return c[device];
 }
 
 struct DistContext {
-    int rank = 0, nranks = 1;
+    int rank = 0, nranks = 1, device = -1;
     ncclComm_t comm = nullptr;
+    bool comm_cached = false;              // comm belongs to comm_cache(device) (users counted), else this handle owns it
+    int64_t row_begin = 0, row_end = 0;    // rows of A this rank owns (qpb200_dist_create_full; -1 when pre-sliced)
     DistBuffers buf{};
     DistState *host_state = nullptr;   // pinned mirror (2 slots: the CG loop runs one step ahead of the host)
     cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -102,12 +114,15 @@ struct DistContext {
 void dist_destroy(DistContext *d) {
     if (!d) return;
     NcclApi *api = nccl_api();
-    // the communicator is process-cached (comm_cache): creating one costs ~1 s, re-solves / new handles reuse it
-    (void)api;
     if (d->host_state) cudaFreeHost(d->host_state);
     for (auto &e : d->ev) if (e) cudaEventDestroy(e);
+    std::lock_guard<std::mutex> g(cache_mutex());
+    // the cached communicator outlives the handle (creating one costs ~1 s, re-solves / new handles reuse it);
+    // a private one goes with its handle
+    if (d->comm_cached) comm_cache(d->device).users -= 1;
+    else if (d->comm && api) api->CommDestroy(d->comm);
     if (d->region_cached) {
-        region_cache().in_use = false;     // mappings stay open for the next handle of this process
+        region_cache(d->device).in_use = false;     // mappings stay open for the next handle on this device
     } else {
         for (void *o : d->opened) if (o) cudaIpcCloseMemHandle(o);
         if (d->region) cudaFree(d->region);
@@ -236,23 +251,47 @@ int dist_init(SparseSolver &s, DistContext *&out, int rank, int nranks, const vo
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
     std::memcpy(&id, unique_id, sizeof(id));
     QPB_CUDA(cudaSetDevice(s.device));
+    if (s.device < 0 || s.device >= kMaxDevices) return fail(QPB200_ERR_ARG, "qpb200_dist_create: device ordinal %d out of range", s.device);
+    d->device = s.device;
     {
         // An all-zero id means "reuse this process's communicator for (device, rank, nranks)": ncclCommInitRank
         // is a ~1 s collective, far more than a solve, and a caller that re-solves related QPs should not pay it
-        // per handle.  Communicators live until process exit.
+        // per handle.  A fresh id replaces the cached communicator only when no live handle uses it; otherwise the
+        // new communicator is private to this handle.  (Every rank takes the same branch as long as the ranks
+        // create and destroy their handles in the same order, which the collective API requires anyway.)
         bool zero_id = true;
         for (size_t i = 0; i < sizeof(id); ++i) zero_id = zero_id && reinterpret_cast<const unsigned char *>(&id)[i] == 0;
-        CommCacheEntry &e = comm_cache();
+        std::unique_lock<std::mutex> g(cache_mutex());
+        CommCacheEntry &e = comm_cache(s.device);
         if (zero_id) {
-            if (!e.comm || e.rank != rank || e.nranks != nranks || e.device != s.device)
+            if (!e.comm || e.rank != rank || e.nranks != nranks)
                 return fail(QPB200_ERR_NCCL, "qpb200_dist_create: zero NCCL id but no cached communicator for rank %d/%d on device %d", rank, nranks, s.device);
-        } else {
-            if (e.comm) api->CommDestroy(e.comm);
+            e.users += 1;
+            d->comm = e.comm;
+            d->comm_cached = true;
+        } else if (e.users == 0) {
+            ncclComm_t old = e.comm;
             e.comm = nullptr;
-            QPB_NCCL(api->CommInitRank(&e.comm, nranks, id, rank));
-            e.rank = rank; e.nranks = nranks; e.device = s.device;
+            e.users = 1;                              // reserved while the (collective, blocking) init runs unlocked
+            e.rank = rank; e.nranks = nranks;
+            d->comm_cached = true;
+            g.unlock();
+            if (old) api->CommDestroy(old);
+            ncclComm_t fresh = nullptr;
+            const ncclResult_t r = api->CommInitRank(&fresh, nranks, id, rank);
+            g.lock();
+            if (r != ncclSuccess) {
+                e.users = 0;
+                e.rank = -1;
+                d->comm_cached = false;
+                return fail(QPB200_ERR_NCCL, "ncclCommInitRank failed: %s", api->GetErrorString(r));
+            }
+            e.comm = fresh;
+            d->comm = fresh;
+        } else {
+            g.unlock();
+            QPB_NCCL(api->CommInitRank(&d->comm, nranks, id, rank));   // owned by this handle
         }
-        d->comm = e.comm;
     }
     QPB_CUDA(s.arena.alloc(&d->buf.state, 1, true));
     QPB_CUDA(s.arena.alloc(&d->buf.wbuf, (size_t)s.n + 8, true));
@@ -275,8 +314,9 @@ int dist_init(SparseSolver &s, DistContext *&out, int rank, int nranks, const vo
     const int mode = s.settings.reserved_i[1];
     if (mode != 1) {
         const int prc = peer_init(s, *d);
-        if (prc != QPB200_OK && mode == 2) return prc;
-        // all ranks must agree: use the peer path only if every rank could map every peer
+        const std::string peer_msg = prc != QPB200_OK ? last_error() : std::string();
+        // all ranks must agree: use the peer path only if every rank could map every peer (the agreement runs BEFORE
+        // any rank returns an error, else the others would wait in the all-reduce forever)
         double ok = d->peer_ok ? 1.0 : 0.0, *dok = nullptr;
         QPB_CUDA(s.arena.alloc(&dok, 2, true));
         QPB_CUDA(cudaMemcpyAsync(dok, &ok, sizeof(double), cudaMemcpyHostToDevice, s.stream));
@@ -284,7 +324,9 @@ int dist_init(SparseSolver &s, DistContext *&out, int rank, int nranks, const vo
         QPB_CUDA(cudaMemcpyAsync(&ok, dok, sizeof(double), cudaMemcpyDeviceToHost, s.stream));
         QPB_CUDA(cudaStreamSynchronize(s.stream));
         d->peer_ok = ok > 0.5;
-        if (!d->peer_ok && mode == 2) return fail(QPB200_ERR_CUDA, "peer-memory path requested but not available on every rank");
+        if (!d->peer_ok && mode == 2)
+            return fail(QPB200_ERR_CUDA, "peer-memory path requested but not available on every rank%s%s", peer_msg.empty() ? "" : ": ",
+                        peer_msg.c_str());
     }
     return QPB200_OK;
 }
@@ -323,21 +365,35 @@ static int peer_init(SparseSolver &s, DistContext &d) {
     const size_t off_XG = off; off += pair;
     d.region_doubles = off;
     // ---- collective decision: reuse the process-cached region + mappings only if EVERY rank can
-    PeerRegionCache &rc = region_cache();
-    const bool mine_ok = !rc.in_use && rc.region && rc.device == s.device && rc.rank == d.rank && rc.nranks == d.nranks && rc.doubles >= off;
+    // (the entry of this device is only touched by the one rank that drives the device; the lock covers the flags)
+    PeerRegionCache &rc = region_cache(s.device);
+    bool mine_ok;
+    {
+        std::lock_guard<std::mutex> g(cache_mutex());
+        mine_ok = !rc.in_use && rc.region && rc.rank == d.rank && rc.nranks == d.nranks && rc.doubles >= off;
+        if (mine_ok) rc.in_use = true;               // reserved; released below if the ranks do not all agree
+    }
     double cannot = mine_ok ? 0.0 : 1.0;
     QPB_CUDA(cudaMemcpyAsync(dm, &cannot, sizeof(double), cudaMemcpyHostToDevice, s.stream));
     QPB_NCCL(api->AllReduce(dm, dm, 1, ncclDouble, ncclMax, d.comm, s.stream));
     QPB_CUDA(cudaMemcpyAsync(&cannot, dm, sizeof(double), cudaMemcpyDeviceToHost, s.stream));
     QPB_CUDA(cudaStreamSynchronize(s.stream));
+    if (cannot >= 0.5 && mine_ok) {
+        std::lock_guard<std::mutex> g(cache_mutex());
+        rc.in_use = false;
+    }
     if (cannot < 0.5) {
-        rc.in_use = true;
         d.region_cached = true;
         d.region = rc.region;
         QPB_CUDA(cudaMemsetAsync(d.region, 0, off * sizeof(double), s.stream));
         for (int q = 0; q < d.nranks; ++q) pd.region[q] = q == d.rank ? d.region : static_cast<double *>(rc.opened[q]);
     } else {
-        const bool own_cache = !rc.in_use;       // nobody holds the entry: replace it; else allocate privately
+        bool own_cache;                          // nobody holds the entry: replace it; else allocate privately
+        {
+            std::lock_guard<std::mutex> g(cache_mutex());
+            own_cache = !rc.in_use;
+            if (own_cache) rc.in_use = true;
+        }
         if (own_cache) {
             for (void *&o : rc.opened) {
                 if (o) cudaIpcCloseMemHandle(o);
@@ -374,14 +430,19 @@ static int peer_init(SparseSolver &s, DistContext &d) {
             cudaError_t e = cudaIpcOpenMemHandle(&ptr, all[(size_t)q], cudaIpcMemLazyEnablePeerAccess);
             if (e != cudaSuccess) {
                 cudaGetLastError();
+                if (own_cache) {                 // the entry was reserved above: release it empty; dist_destroy frees ours
+                    std::lock_guard<std::mutex> g(cache_mutex());
+                    rc.in_use = false;
+                    rc.region = nullptr;
+                    rc.doubles = 0;
+                }
                 return fail(QPB200_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s -- peer path unavailable", q, cudaGetErrorString(e));
             }
             d.opened[q] = ptr;
             pd.region[q] = static_cast<double *>(ptr);
         }
         if (own_cache) {                         // hand the new region to the cache; this handle borrows it
-            rc.in_use = true;
-            rc.device = s.device; rc.rank = d.rank; rc.nranks = d.nranks;
+            rc.rank = d.rank; rc.nranks = d.nranks;
             rc.region = d.region; rc.doubles = off;
             for (int q = 0; q < kMaxPeers; ++q) rc.opened[q] = d.opened[q];
             d.region_cached = true;
@@ -485,17 +546,85 @@ int qpb200_dist_create(qpb200_handle **out, int32_t rank, int32_t nranks, const 
     qpb200_settings s;
     if (settings) s = *settings;
     else qpb200_default_settings(&s);
+    set_host_thread_share(nranks);                 // the ranks of one node share its cores
     if (s.reserved_i[QPB200_RSV_SCALING_ITERS] != 0)
         return fail(QPB200_ERR_ARG, "qpb200_dist_create: equilibration needs column norms over all ranks' rows; not implemented for the row-partitioned path");
     qpb200_handle *h = new (std::nothrow) qpb200_handle();
     if (!h) return fail(QPB200_ERR_ARG, "out of host memory");
     int rc = h->solver.init(n, m_local, P_colptr, P_rowval, P_nzval, A_colptr, A_rowval, A_nzval, q, l_local, u_local, s, index_base);
     if (rc == QPB200_OK) rc = dist_init(h->solver, h->dist, rank, nranks, nccl_unique_id);
+    if (rc == QPB200_OK) h->dist->row_begin = h->dist->row_end = -1;   // caller-made slice (qpb200_dist_create_full fills them in)
     if (rc != QPB200_OK) {
         qpb200_destroy(h);
         return rc;
     }
     *out = h;
+    return QPB200_OK;
+}
+
+int qpb200_dist_create_full(qpb200_handle **out, int32_t rank, int32_t nranks, const void *nccl_unique_id, int64_t n,
+                            int64_t m, const int64_t *P_colptr, const int64_t *P_rowval, const double *P_nzval,
+                            const int64_t *A_colptr, const int64_t *A_rowval, const double *A_nzval, const double *q,
+                            const double *l, const double *u, const qpb200_settings *settings, int32_t index_base) {
+    if (!out) return fail(QPB200_ERR_ARG, "qpb200_dist_create_full: out is NULL");
+    *out = nullptr;
+    if (n <= 0 || m < 0 || nranks < 1 || rank < 0 || rank >= nranks || (index_base != 0 && index_base != 1))
+        return fail(QPB200_ERR_ARG, "qpb200_dist_create_full: bad n / m / rank / nranks / index_base");
+    if (!q || (m > 0 && (!l || !u))) return fail(QPB200_ERR_ARG, "q, l, u must not be NULL");
+    set_host_thread_share(nranks);                 // the ranks of one node share its cores
+    int rc = validate_csc("P", n, n, P_colptr, P_rowval, P_nzval, index_base);
+    if (rc) return rc;
+    if ((rc = validate_csc("A", m, n, A_colptr, A_rowval, A_nzval, index_base))) return rc;
+    std::vector<int64_t> rows, cols;
+    dist_plan(n, m, P_colptr, A_colptr, A_rowval, index_base, nranks, rows, cols);
+    DistSlice sl;
+    dist_slice(n, m, P_colptr, A_colptr, A_rowval, A_nzval, index_base, rank, rows, cols, sl);
+    rc = qpb200_dist_create(out, rank, nranks, nccl_unique_id, n, sl.i1 - sl.i0, sl.Pcolptr.data(), P_rowval + sl.p_off,
+                            P_nzval + sl.p_off, sl.Acolptr.data(), sl.Arowval.data(), sl.Anzval.data(), q,
+                            m ? l + sl.i0 : l, m ? u + sl.i0 : u, settings, index_base);
+    if (rc == QPB200_OK) {
+        (*out)->dist->row_begin = sl.i0;
+        (*out)->dist->row_end = sl.i1;
+    }
+    return rc;
+}
+
+int qpb200_dist_rows(qpb200_handle *h, int64_t *row_begin, int64_t *row_end) {
+    if (!h || !h->dist) return fail(QPB200_ERR_ARG, "qpb200_dist_rows: not a distributed handle");
+    if (h->dist->row_end < 0) return fail(QPB200_ERR_ARG, "qpb200_dist_rows: the handle was created from a caller-made slice");
+    if (row_begin) *row_begin = h->dist->row_begin;
+    if (row_end) *row_end = h->dist->row_end;
+    return QPB200_OK;
+}
+
+int64_t qpb200_debug_partition(int64_t n, int64_t m, const int64_t *P_colptr, const int64_t *A_colptr, const int64_t *A_rowval,
+                               int32_t index_base, int32_t nranks, int64_t *row_bounds_out, int64_t *col_bounds_out) {
+    if (n <= 0 || m < 0 || nranks < 1 || !P_colptr || !A_colptr) return fail(QPB200_ERR_ARG, "qpb200_debug_partition: bad argument");
+    std::vector<int64_t> rows, cols;
+    dist_plan(n, m, P_colptr, A_colptr, A_rowval, index_base, nranks, rows, cols);
+    if (row_bounds_out) std::copy(rows.begin(), rows.end(), row_bounds_out);
+    if (col_bounds_out) std::copy(cols.begin(), cols.end(), col_bounds_out);
+    return nranks;
+}
+
+int qpb200_debug_slice(int64_t n, int64_t m, const int64_t *P_colptr, const int64_t *A_colptr, const int64_t *A_rowval,
+                       const double *A_nzval, int32_t index_base, int32_t rank, int32_t nranks, int64_t *bounds4_out,
+                       int64_t *p_off_out, int64_t *Pcolptr_out, int64_t *Acolptr_out, int64_t *Arowval_out, double *Anzval_out,
+                       int64_t a_cap) {
+    if (n <= 0 || m < 0 || nranks < 1 || rank < 0 || rank >= nranks) return fail(QPB200_ERR_ARG, "qpb200_debug_slice: bad argument");
+    std::vector<int64_t> rows, cols;
+    dist_plan(n, m, P_colptr, A_colptr, A_rowval, index_base, nranks, rows, cols);
+    DistSlice sl;
+    dist_slice(n, m, P_colptr, A_colptr, A_rowval, A_nzval, index_base, rank, rows, cols, sl);
+    if (bounds4_out) { bounds4_out[0] = sl.i0; bounds4_out[1] = sl.i1; bounds4_out[2] = sl.j0; bounds4_out[3] = sl.j1; }
+    if (p_off_out) *p_off_out = sl.p_off;
+    if (Pcolptr_out) std::copy(sl.Pcolptr.begin(), sl.Pcolptr.end(), Pcolptr_out);
+    if (Acolptr_out) std::copy(sl.Acolptr.begin(), sl.Acolptr.end(), Acolptr_out);
+    const int64_t nnz = sl.Acolptr[(size_t)n] - index_base;
+    if (nnz <= a_cap) {
+        if (Arowval_out) std::copy(sl.Arowval.begin(), sl.Arowval.begin() + nnz, Arowval_out);
+        if (Anzval_out) std::copy(sl.Anzval.begin(), sl.Anzval.begin() + nnz, Anzval_out);
+    }
     return QPB200_OK;
 }
 

@@ -13,13 +13,21 @@
 
 namespace qpb {
 
+static std::atomic<int> g_thread_share{1};
+void set_host_thread_share(int ranks_on_node) { g_thread_share = std::max(1, ranks_on_node); }
+
+// QPB200_HOST_THREADS, else OMP_NUM_THREADS when it asks for more than one thread (torch.distributed.run exports
+// OMP_NUM_THREADS=1 for every rank: that is a default, not a request), else all hardware threads; capped at 32 and
+// divided by the number of ranks that share the node (qpb200_dist_create*)
 int host_threads() {
     static int nt = [] {
         const char *e = getenv("QPB200_HOST_THREADS");
-        int v = e ? atoi(e) : (int)std::thread::hardware_concurrency();
+        const char *o = getenv("OMP_NUM_THREADS");
+        int v = e ? atoi(e) : ((o && atoi(o) > 1) ? atoi(o) : (int)std::thread::hardware_concurrency());
         return std::max(1, std::min(v, 32));
     }();
-    return nt;
+    if (getenv("QPB200_HOST_THREADS")) return nt;
+    return std::max(1, std::min(nt, (int)std::thread::hardware_concurrency() / g_thread_share.load()));
 }
 
 // fn(t, begin, end) on contiguous chunks of [0, count) -- plain std::thread, no OpenMP dependency

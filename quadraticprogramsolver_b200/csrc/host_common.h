@@ -164,4 +164,20 @@ cudaError_t staged_upload(void *dst_dev, const double *src_host, size_t count, c
 
 int check_device(int device);   // 0 or QPB200_ERR_DEVICE / QPB200_ERR_CUDA
 
+// ---- partition of one QP over R ranks (dist_partition.cpp)
+struct DistSlice {
+    int64_t i0 = 0, i1 = 0, j0 = 0, j1 = 0;   // rows of A / columns of P owned by the rank
+    int64_t p_off = 0;                        // first non-zero of P the slice uses (offset into the caller's arrays)
+    std::vector<int64_t> Pcolptr;             // n + 1, relative to p_off
+    std::vector<int64_t> Acolptr, Arowval;    // row slice of A as CSC with local row indices
+    std::vector<double> Anzval;
+};
+void balanced_blocks(const int64_t *counts, int64_t len, int parts, std::vector<int64_t> &bounds);
+void dist_plan(int64_t n, int64_t m, const int64_t *Pp, const int64_t *Ap, const int64_t *Ai, int64_t base, int nranks,
+               std::vector<int64_t> &rows, std::vector<int64_t> &cols);
+void dist_slice(int64_t n, int64_t m, const int64_t *Pp, const int64_t *Ap, const int64_t *Ai, const double *Av, int64_t base,
+                int rank, const std::vector<int64_t> &rows, const std::vector<int64_t> &cols, DistSlice &out);
+// Host threads of this process are divided by `ranks_on_node` (one process per GPU shares the node's cores)
+void set_host_thread_share(int ranks_on_node);
+
 }  // namespace qpb

@@ -276,13 +276,7 @@ class QPB200Batch:
             raise ValueError("P must be [batch, n, n] and A [batch, n, m] (column-major m x n blocks)")
         if q.shape != (self.batch, self.n) or l.shape != (self.batch, self.m) or u.shape != (self.batch, self.m):
             raise ValueError("dimension mismatch in q, l or u")
-        kw.setdefault("linSolver", "cholesky")
-        unblocked = bool(kw.pop("unblockedCholesky", False))
-        # A/B switch of the n = 64, m <= 96 kernel: "smem" = products out of shared memory, "regs" = A in registers
-        variant = {"auto": 0, "smem": 1, "regs": 2, "regs_ak": 3}[kw.pop("denseVariant", "auto")]
-        self.settings = make_settings(**kw)
-        self.settings.reserved_i[0] = 1 if unblocked else 0
-        self.settings.reserved_i[3] = variant                # QPB200_RSV_DENSE_VARIANT
+        self.settings = _batch_settings(kw)
         self._h = C.c_void_p()
         _lib.check(lib.qpb200_batch_create(C.byref(self._h), self.batch, self.n, self.m, _pd(P), _pd(A_cm), _pd(q), _pd(l),
                                            _pd(u), C.byref(self.settings)))
@@ -333,13 +327,46 @@ class QPB200Batch:
             pass
 
 
-def SolveQuadraticProgramBatch(P, q, A_cm, l, u, X0=None, **kw):
+def _batch_settings(kw):
+    kw = dict(kw)
+    kw.setdefault("linSolver", "cholesky")
+    unblocked = bool(kw.pop("unblockedCholesky", False))
+    # A/B switch of the n = 64, m <= 96 kernel: "smem" = products out of shared memory, "regs" = A in registers
+    variant = {"auto": 0, "smem": 1, "regs": 2, "regs_ak": 3}[kw.pop("denseVariant", "auto")]
+    chunk = int(kw.pop("batchChunk", 0))
+    s = make_settings(**kw)
+    s.reserved_i[0] = 1 if unblocked else 0
+    s.reserved_i[3] = variant                # QPB200_RSV_DENSE_VARIANT
+    s.reserved_i[6] = chunk                  # QPB200_RSV_BATCH_CHUNK
+    return s
+
+
+def SolveQuadraticProgramBatch(P, q, A_cm, l, u, X0=None, pipelined=True, **kw):
     """Batched form: every problem is solved as ``SolveQuadraticProgram!`` with a direct (exact-solve)
-    plugin would.  Returns ``(X, flags, iters, info)``."""
-    with QPB200Batch(P, q, A_cm, l, u, **kw) as b:
-        X = None if X0 is None else np.array(X0, dtype=np.float64)
-        X, flags, iters = b.solve(X)
-        return X, flags, iters, b.info
+    plugin would.  Returns ``(X, flags, iters, info)``.  ``pipelined`` (default): one ``qpb200_batch_solve_once``
+    call -- chunked upload overlapped with the solve; ``False``: create + solve + destroy (everything resident)."""
+    if not pipelined:
+        with QPB200Batch(P, q, A_cm, l, u, **kw) as b:
+            X = None if X0 is None else np.array(X0, dtype=np.float64)
+            X, flags, iters = b.solve(X)
+            return X, flags, iters, b.info
+    P = np.ascontiguousarray(P, dtype=np.float64); A_cm = np.ascontiguousarray(A_cm, dtype=np.float64)
+    q = np.ascontiguousarray(q, dtype=np.float64); l = np.ascontiguousarray(l, dtype=np.float64)
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    batch, n = int(P.shape[0]), int(P.shape[1])
+    m = int(A_cm.shape[2])
+    if P.shape != (batch, n, n) or A_cm.shape != (batch, n, m):
+        raise ValueError("P must be [batch, n, n] and A [batch, n, m] (column-major m x n blocks)")
+    if q.shape != (batch, n) or l.shape != (batch, m) or u.shape != (batch, m):
+        raise ValueError("dimension mismatch in q, l or u")
+    X = np.zeros((batch, n)) if X0 is None else np.array(X0, dtype=np.float64)
+    flags = np.zeros(batch, dtype=np.int32)
+    iters = np.zeros(batch, dtype=np.int64)
+    info = Info()
+    settings = _batch_settings(kw)
+    _lib.check(_lib.load().qpb200_batch_solve_once(batch, n, m, _pd(P), _pd(A_cm), _pd(q), _pd(l), _pd(u), C.byref(settings),
+                                                   _pd(X), flags.ctypes.data_as(C.POINTER(C.c_int32)), _p64(iters), C.byref(info)))
+    return X, flags, iters, info.as_dict()
 
 
 class QPB200DistSolver:
@@ -349,18 +376,16 @@ class QPB200DistSolver:
     memory (``distMode="auto"``/``"peer"``) or through NCCL (``"nccl"``)."""
     _comm_key = None
 
-    def __init__(self, mP, vQ, mA, vL, vU, group=None, presliced=None, **kw):
+    def __init__(self, mP, vQ, mA, vL, vU, group=None, presliced=None, arrays=None, **kw):
+        """``presliced``: a slice made by ``partition.slice_problem`` (-> ``qpb200_dist_create``); default: the whole QP
+        goes to ``qpb200_dist_create_full`` and the library partitions it.  ``arrays = ((Pp, Pi, Pv), (Ap, Ai, Av))``:
+        the CSC arrays already in Julia's Int64 layout (what a ``ccall`` passes), instead of scipy matrices."""
         import torch
         import torch.distributed as dist
-        from . import partition
         lib = _lib.load()
         self.rank = dist.get_rank(group)
         self.nranks = dist.get_world_size(group)
-        self.n = int(mP.shape[0])
-        if presliced is None:
-            presliced = partition.slice_problem(mP, mA, vL, vU, self.rank, self.nranks)
-        P_r, A_r, l_r, u_r, self.rows, self.cols = presliced
-        self.m_local = int(A_r.shape[0])
+        self.n = int(np.shape(vQ)[0])
         # rank 0 creates the NCCL id; the group (any backend) carries its 128 bytes
         idbuf = np.zeros(128, dtype=np.uint8)
         key = (id(group), self.rank, self.nranks)
@@ -372,10 +397,7 @@ class QPB200DistSolver:
             box = [idbuf.tobytes()]
             dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
             idbuf = np.frombuffer(box[0], dtype=np.uint8).copy()
-        Pp, Pi, Pv = _csc_arrays(P_r)
-        Ap, Ai, Av = _csc_arrays(A_r)
         vQ = np.ascontiguousarray(vQ, dtype=np.float64)
-        l_r = np.ascontiguousarray(l_r, dtype=np.float64); u_r = np.ascontiguousarray(u_r, dtype=np.float64)
         kw.setdefault("device", torch.cuda.current_device() if torch.cuda.is_available() else -1)
         # collective: "auto" = in-kernel all-reduce over NVLink peer memory when available, else NCCL;
         # "nccl" = host-driven segments + ncclAllReduce; "peer" = peer path required
@@ -383,9 +405,27 @@ class QPB200DistSolver:
         self.settings = make_settings(**kw)
         self.settings.reserved_i[1] = dist_mode
         self._h = C.c_void_p()
-        _lib.check(lib.qpb200_dist_create(C.byref(self._h), self.rank, self.nranks, idbuf.ctypes.data_as(C.c_void_p),
-                                          self.n, self.m_local, _p64(Pp), _p64(Pi), _pd(Pv), _p64(Ap), _p64(Ai), _pd(Av),
-                                          _pd(vQ), _pd(l_r), _pd(u_r), C.byref(self.settings), 0))
+        if presliced is not None:
+            P_r, A_r, l_r, u_r, self.rows, self.cols = presliced
+            self.m_local = int(A_r.shape[0])
+            Pp, Pi, Pv = _csc_arrays(P_r)
+            Ap, Ai, Av = _csc_arrays(A_r)
+            l_r = np.ascontiguousarray(l_r, dtype=np.float64); u_r = np.ascontiguousarray(u_r, dtype=np.float64)
+            _lib.check(lib.qpb200_dist_create(C.byref(self._h), self.rank, self.nranks, idbuf.ctypes.data_as(C.c_void_p),
+                                              self.n, self.m_local, _p64(Pp), _p64(Pi), _pd(Pv), _p64(Ap), _p64(Ai), _pd(Av),
+                                              _pd(vQ), _pd(l_r), _pd(u_r), C.byref(self.settings), 0))
+        else:
+            (Pp, Pi, Pv), (Ap, Ai, Av) = arrays if arrays is not None else (_csc_arrays(mP), _csc_arrays(mA))
+            vL = np.ascontiguousarray(vL, dtype=np.float64); vU = np.ascontiguousarray(vU, dtype=np.float64)
+            m = int(vL.shape[0])
+            _lib.check(lib.qpb200_dist_create_full(C.byref(self._h), self.rank, self.nranks, idbuf.ctypes.data_as(C.c_void_p),
+                                                   self.n, m, _p64(Pp), _p64(Pi), _pd(Pv), _p64(Ap), _p64(Ai), _pd(Av),
+                                                   _pd(vQ), _pd(vL), _pd(vU), C.byref(self.settings), 0))
+            r0, r1 = C.c_int64(), C.c_int64()
+            _lib.check(lib.qpb200_dist_rows(self._h, C.byref(r0), C.byref(r1)))
+            self.rows = (int(r0.value), int(r1.value))
+            self.cols = None
+            self.m_local = self.rows[1] - self.rows[0]
         QPB200DistSolver._comm_key = key
         self.info = None
 

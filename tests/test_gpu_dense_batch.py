@@ -135,3 +135,17 @@ def test_batch_update_vectors_resolves_without_reupload(lib):
     assert np.array_equal(X1, X2) and np.array_equal(f1, f2) and np.array_equal(i1, i2)
     X4, f4, i4, _ = S.SolveQuadraticProgramBatch(P, q, A, l2, u2)
     assert np.array_equal(X3, X4) and np.array_equal(i3, i4)
+
+
+def test_pipelined_one_shot_solve_equals_resident_solve_bit_for_bit(lib):
+    """qpb200_batch_solve_once (chunked upload overlapped with the solve; 5 chunks, the last one ragged) against
+    create + solve with everything resident."""
+    P, q, A, l, u = config_cfg3_batch(1100, 64, 96, seed=77)
+    rng = np.random.default_rng(5)
+    X0 = rng.standard_normal((1100, 64))
+    Xa, fa, ia, infa = _S().SolveQuadraticProgramBatch(P, q, A, l, u, X0=X0, batchChunk=256)
+    Xb, fb, ib, infb = _S().SolveQuadraticProgramBatch(P, q, A, l, u, X0=X0, pipelined=False)
+    assert np.array_equal(Xa, Xb) and np.array_equal(fa, fb) and np.array_equal(ia, ib)
+    assert infa["kernel_launches"] == 5 and infa["iterations"] == infb["iterations"] == int(ia.sum())
+    Xc, fc, ic, _ = _S().SolveQuadraticProgramBatch(P[:100], q[:100], A[:100], l[:100], u[:100], X0=X0[:100])   # one chunk
+    assert np.array_equal(Xc, Xb[:100]) and np.array_equal(ic, ib[:100])

@@ -291,3 +291,40 @@ def test_bench_reference_arm_prints_exactly_one_json_line():
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
     assert "workload" in d["config"]
+
+
+# ---------------------------------------------------------------------------------------------------
+# The partition behind qpb200_dist_create_full (dist_partition.cpp) against partition.py, without a device
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nranks", [1, 2, 3, 8])
+@pytest.mark.parametrize("base", [0, 1])
+def test_in_library_partition_and_slices_match_partition_py(lib, nranks, base):
+    from quadraticprogramsolver_b200 import partition
+    from quadraticprogramsolver_b200.solver import _csc_arrays
+    from workloads.problems import config_sparse
+    P, q, A, l, u = config_sparse(900, 1700, 6e-3, seed=21)
+    A = sp.csc_matrix(sp.vstack([A[:400], sp.csr_matrix((37, 900)), A[400:]]))      # a run of empty rows
+    n, m = P.shape[0], A.shape[0]
+    (Pp, Pi, Pv), (Ap, Ai, Av) = _csc_arrays(P), _csc_arrays(A)
+    Pp, Pi, Ap, Ai = Pp + base, Pi + base, Ap + base, Ai + base
+    p64 = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))
+    pd = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    rb = np.zeros(nranks + 1, dtype=np.int64); cb = np.zeros(nranks + 1, dtype=np.int64)
+    assert lib.qpb200_debug_partition(n, m, p64(Pp), p64(Ap), p64(Ai), base, nranks, p64(rb), p64(cb)) == nranks
+    rb_py, cb_py = partition.plan(P, A, nranks)
+    assert np.array_equal(rb, rb_py) and np.array_equal(cb, cb_py)
+    assert rb[0] == 0 and rb[-1] == m and cb[0] == 0 and cb[-1] == n
+    for rank in range(nranks):
+        b4 = np.zeros(4, dtype=np.int64); poff = C.c_int64()
+        Pc = np.zeros(n + 1, dtype=np.int64); Ac = np.zeros(n + 1, dtype=np.int64)
+        Ar = np.zeros(A.nnz + 1, dtype=np.int64); Avv = np.zeros(A.nnz + 1)
+        assert lib.qpb200_debug_slice(n, m, p64(Pp), p64(Ap), p64(Ai), pd(Av), base, rank, nranks, p64(b4), C.byref(poff),
+                                      p64(Pc), p64(Ac), p64(Ar), pd(Avv), A.nnz + 1) == 0
+        P_r, A_r, l_r, u_r, (i0, i1), (j0, j1) = partition.slice_problem(P, A, l, u, rank, nranks)
+        assert b4.tolist() == [i0, i1, j0, j1]
+        nnzp = Pc[-1] - base
+        mine = sp.csc_matrix((Pv[poff.value:poff.value + nnzp], Pi[poff.value:poff.value + nnzp] - base, Pc - base), shape=(n, n))
+        assert (mine != P_r).nnz == 0
+        nnza = Ac[-1] - base
+        mine = sp.csc_matrix((Avv[:nnza], Ar[:nnza] - base, Ac - base), shape=(i1 - i0, n))
+        assert (mine != A_r).nnz == 0 and mine.nnz == A_r.nnz
