@@ -463,8 +463,14 @@ def run_cfg3(args):
         torch.cuda.synchronize()
 
     lo, hi = batch * rank // world, batch * (rank + 1) // world
-    P, q, A, l, u = config_cfg3_batch(batch, 64, 96, seed=1234)
-    P, q, A, l, u = P[lo:hi].copy(), q[lo:hi].copy(), A[lo:hi].copy(), l[lo:hi].copy(), u[lo:hi].copy()
+    shared = args.workload == "cfg3shared"
+    if shared:          # MPC-style: ONE (P, A) for the whole batch, 65 536 different (q, l, u) -- SURVEY.md 8(f) row 3
+        from workloads.problems import config_cfg3_shared
+        P, q, A, l, u = config_cfg3_shared(batch, 64, 96, seed=1234)
+        q, l, u = q[lo:hi].copy(), l[lo:hi].copy(), u[lo:hi].copy()
+    else:
+        P, q, A, l, u = config_cfg3_batch(batch, 64, 96, seed=1234)
+        P, q, A, l, u = P[lo:hi].copy(), q[lo:hi].copy(), A[lo:hi].copy(), l[lo:hi].copy(), u[lo:hi].copy()
     kw = dict(device=local_rank)
     b = S.QPB200Batch(P, q, A, l, u, **kw)
     for _ in range(args.warmup):
@@ -500,8 +506,10 @@ def run_cfg3(args):
         line = {"metric": "qp_solves_per_s", "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": tot[0] / args.steps, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"cfg3: {batch} dense QPs n=64 m=96 (randomQp recipe d=1), reference defaults, Cholesky of "
-                           "P+sigma I+rho A'A per QP", "parallelism": f"batch slices over {world} GPU(s), no collective",
+                "config": {"workload": (f"cfg3 (shared matrices, MPC-style): {batch} dense QPs n=64 m=96 with ONE (P, A) and "
+                                        "different q, l, u; reference defaults; one Cholesky factor for the batch" if shared else
+                                        f"cfg3: {batch} dense QPs n=64 m=96 (randomQp recipe d=1), reference defaults, Cholesky of "
+                                        "P+sigma I+rho A'A per QP"), "parallelism": f"batch slices over {world} GPU(s), no collective",
                            "admm_iters_per_solve": tot[2] / (batch * args.steps)},
                 "clocks": clocks,
                 "e2e": {"value": batch * e2e_steps / tot[1], "unit": "solves/s", "h2d_bytes_per_step": int(8 * (P.size + A.size + q.size + l.size + u.size + q.size)) * world,
@@ -510,12 +518,17 @@ def run_cfg3(args):
                 "roofline": {"bound": "fp64_fma", "achieved": flops / (tot[0] * 1e-3) / 1e12 / world, "peak": fp64_peak, "unit": "TFLOP/s",
                              "frac": flops / (tot[0] * 1e-3) / 1e12 / world / fp64_peak, "traffic": None,
                              "peak_source": fp64_src,
-                             "kernel": "dense_batch_kernel<96,2> (A and K^-1 register-resident during the iterations, shuffle reduce-scatters; DMMA only in the factorisation)"},
+                             "kernel": ("dense_shared_kernel (16 problems per CTA as the columns of three DMMA GEMMs per iteration, "
+                                        "iterates in accumulator-fragment registers)" if shared else
+                                        "dense_batch_kernel<96,2> (A and K^-1 register-resident during the iterations, shuffle "
+                                        "reduce-scatters; DMMA only in the factorisation)")},
                 "admm_iters_per_s": tot[2] / (tot[0] * 1e-3)}
         if world == 1 and not args.no_cpu:
             from oracle import c_oracle
             ns = 2048
-            Xr, fr, ir, sec, rc = c_oracle.solve_dense_batch(P[:ns], q[:ns], A[:ns], l[:ns], u[:ns])
+            Pn = np.ascontiguousarray(np.broadcast_to(P, (ns, 64, 64))) if shared else P[:ns]
+            An = np.ascontiguousarray(np.broadcast_to(A, (ns, 64, 96))) if shared else A[:ns]
+            Xr, fr, ir, sec, rc = c_oracle.solve_dense_batch(Pn, q[:ns], An, l[:ns], u[:ns])
             line["cpu_baseline"] = {"value": ns / sec, "unit": "solves/s", "cores": c_oracle.num_threads(), "kind": "port",
                                     "sample": f"first {ns} problems of the batch, oracle/qp_oracle.c, OpenMP",
                                     "parity": {"flags_equal": bool(np.array_equal(fr, flags[:ns])),
@@ -532,7 +545,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg5", choices=["cfg5", "cfg2", "cfg3", "cfg4", "banded"])
+    ap.add_argument("--workload", default="cfg5", choices=["cfg5", "cfg2", "cfg3", "cfg3shared", "cfg4", "banded"])
     ap.add_argument("--batch", type=int, default=65536, help="cfg3 batch size")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink cfg5 (tests only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
@@ -548,7 +561,7 @@ def main():
     buf = io.StringIO()
     try:
         with contextlib.redirect_stdout(buf):
-            if args.workload == "cfg3":
+            if args.workload in ("cfg3", "cfg3shared"):
                 run_cfg3(args)
             elif args.impl == "reference":
                 run_reference(args)

@@ -179,6 +179,13 @@ int qpb200_batch_solve(qpb200_batch *h, double *X_inout, int32_t *flags, int64_t
  * the next qpb200_batch_solve uploads nothing but the start points.                                            */
 int qpb200_batch_update_vectors(qpb200_batch *h, const double *q, const double *l, const double *u);
 void qpb200_batch_destroy(qpb200_batch *h);
+/* The MPC-style batch proper: every problem has the SAME P[n x n] and A[m x n] (column-major,
+ * passed once), only q[batch*n], l, u[batch*m] differ.  One K^-1 for the batch; 16 problems at a time are the columns
+ * of FP64 tensor-pipe GEMMs (n <= 64, m <= 96; adaptive_rho must be 0).  Same handle type: qpb200_batch_solve,
+ * qpb200_batch_update_vectors and qpb200_batch_destroy apply.                                                       */
+int qpb200_batch_create_shared(qpb200_batch **out, int64_t batch, int64_t n, int64_t m,
+                               const double *P, const double *A, const double *q, const double *l, const double *u,
+                               const qpb200_settings *settings);
 /* A batch that is solved once (create + solve + destroy in one call, what SolveQuadraticProgramBatch does): the batch
  * is cut into chunks of settings.reserved_i[QPB200_RSV_BATCH_CHUNK] problems (0 = 4096) and chunk c + 1 is uploaded
  * while the kernel of chunk c runs; only two chunks are resident.  Same results as create + solve, bit for bit.

@@ -55,7 +55,7 @@ EXPORTS = [
     "qpb200_destroy",
     "qpb200_apply", "qpb200_time_apply", "qpb200_apply_bytes",
     "qpb200_batch_create", "qpb200_batch_solve", "qpb200_batch_update_vectors", "qpb200_batch_destroy",
-    "qpb200_batch_solve_once",
+    "qpb200_batch_solve_once", "qpb200_batch_create_shared",
     "qpb200_dist_unique_id", "qpb200_dist_create", "qpb200_dist_create_full", "qpb200_dist_rows", "qpb200_dist_solve",
     "qpb200_debug_tile_plan", "qpb200_debug_tile_nnz", "qpb200_debug_equilibrate", "qpb200_debug_assemble_h",
     "qpb200_debug_partition", "qpb200_debug_slice",
@@ -93,6 +93,8 @@ def load():
     lib.qpb200_apply_bytes.restype = C.c_int64
     lib.qpb200_batch_create.argtypes = [C.POINTER(pv), C.c_int64, C.c_int64, C.c_int64, pd, pd, pd, pd, pd,
                                         C.POINTER(Settings)]
+    lib.qpb200_batch_create_shared.argtypes = [C.POINTER(pv), C.c_int64, C.c_int64, C.c_int64, pd, pd, pd, pd, pd,
+                                               C.POINTER(Settings)]
     lib.qpb200_batch_solve.argtypes = [pv, pd, C.POINTER(C.c_int32), p64, C.POINTER(Info)]
     lib.qpb200_batch_solve_once.argtypes = [C.c_int64, C.c_int64, C.c_int64, pd, pd, pd, pd, pd, C.POINTER(Settings), pd,
                                             C.POINTER(C.c_int32), p64, C.POINTER(Info)]

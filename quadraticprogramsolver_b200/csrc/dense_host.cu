@@ -5,6 +5,7 @@
 #include <new>
 
 #include "dense_kernel.cuh"
+#include "dense_shared_kernel.cuh"
 #include "host_common.h"
 
 namespace qpb {
@@ -23,6 +24,8 @@ struct DenseBatch {
     double setup_ms = 0.0;
     size_t smem = 0;
     int reg = 0;                 // mp = 96: 0 = products out of shared memory, 1 = A in registers, 2 = A and K^-1 in registers
+    bool shared = false;         // one (P, A) for the whole batch: dense_shared_kernel.cuh
+    DenseSharedParams sprm{};
     ~DenseBatch() {
         if (device >= 0) cudaSetDevice(device);
         if (ev0) cudaEventDestroy(ev0);
@@ -127,6 +130,15 @@ static int batch_upload_matrices(DenseBatch &B, int64_t count, const double *P, 
 }
 
 static int batch_launch(DenseBatch &B, int64_t count) {
+    if (B.shared) {
+        QPB_CUDA(cudaMemsetAsync(B.prm.totals, 0, 4 * sizeof(unsigned long long), B.stream));
+        QPB_CUDA(cudaMemsetAsync(B.prm.queue, 0, 4 * sizeof(unsigned int), B.stream));
+        QPB_CUDA(cudaEventRecord(B.ev0, B.stream));
+        dense_shared_kernel<<<B.grid, kShThreads, B.smem, B.stream>>>(B.sprm);
+        QPB_CUDA(cudaGetLastError());
+        QPB_CUDA(cudaEventRecord(B.ev1, B.stream));
+        return QPB200_OK;
+    }
     B.prm.batch = (int)count;
     B.grid = (int)std::min<int64_t>(count, (int64_t)B.grid_cap);
     QPB_CUDA(cudaMemsetAsync(B.prm.totals, 0, 4 * sizeof(unsigned long long), B.stream));
@@ -162,6 +174,103 @@ int qpb200_batch_create(qpb200_batch **out, int64_t batch, int64_t n, int64_t m,
         if (e == cudaSuccess) e = cudaStreamSynchronize(B.stream);
         if (e != cudaSuccess) rc = fail(QPB200_ERR_CUDA, "qpb200_batch_create: vector upload failed: %s", cudaGetErrorString(e));
     }
+    if (rc != QPB200_OK) {
+        delete h;
+        return rc;
+    }
+    B.setup_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    *out = h;
+    return QPB200_OK;
+}
+
+// A batch whose problems share P and A (MPC-style: q, l, u differ): one K^-1 for the batch, 16 problems per CTA as the
+// columns of FP64 tensor-pipe GEMMs (dense_shared_kernel.cuh).  The handle works with qpb200_batch_solve /
+// qpb200_batch_update_vectors / qpb200_batch_destroy like any other.
+int qpb200_batch_create_shared(qpb200_batch **out, int64_t batch, int64_t n, int64_t m, const double *P, const double *A,
+                               const double *q, const double *l, const double *u, const qpb200_settings *settings) {
+    if (!out) return fail(QPB200_ERR_ARG, "qpb200_batch_create_shared: out is NULL");
+    *out = nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    if (batch <= 0 || batch >= (int64_t(1) << 31) || n <= 0 || n > kDN || m <= 0 || m > 96)
+        return fail(QPB200_ERR_ARG, "qpb200_batch_create_shared: need batch > 0, 0 < n <= 64, 0 < m <= 96 (got %lld, %lld, %lld)",
+                    (long long)batch, (long long)n, (long long)m);
+    if (!P || !A || !q || !l || !u) return fail(QPB200_ERR_ARG, "qpb200_batch_create_shared: NULL array");
+    qpb200_settings s;
+    if (settings) s = *settings;
+    else { qpb200_default_settings(&s); s.lin_solver = QPB200_LINSOLVE_CHOLESKY; }
+    if (!(s.rho > 0.0) || !(s.sigma >= 0.0) || s.max_iter < 0 || s.check_every <= 0)
+        return fail(QPB200_ERR_ARG, "settings: need rho > 0, sigma >= 0, max_iter >= 0, check_every > 0");
+    if (s.lin_solver != QPB200_LINSOLVE_CHOLESKY || s.adaptive_rho || s.reserved_i[QPB200_RSV_SCALING_ITERS] != 0)
+        return fail(QPB200_ERR_ARG, "qpb200_batch_create_shared: needs lin_solver = CHOLESKY, adaptive_rho = 0 (one factor serves the "
+                                    "whole batch only while every problem keeps the same rho) and no equilibration");
+    if (s.max_iter >= (int64_t(1) << 30)) return fail(QPB200_ERR_ARG, "qpb200_batch_create_shared: max_iter too large");
+    if (!all_finite(P, (size_t)n * n) || !all_finite(A, (size_t)m * n)) return fail(QPB200_ERR_NONFINITE, "P or A has a non-finite entry");
+    if (!all_finite(q, (size_t)batch * n)) return fail(QPB200_ERR_NONFINITE, "q has a non-finite entry");
+    for (size_t i = 0; i < (size_t)batch * m; ++i)
+        if (std::isnan(l[i]) || std::isnan(u[i]) || l[i] > u[i]) return fail(QPB200_ERR_NONFINITE, "bounds: need l <= u, not NaN (entry %zu)", i);
+    int rc = check_device(s.device);
+    if (rc) return rc;
+    qpb200_batch *h = new (std::nothrow) qpb200_batch();
+    if (!h) return fail(QPB200_ERR_ARG, "out of host memory");
+    DenseBatch &B = h->b;
+    auto body = [&]() -> int {
+        QPB_CUDA(cudaGetDevice(&B.device));
+        B.batch = batch; B.n = (int)n; B.m = (int)m; B.mp = ((int)m + 7) & ~7;
+        B.settings = s;
+        B.shared = true;
+        double *dP, *dA, *dK, *dq, *dl, *du;
+        QPB_CUDA(B.arena.alloc(&dP, (size_t)n * n));
+        QPB_CUDA(B.arena.alloc(&dA, (size_t)m * n));
+        QPB_CUDA(B.arena.alloc(&dK, (size_t)kDN * kDN));
+        QPB_CUDA(B.arena.alloc(&dq, (size_t)batch * n));
+        QPB_CUDA(B.arena.alloc(&dl, (size_t)batch * m));
+        QPB_CUDA(B.arena.alloc(&du, (size_t)batch * m));
+        QPB_CUDA(B.arena.alloc(&B.prm.X, (size_t)batch * n));
+        QPB_CUDA(B.arena.alloc(&B.prm.flags, (size_t)batch));
+        QPB_CUDA(B.arena.alloc(&B.prm.iters, (size_t)batch));
+        QPB_CUDA(B.arena.alloc(&B.prm.factor_fail, 1, true));
+        QPB_CUDA(B.arena.alloc(&B.prm.totals, 4, true));
+        QPB_CUDA(B.arena.alloc(&B.prm.queue, 4, true));
+        QPB_CUDA(cudaStreamCreateWithFlags(&B.stream, cudaStreamNonBlocking));
+        QPB_CUDA(cudaEventCreate(&B.ev0));
+        QPB_CUDA(cudaEventCreate(&B.ev1));
+        QPB_CUDA(cudaMemcpyAsync(dP, P, (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice, B.stream));
+        QPB_CUDA(cudaMemcpyAsync(dA, A, (size_t)m * n * sizeof(double), cudaMemcpyHostToDevice, B.stream));
+        QPB_CUDA(cudaMemcpyAsync(dq, q, (size_t)batch * n * sizeof(double), cudaMemcpyHostToDevice, B.stream));
+        QPB_CUDA(cudaMemcpyAsync(dl, l, (size_t)batch * m * sizeof(double), cudaMemcpyHostToDevice, B.stream));
+        QPB_CUDA(cudaMemcpyAsync(du, u, (size_t)batch * m * sizeof(double), cudaMemcpyHostToDevice, B.stream));
+        B.prm.batch = (int)batch; B.prm.n = B.n; B.prm.m = B.m; B.prm.mp = B.mp;
+        B.prm.P = dP; B.prm.A = dA; B.prm.q = dq; B.prm.l = dl; B.prm.u = du;
+        // ---- the one factorisation of the batch
+        const int mp4 = ((int)m + 3) & ~3;
+        const size_t fsm = dense_smem_bytes(mp4);
+        QPB_CUDA(cudaFuncSetAttribute((const void *)dense_shared_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+        dense_shared_factor_kernel<<<1, kDThreads, fsm, B.stream>>>(dP, dA, B.n, B.m, mp4, s.rho, s.sigma, dK, B.prm.factor_fail);
+        QPB_CUDA(cudaGetLastError());
+        int ffail = 0;
+        QPB_CUDA(cudaMemcpyAsync(&ffail, B.prm.factor_fail, sizeof(int), cudaMemcpyDeviceToHost, B.stream));
+        QPB_CUDA(cudaStreamSynchronize(B.stream));
+        if (ffail) return fail(QPB200_ERR_FACTOR, "Cholesky breakdown: a pivot of P + sigma I + rho A'A was not positive");
+        DenseSharedParams &sp = B.sprm;
+        sp.batch = (int)batch; sp.n = B.n; sp.m = B.m; sp.mp = B.mp;
+        sp.P = dP; sp.A = dA; sp.Kinv = dK; sp.q = dq; sp.l = dl; sp.u = du;
+        sp.X = B.prm.X; sp.flags = B.prm.flags; sp.iters = B.prm.iters; sp.totals = B.prm.totals; sp.queue = B.prm.queue;
+        AdmmSettingsDev &d = sp.s;
+        d.max_iter = s.max_iter; d.check_every = s.check_every; d.pcg_max_iter = 0;
+        d.eps_abs = s.eps_abs; d.eps_rel = s.eps_rel; d.rho = s.rho; d.sigma = s.sigma; d.alpha = s.alpha;
+        d.rho_factor = s.rho_factor; d.pcg_eps = 0; d.pcg_rel_eps = 0; d.adaptive_rho = 0;
+        B.prm.s = d;
+        B.smem = dense_shared_smem_bytes(B.mp);
+        QPB_CUDA(cudaFuncSetAttribute((const void *)dense_shared_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.smem));
+        int per_sm = 0, num_sms = 0;
+        QPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)dense_shared_kernel, kShThreads, B.smem));
+        if (per_sm < 1) return fail(QPB200_ERR_CUDA, "shared-matrix batch kernel does not fit on an SM (smem %zu)", B.smem);
+        QPB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, B.device));
+        B.grid_cap = num_sms * per_sm;
+        B.grid = (int)std::min<int64_t>((batch + kShNc - 1) / kShNc, (int64_t)B.grid_cap);
+        return QPB200_OK;
+    };
+    rc = body();
     if (rc != QPB200_OK) {
         delete h;
         return rc;

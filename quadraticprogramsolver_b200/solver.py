@@ -266,20 +266,25 @@ class QPB200Batch:
     A_b[i, j]``; see ``problems.config_cfg3_batch``); ``q[batch, n]``, ``l, u[batch, m]``."""
 
     def __init__(self, P, q, A_cm, l, u, **kw):
+        """``P[n, n]`` and ``A_cm[n, m]`` (ONE pair for the whole batch, MPC-style: only q, l, u differ) select the
+        shared-matrix engine (``qpb200_batch_create_shared``: one factor, tensor-pipe GEMMs over 16 problems)."""
         lib = _lib.load()
         P = np.ascontiguousarray(P, dtype=np.float64); A_cm = np.ascontiguousarray(A_cm, dtype=np.float64)
         q = np.ascontiguousarray(q, dtype=np.float64); l = np.ascontiguousarray(l, dtype=np.float64)
         u = np.ascontiguousarray(u, dtype=np.float64)
-        self.batch, self.n = int(P.shape[0]), int(P.shape[1])
-        self.m = int(A_cm.shape[2])
-        if P.shape != (self.batch, self.n, self.n) or A_cm.shape != (self.batch, self.n, self.m):
-            raise ValueError("P must be [batch, n, n] and A [batch, n, m] (column-major m x n blocks)")
+        self.shared = P.ndim == 2
+        self.batch, self.n = int(q.shape[0]), int(q.shape[1])
+        self.m = int(A_cm.shape[-1])
+        lead = () if self.shared else (self.batch,)
+        if P.shape != lead + (self.n, self.n) or A_cm.shape != lead + (self.n, self.m):
+            raise ValueError("P must be [batch, n, n] and A [batch, n, m] (column-major m x n blocks), or one [n, n] / [n, m] pair")
         if q.shape != (self.batch, self.n) or l.shape != (self.batch, self.m) or u.shape != (self.batch, self.m):
             raise ValueError("dimension mismatch in q, l or u")
         self.settings = _batch_settings(kw)
         self._h = C.c_void_p()
-        _lib.check(lib.qpb200_batch_create(C.byref(self._h), self.batch, self.n, self.m, _pd(P), _pd(A_cm), _pd(q), _pd(l),
-                                           _pd(u), C.byref(self.settings)))
+        create = lib.qpb200_batch_create_shared if self.shared else lib.qpb200_batch_create
+        _lib.check(create(C.byref(self._h), self.batch, self.n, self.m, _pd(P), _pd(A_cm), _pd(q), _pd(l), _pd(u),
+                          C.byref(self.settings)))
         self.info = None
 
     def solve(self, X=None):
@@ -345,7 +350,7 @@ def SolveQuadraticProgramBatch(P, q, A_cm, l, u, X0=None, pipelined=True, **kw):
     """Batched form: every problem is solved as ``SolveQuadraticProgram!`` with a direct (exact-solve)
     plugin would.  Returns ``(X, flags, iters, info)``.  ``pipelined`` (default): one ``qpb200_batch_solve_once``
     call -- chunked upload overlapped with the solve; ``False``: create + solve + destroy (everything resident)."""
-    if not pipelined:
+    if not pipelined or np.ndim(P) == 2:           # (a shared (P, A) pair uploads next to nothing: nothing to pipeline)
         with QPB200Batch(P, q, A_cm, l, u, **kw) as b:
             X = None if X0 is None else np.array(X0, dtype=np.float64)
             X, flags, iters = b.solve(X)

@@ -149,3 +149,56 @@ def test_pipelined_one_shot_solve_equals_resident_solve_bit_for_bit(lib):
     assert infa["kernel_launches"] == 5 and infa["iterations"] == infb["iterations"] == int(ia.sum())
     Xc, fc, ic, _ = _S().SolveQuadraticProgramBatch(P[:100], q[:100], A[:100], l[:100], u[:100], X0=X0[:100])   # one chunk
     assert np.array_equal(Xc, Xb[:100]) and np.array_equal(ic, ib[:100])
+
+
+# ---------------------------------------------------------------------------------------------------
+# Shared-(P, A) batch (MPC-style): one factor, 16 problems per CTA as GEMM columns
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(64, 96), (64, 50), (40, 96), (17, 23)], ids=lambda s: f"n{s[0]}_m{s[1]}")
+def test_shared_matrix_batch_matches_oracle_and_per_problem_kernel(lib, shape):
+    from workloads.problems import config_cfg3_shared
+    n, m = shape
+    batch = 150                                   # 10 tiles of 16 columns with a ragged tail, slots refilled as columns finish
+    P, q, A, l, u = config_cfg3_shared(batch, n, m, seed=11)
+    rng = np.random.default_rng(3)
+    X0 = rng.standard_normal((batch, n)) * 0.1
+    S = _S()
+    with S.QPB200Batch(P, q, A, l, u) as b:
+        assert b.shared
+        X, flags, iters = b.solve(X0.copy())
+        info = dict(b.info)
+        X2, f2, i2 = b.solve(X0.copy())
+        assert np.array_equal(X, X2) and np.array_equal(iters, i2)            # bit-reproducible
+    Pb = np.ascontiguousarray(np.broadcast_to(P, (batch, n, n)))
+    Ab = np.ascontiguousarray(np.broadcast_to(A, (batch, n, m)))
+    Xr, fr, ir, _, rc = c_oracle.solve_dense_batch(Pb, q, Ab, l, u, x0=X0)     # oracle mode D, problem by problem
+    assert rc == 0
+    _check(X, flags, iters, Xr, fr, ir)
+    assert info["iterations"] == int(iters.sum())
+    Xp, fp, ip, _ = S.SolveQuadraticProgramBatch(Pb, q, Ab, l, u, X0=X0)       # the per-problem-factor kernel
+    assert np.array_equal(flags, fp) and np.max(np.abs(iters - ip)) <= 2
+    assert np.max(np.abs(X - Xp)) <= 1e-8 * (1 + np.max(np.abs(Xp)))
+
+
+def test_shared_matrix_batch_iteration_cap_resolve_and_errors(lib):
+    from workloads.problems import config_cfg3_shared
+    S = _S()
+    P, q, A, l, u = config_cfg3_shared(40, 64, 96, seed=5)
+    Pb = np.ascontiguousarray(np.broadcast_to(P, (40, 64, 64)))
+    Ab = np.ascontiguousarray(np.broadcast_to(A, (40, 64, 96)))
+    for cap in (60, 75):                          # a cap between two check points / on a check point
+        X, flags, iters, _ = S.SolveQuadraticProgramBatch(P, q, A, l, u, numIterations=cap)
+        Xr, fr, ir, _, _ = c_oracle.solve_dense_batch(Pb, q, Ab, l, u, numIterations=cap)
+        assert np.array_equal(flags, fr) and np.array_equal(iters, ir) and np.all(iters <= cap)
+        assert np.max(np.abs(X - Xr)) <= 1e-9 * (1 + np.max(np.abs(Xr)))
+    with S.QPB200Batch(P, q, A, l, u) as b:       # MPC-style re-solve: new vectors, same factor
+        b.solve()
+        q2 = q[::-1].copy()
+        b.update_vectors(q=q2)
+        X, flags, iters = b.solve()
+    Xr, fr, ir, _, _ = c_oracle.solve_dense_batch(Pb, q2, Ab, l, u)
+    _check(X, flags, iters, Xr, fr, ir)
+    with pytest.raises(S.QPB200Error):
+        S.QPB200Batch(P, q, A, l, u, adptRho=True)                             # one factor needs one rho
+    with pytest.raises(S.QPB200Error):
+        S.QPB200Batch(-P, q, A * 0.0, l, u)                                    # K not positive definite

@@ -292,6 +292,25 @@ def config_cfg3_batch(batch: int, n: int = 64, m: int = 96, seed: int = 1234):
     return np.ascontiguousarray(P), q, A_cm, l, u
 
 
+def config_cfg3_shared(batch: int, n: int = 64, m: int = 96, seed: int = 1234):
+    """configs[2] as an MPC controller sees it: ONE plant model -- one P[n, n], one A (column-major
+    m x n as ``A_cm[n, m]``) -- and ``batch`` different right-hand sides q[batch, n], l, u[batch, m] (the recipe of
+    ``config_cfg3_batch`` for the vectors).  ``np.broadcast_to(P, (batch, n, n))`` gives the per-problem layout."""
+    rng = np.random.default_rng(seed)
+    mM = rng.standard_normal((n, n))
+    P = mM.T @ mM + 1e-2 * np.eye(n)
+    P = 0.5 * (P + P.T)
+    A_rm = rng.standard_normal((m, n))
+    q = rng.standard_normal((batch, n))
+    l = -rng.random((batch, m))
+    u = rng.random((batch, m))
+    vI = rng.random((batch, m)) <= 0.15
+    l[vI] = u[vI]
+    vI = rng.random((batch, m)) <= 0.15
+    u[vI] = 1.0
+    return np.ascontiguousarray(P), q, np.ascontiguousarray(A_rm.T), l, u
+
+
 def config_banded(n: int = 1_000_000, m: int = 2_000_000, nnz_row_p: int = 26, nnz_row_a: int = 5, band: int = 256,
                   seed: int = 1234):
     """A QP with the SAME sizes and non-zeros per row as cfg5 but with every row's columns inside a band of
