@@ -158,6 +158,34 @@ int qpb200_update_settings(qpb200_handle *h, const qpb200_settings *settings);
 int qpb200_set_rho_scale(qpb200_handle *h, const double *rho_scale);
 void qpb200_destroy(qpb200_handle *h);
 
+/* ---- the reference's second solver, ProxQP.jl, on the same kernels ------------------------
+ *     min 0.5 x'Px + q'x   s.t.   A x = b,   C x <= d
+ * replaces SolveQuadraticProgram!(sQpProb::ProxQP; numIterations = 2000, eps_abs = 1e-7, eps_rel = 1e-6,
+ * numItrConv = 50, rho = 1e2, sigma = 1e-2, adptRho = true, tau = 10)  (/root/reference/ProxQP.jl:118-173) with its
+ * Cholesky of M = P + rho (A'A + C'C) + sigma I (:175-205) and CheckConvergence! (:250-296).
+ * The handle comes from qpb200_create with lin_solver = QPB200_LINSOLVE_CHOLESKY, constraint matrix [A; C] (the first
+ * m_eq rows are the equalities), l ignored, u = [b; d].  Settings read here: max_iter, eps_abs, eps_rel, check_every,
+ * rho, sigma, adaptive_rho, rho_factor (= tau); qpb200_proxqp_default_settings fills in the reference's defaults.
+ * x[n], y[m_eq], z[m - m_eq], s[m - m_eq] are the start point in (the inner constructor ProxQP.jl:36 takes them
+ * explicitly) and the final iterates out; init_slack != 0: s_in is ignored and the slack starts from
+ * s = max(d - C x, 0) (:109), computed on the device (s may then also be NULL: the final slack is not returned).
+ * As in the reference all max_iter iterations run; report->iterations is the iteration of the last converged check. */
+typedef struct qpb200_proxqp_report {
+    int32_t converged;       /* dReport["Converged"]: convFlag of the last check                   */
+    int32_t reserved;
+    int64_t iterations;      /* dReport["Iterations"]                                              */
+    double rho;              /* dReport["rho"] (final)                                             */
+    double sigma;
+    double res_prim;         /* dReport["PrimalResidual"]                                          */
+    double res_dual;         /* dReport["DualResidual"]                                            */
+    int64_t rho_updates;     /* refactorisations triggered by the adaptive rho                     */
+    double solve_ms;         /* device time, CUDA events (refactorisations included)               */
+    int64_t kernel_launches;
+} qpb200_proxqp_report;
+void qpb200_proxqp_default_settings(qpb200_settings *s);
+int qpb200_proxqp_solve(qpb200_handle *h, int64_t m_eq, const qpb200_settings *settings, double *x, double *y, double *z,
+                        double *s, int32_t init_slack, qpb200_proxqp_report *report);
+
 /* The operators of the path on their own (SparseArrays mul!, SolveQuadraticProgram.jl:85-89,
  * LinearSystemSolvers.jl:135,139,153-155): which = 0: y[n] = P x[n]; 1: y[m] = A x[n];
  * 2: y[n] = A' x[m]; 3: y[n] = (P + sigma I + rho A'A) x[n].  Host vectors in and out.          */

@@ -48,11 +48,18 @@ class Info(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class ProxReport(C.Structure):
+    """``qpb200_proxqp_report`` (include/qpb200.h)."""
+    _fields_ = [("converged", C.c_int32), ("reserved", C.c_int32), ("iterations", C.c_int64), ("rho", C.c_double),
+                ("sigma", C.c_double), ("res_prim", C.c_double), ("res_dual", C.c_double), ("rho_updates", C.c_int64),
+                ("solve_ms", C.c_double), ("kernel_launches", C.c_int64)]
+
+
 # every symbol include/qpb200.h declares
 EXPORTS = [
     "qpb200_version", "qpb200_device_count", "qpb200_default_settings", "qpb200_last_error",
     "qpb200_create", "qpb200_solve", "qpb200_update_vectors", "qpb200_update_settings", "qpb200_set_rho_scale",
-    "qpb200_destroy",
+    "qpb200_destroy", "qpb200_proxqp_default_settings", "qpb200_proxqp_solve",
     "qpb200_apply", "qpb200_time_apply", "qpb200_apply_bytes",
     "qpb200_batch_create", "qpb200_batch_solve", "qpb200_batch_update_vectors", "qpb200_batch_destroy",
     "qpb200_batch_solve_once", "qpb200_batch_create_shared",
@@ -85,6 +92,9 @@ def load():
     lib.qpb200_update_vectors.argtypes = [pv, pd, pd, pd]
     lib.qpb200_update_settings.argtypes = [pv, C.POINTER(Settings)]
     lib.qpb200_set_rho_scale.argtypes = [pv, pd]
+    lib.qpb200_proxqp_default_settings.argtypes = [C.POINTER(Settings)]
+    lib.qpb200_proxqp_default_settings.restype = None
+    lib.qpb200_proxqp_solve.argtypes = [pv, C.c_int64, C.POINTER(Settings), pd, pd, pd, pd, C.c_int32, C.POINTER(ProxReport)]
     lib.qpb200_destroy.argtypes = [pv]
     lib.qpb200_destroy.restype = None
     lib.qpb200_apply.argtypes = [pv, C.c_int32, pd, pd]

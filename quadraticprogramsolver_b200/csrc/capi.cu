@@ -96,6 +96,30 @@ int qpb200_set_rho_scale(qpb200_handle *h, const double *rho_scale) {
     return h->solver.set_rho_scale(rho_scale);
 }
 
+void qpb200_proxqp_default_settings(qpb200_settings *s) {
+    if (!s) return;
+    qpb200_default_settings(s);
+    s->max_iter = 2000;          // ProxQP.jl:118
+    s->eps_abs = 1e-7;
+    s->eps_rel = 1e-6;
+    s->check_every = 50;
+    s->rho = 1e2;
+    s->sigma = 1e-2;
+    s->adaptive_rho = 1;
+    s->rho_factor = 10.0;        // tau
+    s->lin_solver = QPB200_LINSOLVE_CHOLESKY;
+}
+
+int qpb200_proxqp_solve(qpb200_handle *h, int64_t m_eq, const qpb200_settings *settings, double *x, double *y, double *z,
+                        double *s, int32_t init_slack, qpb200_proxqp_report *report) {
+    if (!h) return qpb::fail(QPB200_ERR_ARG, "qpb200_proxqp_solve: handle is NULL");
+    if (h->dist) return qpb::fail(QPB200_ERR_ARG, "qpb200_proxqp_solve: not implemented for distributed handles");
+    qpb200_settings ps;
+    if (settings) ps = *settings;
+    else qpb200_proxqp_default_settings(&ps);
+    return h->solver.solve_proxqp(m_eq, ps, x, y, z, s, init_slack != 0, report);
+}
+
 void qpb200_destroy(qpb200_handle *h) {
     if (!h) return;
     const auto t0 = std::chrono::steady_clock::now();

@@ -2,7 +2,12 @@
 // (settings.lin_solver = QPB200_LINSOLVE_CHOLESKY on qpb200_create); design notes in direct_kernels.cuh.
 // Replaces the factorisation calls of the reference's direct plugins: ldlt / qdldl / ldl at init
 // (LinearSystemSolvers.jl:18,49,81) and on every rho change (:30-32,61-63,93-95).
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
 #include "direct_kernels.cuh"
+#include "proxqp_kernels.cuh"
 #include "host_common.h"
 #include "sparse_solver.h"
 
@@ -192,6 +197,98 @@ int SparseSolver::refactor(double rho, int64_t *launches) {
     }
     k_valid = true;
     k_rho = rho;
+    return QPB200_OK;
+}
+
+// ProxQP front end (proxqp_kernels.cuh) on an exact-solve handle whose constraint matrix is [A; C].
+int SparseSolver::solve_proxqp(int64_t m_eq, const qpb200_settings &ps, double *x, double *y, double *z, double *sl,
+                               bool init_slack, qpb200_proxqp_report *report) {
+    if (!direct) return fail(QPB200_ERR_ARG, "qpb200_proxqp_solve: the handle must be created with lin_solver = QPB200_LINSOLVE_CHOLESKY");
+    if (scaled || prob.rs) return fail(QPB200_ERR_ARG, "qpb200_proxqp_solve: equilibration / per-constraint rho are not part of this solver");
+    if (m_eq < 0 || m_eq > m) return fail(QPB200_ERR_ARG, "qpb200_proxqp_solve: m_eq = %lld outside [0, %d]", (long long)m_eq, m);
+    if (!x || (m_eq > 0 && !y) || (m_eq < m && (!z || (!sl && !init_slack)))) return fail(QPB200_ERR_ARG, "qpb200_proxqp_solve: NULL vector");
+    if (!(ps.rho > 0.0) || !(ps.sigma >= 0.0) || ps.max_iter < 0 || ps.check_every <= 0 || !(ps.rho_factor > 0.0))
+        return fail(QPB200_ERR_ARG, "qpb200_proxqp_solve: need rho > 0, sigma >= 0, max_iter >= 0, check_every > 0, tau > 0");
+    const int m_in = m - (int)m_eq;
+    if (!all_finite(x, (size_t)n) || (m_eq && !all_finite(y, (size_t)m_eq)) || (m_in && !all_finite(z, (size_t)m_in)) ||
+        (sl && !init_slack && m_in && !all_finite(sl, (size_t)m_in)))
+        return fail(QPB200_ERR_NONFINITE, "qpb200_proxqp_solve: a start vector holds NaN or Inf");
+    for (int i = 0; i < m; ++i)
+        if (!std::isfinite(h_u[(size_t)i])) return fail(QPB200_ERR_ARG, "qpb200_proxqp_solve: b and d (the handle's u) must be finite (row %d)", i);
+    QPB_CUDA(cudaSetDevice(device));
+    static std::mutex mu;
+    static bool prepped[64] = {false};
+    {
+        std::lock_guard<std::mutex> gl(mu);
+        if (device >= 0 && device < 64 && !prepped[device]) {
+            int per_sm = 0;
+            if (int prc = prep_tile_kernel((const void *)proxqp_kernel<1>, &per_sm)) return prc;
+            if (per_sm * num_sms < grid) return fail(QPB200_ERR_CUDA, "proxqp kernel cannot be co-resident at grid %d", grid);
+            prepped[device] = true;
+        }
+    }
+    if (ps.sigma != settings.sigma) k_valid = false;   // M = P + sigma I + rho Abar'Abar
+    settings.sigma = ps.sigma;
+    AdmmSettingsDev &dv = prob.s;
+    dv.max_iter = ps.max_iter; dv.check_every = ps.check_every; dv.eps_abs = ps.eps_abs; dv.eps_rel = ps.eps_rel;
+    dv.sigma = ps.sigma; dv.adaptive_rho = ps.adaptive_rho; dv.rho = ps.rho;
+    int rc = reset_state(nullptr);
+    if (rc) return rc;
+    QPB_CUDA(cudaMemcpyAsync(prob.XG, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, stream));
+    if (m_eq) QPB_CUDA(cudaMemcpyAsync(prob.zt, y, (size_t)m_eq * sizeof(double), cudaMemcpyHostToDevice, stream));
+    if (m_in) QPB_CUDA(cudaMemcpyAsync(prob.zt + m_eq, z, (size_t)m_in * sizeof(double), cudaMemcpyHostToDevice, stream));
+    if (m_in && sl && !init_slack) QPB_CUDA(cudaMemcpyAsync(prob.z + m_eq, sl, (size_t)m_in * sizeof(double), cudaMemcpyHostToDevice, stream));
+    static_assert(sizeof(ProxInfoDev) <= sizeof(AdmmInfoDev), "the report block reuses the ADMM info block");
+    ProxInfoDev *d_info = reinterpret_cast<ProxInfoDev *>(prob.info);
+    ProxDev pd{};
+    pd.m_eq = (int)m_eq;
+    pd.init_s = init_slack ? 1 : 0;
+    pd.tau = ps.rho_factor;
+    pd.info = d_info;
+    pd.carry = ProxInfoDev{};
+    pd.carry.res_prim = pd.carry.res_dual = INFINITY;
+    prob.iter0 = 0;
+    prob.rho0 = prob.rhorho0 = ps.rho;
+    prob.resume_changed = 0;
+    int64_t launches = 0;
+    QPB_CUDA(cudaEventRecord(ev0, stream));
+    if (!k_valid || k_rho != ps.rho)
+        if ((rc = refactor(ps.rho, &launches))) return rc;
+    ProxInfoDev hi{};
+    for (;;) {
+        QPB_CUDA(cudaMemsetAsync(sync_words, 0, 64 * sizeof(unsigned long long), stream));
+        void *args[] = {(void *)&prob, (void *)&pd};
+        QPB_CUDA(cudaLaunchCooperativeKernel((const void *)proxqp_kernel<1>, dim3(grid), dim3(kThreads), args, sizeof(SpmvSmem), stream));
+        ++launches;
+        QPB_CUDA(cudaMemcpyAsync(&hi, d_info, sizeof(hi), cudaMemcpyDeviceToHost, stream));
+        QPB_CUDA(cudaStreamSynchronize(stream));
+        if (hi.status == 0) break;
+        pd.carry = hi;                               // UpdateDecomposition! for the new rho (ProxQP.jl:159-165), then go on
+        prob.iter0 = hi.iterations_done;
+        prob.rho0 = prob.rhorho0 = hi.rho;
+        prob.resume_changed = 1;
+        if ((rc = refactor(hi.rho, &launches))) return rc;
+    }
+    QPB_CUDA(cudaEventRecord(ev1, stream));
+    QPB_CUDA(cudaMemcpyAsync(x, prob.XG, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    if (m_eq) QPB_CUDA(cudaMemcpyAsync(y, prob.zt, (size_t)m_eq * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    if (m_in) QPB_CUDA(cudaMemcpyAsync(z, prob.zt + m_eq, (size_t)m_in * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    if (m_in && sl) QPB_CUDA(cudaMemcpyAsync(sl, prob.z + m_eq, (size_t)m_in * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    QPB_CUDA(cudaStreamSynchronize(stream));
+    float ms = 0.f;
+    QPB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+    if (report) {
+        std::memset(report, 0, sizeof(*report));
+        report->converged = hi.converged;
+        report->iterations = hi.conv_iter > 0 ? hi.conv_iter : ps.max_iter;   // ProxQP.jl:125,156
+        report->rho = hi.rho;
+        report->sigma = ps.sigma;
+        report->res_prim = hi.res_prim;
+        report->res_dual = hi.res_dual;
+        report->rho_updates = hi.rho_updates;
+        report->solve_ms = ms;
+        report->kernel_launches = launches;
+    }
     return QPB200_OK;
 }
 

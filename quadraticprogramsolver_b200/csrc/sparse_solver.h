@@ -49,6 +49,9 @@ struct SparseSolver {
     bool pol_ready = false;
     long long pol_out[3] = {0, 0, 0};
     int polish();                                  // one cooperative launch on `stream` after the ADMM loop
+    // the reference's second solver (ProxQP.jl) on an exact-solve handle holding [A; C]: proxqp_kernels.cuh
+    int solve_proxqp(int64_t m_eq, const qpb200_settings &ps, double *x, double *y, double *z, double *s, bool init_slack,
+                     qpb200_proxqp_report *report);
     int refactor(double rho, int64_t *launches);   // build K for rho and invert it in place
     bool one_reduction() const;   // which arrangement of the (P)CG recurrence admm_kernel runs (QPB200_RSV_CG_RECURRENCE)
     int solve(double *x_inout, double *z_out, double *y_out, qpb200_info *info);
