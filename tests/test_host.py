@@ -26,15 +26,16 @@ def test_header_symbols_exported(lib):
 
 def test_struct_layout_matches_header(lib, tmp_path):
     src = tmp_path / "sz.c"
-    src.write_text('#include "qpb200.h"\n#include <stdio.h>\n#include <stddef.h>\nint main(){printf("%zu %zu %zu %zu\\n", '
+    src.write_text('#include "qpb200.h"\n#include <stdio.h>\n#include <stddef.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n", '
                    'sizeof(qpb200_settings), sizeof(qpb200_info), offsetof(qpb200_settings, pcg_eps), '
-                   'offsetof(qpb200_info, solve_ms));return 0;}')
+                   'offsetof(qpb200_info, solve_ms), sizeof(qpb200_proxqp_report), offsetof(qpb200_info, polish_active));return 0;}')
     exe = tmp_path / "sz"
     import subprocess
     subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
-    a, b, c, d = map(int, subprocess.check_output([str(exe)]).split())
+    a, b, c, d, e, f = map(int, subprocess.check_output([str(exe)]).split())
     assert a == C.sizeof(_lib.Settings) and b == C.sizeof(_lib.Info)
     assert c == _lib.Settings.pcg_eps.offset and d == _lib.Info.solve_ms.offset
+    assert e == C.sizeof(_lib.ProxReport) and f == _lib.Info.polish_active.offset
 
 
 def test_default_settings_match_reference_kwargs(lib):
@@ -328,3 +329,23 @@ def test_in_library_partition_and_slices_match_partition_py(lib, nranks, base):
         nnza = Ac[-1] - base
         mine = sp.csc_matrix((Avv[:nnza], Ar[:nnza] - base, Ac - base), shape=(i1 - i0, n))
         assert (mine != A_r).nnz == 0 and mine.nnz == A_r.nnz
+
+
+def test_julia_shim_binds_exported_symbols_and_mirrors_the_struct_layouts(lib):
+    """Julia is absent here, so the shim cannot run; what can be checked statically is: every symbol it ccalls is exported,
+    and its three mutable structs list the same fields in the same order as the ctypes mirrors (whose sizes and offsets
+    test_struct_layout_matches_header checks against the header)."""
+    src = open(os.path.join(ROOT, "julia", "QPB200.jl")).read()
+    syms = set(re.findall(r"ccall\(\(:(qpb200_[a-z0-9_]+)", src))
+    assert syms and syms <= set(_lib.EXPORTS)
+    for fam in ("qpb200_create", "qpb200_batch_solve_once", "qpb200_batch_create_shared", "qpb200_dist_create_full",
+                "qpb200_proxqp_solve", "qpb200_set_rho_scale"):
+        assert fam in syms, fam
+
+    def fields(name):
+        body = re.search(r"mutable struct %s\n(.*?)\n    %s\(\) = new\(\)" % (name, name), src, re.S).group(1)
+        return [ln.split("::")[0].strip() for ln in body.splitlines() if "::" in ln]
+
+    assert fields("Settings") == [f for f, _ in _lib.Settings._fields_]
+    assert fields("Info") == [f for f, _ in _lib.Info._fields_]
+    assert fields("ProxReport") == [f for f, _ in _lib.ProxReport._fields_]
