@@ -547,6 +547,9 @@ int qpb200_dist_create(qpb200_handle **out, int32_t rank, int32_t nranks, const 
     if (settings) s = *settings;
     else qpb200_default_settings(&s);
     set_host_thread_share(nranks);                 // the ranks of one node share its cores
+    if (s.lin_solver != QPB200_LINSOLVE_PCG || s.reserved_i[QPB200_RSV_POLISH] != 0)
+        return fail(QPB200_ERR_ARG, "qpb200_dist_create: the row-partitioned path implements lin_solver = PCG without polish "
+                                    "(the exact solve and the polish need the whole K / KKT operator on one device)");
     if (s.reserved_i[QPB200_RSV_SCALING_ITERS] != 0)
         return fail(QPB200_ERR_ARG, "qpb200_dist_create: equilibration needs column norms over all ranks' rows; not implemented for the row-partitioned path");
     qpb200_handle *h = new (std::nothrow) qpb200_handle();
