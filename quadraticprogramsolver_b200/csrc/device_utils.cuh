@@ -173,22 +173,24 @@ __device__ __forceinline__ void grid_barrier_reduce(const GridSync &gs, SyncStat
         for (int i = 0; i < NV; ++i) slots[blockIdx.x * kMaxRed + i] = v[i];
     }
     grid_barrier(gs, st);
-    if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;
+    // Every CTA combines the gridDim.x partials in the same fixed order.  All threads of the CTA take part: thread t
+    // loads partials t, t + kThreads, ... (independent L2 loads, all in flight together), then one block reduction.
+    // (Round 1 had a single warp walk the partials 32 at a time: ~19 dependent L2 round trips per reduction at 592
+    //  CTAs, 4-6 us on the critical path of every dot product.)
+    double acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] = 0.0;
+    for (unsigned j = threadIdx.x; j < gridDim.x; j += kThreads) {
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
-            double x = 0.0;
-            for (unsigned j = lane; j < gridDim.x; j += 32) {
-                const double y = __ldcg(slots + j * kMaxRed + i);
-                x = IS_MAX ? nanmax(x, y) : x + y;
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double y = __shfl_down_sync(0xffffffffu, x, o);
-                x = IS_MAX ? nanmax(x, y) : x + y;
-            }
-            if (lane == 0) bcast[i] = x;
+            const double y = __ldcg(slots + j * kMaxRed + i);
+            acc[i] = IS_MAX ? nanmax(acc[i], y) : acc[i] + y;
         }
+    }
+    block_reduce<NV, IS_MAX>(acc, red);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) bcast[i] = acc[i];
     }
     __syncthreads();
 #pragma unroll
