@@ -94,34 +94,26 @@ __device__ __forceinline__ void sys_barrier_impl(const GridSync &gs, SyncState &
             if (lane == 0) fence_acq_rel_gpu();     // one fence per warp: a fence executed by 32 lanes is 32 fences
             __syncwarp();
             if (NV > 0) {
-                // this warp is alone on the critical path: ONE walk over the CTA partials for all NV values (they sit
-                // next to each other), 4 independent loads per value in flight per lane
-                double x[NV];
+                for (int i = 0; i < NV; ++i) {
+                    // this warp is alone on the critical path: keep 8 independent L2 loads in flight per lane
+                    double x = 0.0;
+                    for (unsigned jb = lane; jb < gridDim.x; jb += 32 * 8) {
+                        double tl[8];
 #pragma unroll
-                for (int i = 0; i < NV; ++i) x[i] = 0.0;
-                for (unsigned jb = lane; jb < gridDim.x; jb += 32 * 4) {
-                    double tl[4][NV];
+                        for (int e = 0; e < 8; ++e) {
+                            const unsigned j = jb + 32 * e;
+                            tl[e] = j < gridDim.x ? __ldcg(loc + j * 4 + i) : 0.0;
+                        }
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const unsigned j = jb + 32 * e;
-#pragma unroll
-                        for (int i = 0; i < NV; ++i) tl[e][i] = j < gridDim.x ? __ldcg(loc + j * 4 + i) : 0.0;
+                        for (int e = 0; e < 8; ++e) x += tl[e];
                     }
 #pragma unroll
-                    for (int e = 0; e < 4; ++e)
-#pragma unroll
-                        for (int i = 0; i < NV; ++i) x[i] += tl[e][i];
-                }
-#pragma unroll
-                for (int i = 0; i < NV; ++i) {
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) x[i] += __shfl_down_sync(0xffffffffu, x[i], o);
-                    x[i] = __shfl_sync(0xffffffffu, x[i], 0);
-                }
-                if (lane < pd.nranks) {
-                    const long long off = (long long)(tot - pd.region[pd.rank]) + pd.rank * 4;
-#pragma unroll
-                    for (int i = 0; i < NV; ++i) pd.region[lane][off + i] = x[i];
+                    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+                    x = __shfl_sync(0xffffffffu, x, 0);
+                    if (lane < pd.nranks) {
+                        const long long off = (long long)(tot - pd.region[pd.rank]) + pd.rank * 4 + i;
+                        pd.region[lane][off] = x;
+                    }
                 }
             }
             __syncwarp();
