@@ -114,10 +114,30 @@ static void spmv(const csr_t *M, const double *x, double *y) {
     }
 }
 
+/* Dot product with a summation order that does NOT depend on the number of threads: fixed blocks of DOT_BLOCK
+ * elements are summed left to right, the block sums are added left to right.  (An OpenMP `reduction(+)` partitions by
+ * thread count, so the same test gave different exit checks on an 8-, a 16- and a 32-core host whenever the ADMM
+ * stop test fired on rounding noise.  With this the oracle is bit-reproducible from box to box.) */
+#define DOT_BLOCK 4096
 static double dot(const double *a, const double *b, int64_t n) {
+    const int64_t nb = (n + DOT_BLOCK - 1) / DOT_BLOCK;
+    if (nb <= 1) {
+        double s = 0.0;
+        for (int64_t i = 0; i < n; ++i) s += a[i] * b[i];
+        return s;
+    }
+    double stack_part[1024];
+    double *part = nb <= 1024 ? stack_part : (double *)malloc((size_t)nb * sizeof(double));
+#pragma omp parallel for schedule(static)
+    for (int64_t blk = 0; blk < nb; ++blk) {
+        const int64_t i0 = blk * DOT_BLOCK, i1 = i0 + DOT_BLOCK < n ? i0 + DOT_BLOCK : n;
+        double s = 0.0;
+        for (int64_t i = i0; i < i1; ++i) s += a[i] * b[i];
+        part[blk] = s;
+    }
     double s = 0.0;
-#pragma omp parallel for reduction(+ : s) schedule(static)
-    for (int64_t i = 0; i < n; ++i) s += a[i] * b[i];
+    for (int64_t blk = 0; blk < nb; ++blk) s += part[blk];
+    if (part != stack_part) free(part);
     return s;
 }
 

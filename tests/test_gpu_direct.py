@@ -8,6 +8,7 @@ import pytest
 import scipy.sparse as sp
 
 from oracle import qp_oracle
+from parity_util import assert_parity
 from workloads.problems import GenerateRandomQP, ProblemClass, config_cfg1, config_sparse
 
 pytestmark = pytest.mark.gpu
@@ -21,10 +22,21 @@ def _solver():
 
 
 def _check(x, flag, info, xr, fr, ir, tol=1e-6):
-    assert int(flag) == int(fr), f"flag {int(flag)} vs oracle {int(fr)}"
-    assert abs(int(info["iterations"]) - int(ir["iterations"])) <= 2, f"iterations {info['iterations']} vs {ir['iterations']}"
-    err = float(np.max(np.abs(x - xr)))
-    assert err <= tol * (1.0 + float(np.max(np.abs(xr)))), f"|x - x_ref|inf = {err:.3e}"
+    assert_parity(x, flag, info, xr, fr, ir, tol=tol)                   # strict criterion (tests/parity_util.py)
+
+
+def _check_sweep(S, prob, x, flag, info, xr, fr, ir, what):
+    """Strict parity incl. the refactorisation count; where the exit checks differ because the stop test fired on
+    rounding noise, the same-trajectory criterion of tests/parity_util.py."""
+    def gpu_at(k):
+        xk, _, ik = S.SolveQuadraticProgram(*prob, linSolver="cholesky", **dict(RUNTESTS_KW, numIterations=k))
+        return xk, ik
+
+    def ref_at(k):
+        xk, _, ik = qp_oracle.solve(*prob, mode="D", **dict(RUNTESTS_KW, numIterations=k))
+        return xk, ik
+
+    assert_parity(x, flag, info, xr, fr, ir, resolve_gpu=gpu_at, resolve_ref=ref_at, rho_updates=True, what=what)
 
 
 def _problem(pc, n, seed):
@@ -39,8 +51,7 @@ def test_runtests_sweep_n10_exact_solve(lib, pc, seed):
     P, q, A, l, u = _problem(pc, 10, seed)
     x, flag, info = S.SolveQuadraticProgram(P, q, A, l, u, linSolver="cholesky", **RUNTESTS_KW)
     xr, fr, ir = qp_oracle.solve(P, q, A, l, u, mode="D", **RUNTESTS_KW)
-    _check(x, flag, info, xr, fr, ir)
-    assert info["rho_updates"] == ir["rho_updates"]
+    _check_sweep(S, (P, q, A, l, u), x, flag, info, xr, fr, ir, f"{pc.name} n=10 seed={seed} (exact solve):")
     assert info["pcg_iters_total"] == 0
 
 
@@ -54,8 +65,7 @@ def test_runtests_sweep_n100_exact_solve(lib, pc, seed):
     P, q, A, l, u = _problem(pc, 100, seed)
     x, flag, info = S.SolveQuadraticProgram(P, q, A, l, u, linSolver="cholesky", **RUNTESTS_KW)
     xr, fr, ir = qp_oracle.solve(P, q, A, l, u, mode="D", **RUNTESTS_KW)
-    _check(x, flag, info, xr, fr, ir)
-    assert info["rho_updates"] == ir["rho_updates"]
+    _check_sweep(S, (P, q, A, l, u), x, flag, info, xr, fr, ir, f"{pc.name} n=100 seed={seed} (exact solve):")
 
 
 @pytest.mark.parametrize("seed", [1234, 1235, 1236])

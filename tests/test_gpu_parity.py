@@ -15,6 +15,7 @@ import pytest
 import scipy.sparse as sp
 
 from oracle import c_oracle, qp_oracle
+from parity_util import assert_parity
 from workloads.problems import (GenerateRandomQP, ProblemClass, config_cfg1, config_cfg4,
                                                   config_cfg5, config_sparse, sprandn)
 
@@ -30,10 +31,7 @@ def _solver():
 
 
 def _assert_parity(x, flag, info, x_ref, flag_ref, it_ref, tol=1e-6):
-    assert int(flag) == int(flag_ref), f"flag {int(flag)} vs oracle {int(flag_ref)}"
-    assert abs(int(info["iterations"]) - int(it_ref)) <= 2, f"iterations {info['iterations']} vs oracle {it_ref}"
-    err = np.max(np.abs(x - x_ref))
-    assert err <= tol * (1.0 + np.max(np.abs(x_ref))), f"|x - x_ref|inf = {err:.3e}"
+    assert_parity(x, flag, info, x_ref, flag_ref, it_ref, tol=tol)      # strict criterion (tests/parity_util.py)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -128,8 +126,17 @@ def test_all_problem_classes_n10(lib, pc):
     kw = dict(numIterations=50000, epsAbs=1e-7, epsRel=1e-7, rho=0.1, adptRho=True, epsPcg=1e-11)
     x, flag, info = S.SolveQuadraticProgram(P, q, A, l, u, **kw)
     x_ref, flag_ref, info_ref = qp_oracle.solve(P, q, A, l, u, mode="J", **kw)
-    _assert_parity(x, flag, info, x_ref, flag_ref, info_ref["iterations"])
-    assert info["rho_updates"] == info_ref["rho_updates"]
+
+    def gpu_at(k):
+        xk, _, ik = S.SolveQuadraticProgram(P, q, A, l, u, **dict(kw, numIterations=k))
+        return xk, ik
+
+    def ref_at(k):
+        xk, _, ik = qp_oracle.solve(P, q, A, l, u, mode="J", **dict(kw, numIterations=k))
+        return xk, ik
+
+    assert_parity(x, flag, info, x_ref, flag_ref, info_ref, resolve_gpu=gpu_at, resolve_ref=ref_at, rho_updates=True,
+                  what=f"{pc.name} n=10:")
 
 
 @pytest.mark.skipif(not GOLDEN, reason="no golden fixtures")
@@ -447,8 +454,18 @@ def test_runtests_sweep(lib, pc, n, seed):
     kw = dict(RUNTESTS_KW, epsPcg=1e-11)
     x, flag, info = S.SolveQuadraticProgram(P, q, A, l, u, **kw)
     xc, fc, ic = c_oracle.solve_sparse(P, q, A, l, u, precond=1, **kw)
-    _assert_parity(x, flag, info, xc, fc, ic["iterations"])
-    assert info["rho_updates"] == ic["rho_updates"]
+
+    def gpu_at(k):
+        xk, _, ik = S.SolveQuadraticProgram(P, q, A, l, u, **dict(kw, numIterations=k))
+        return xk, ik
+
+    def ref_at(k):
+        xk, _, ik = c_oracle.solve_sparse(P, q, A, l, u, precond=1, **dict(kw, numIterations=k))
+        return xk, ik
+
+    # strict parity; where the exit checks differ (stop test fired on rounding noise) the same-trajectory criterion
+    assert_parity(x, flag, info, xc, fc, ic, resolve_gpu=gpu_at, resolve_ref=ref_at, rho_updates=True,
+                  what=f"{pc.name} n={n} seed={seed}:")
     if P.shape[0] + A.shape[0] <= 2500:
         xd, fd, idd = qp_oracle.solve(P, q, A, l, u, mode="D", **RUNTESTS_KW)
         assert int(fd) != 1 and int(flag) != 1

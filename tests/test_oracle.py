@@ -215,3 +215,43 @@ def test_equality_rho_scale_cuts_iterations_on_an_equality_constrained_qp():
     _, f0, i0 = qp_oracle.solve(P, q, A, l, u, mode="D", **kw)
     _, f1, i1 = qp_oracle.solve(P, q, A, l, u, mode="D", rhoScale=equality_rho_scale(l, u), **kw)
     assert int(f1) != 1 and i1["iterations"] < i0["iterations"]
+
+
+def test_noise_triggered_exit_and_the_same_trajectory_criterion():
+    """equalityConstrainedQp, n = 10, seed 1235 with RunTests.jl:50-53 settings ends on convAdmm (|dx|, |dz| <= 1e-9)
+    after the iterates have stalled at rho = 1e6: three CPU restatements of the same iteration exit at three different
+    checks with the same x.  tests/parity_util.py's same-trajectory criterion (used by the GPU sweeps for exactly this
+    case) accepts such a pair and still rejects a wrong iterate."""
+    import warnings
+
+    from oracle import c_oracle
+    from parity_util import assert_parity
+
+    P, q, A, l, u = GenerateRandomQP(ProblemClass.equalityConstrainedQp, 10, numConstraints=5, seed=1235)
+    kw = dict(numIterations=50000, epsAbs=1e-7, epsRel=1e-7, rho=0.1, adptRho=True, epsPcg=1e-11)
+    xc, fc, ic = c_oracle.solve_sparse(P, q, A, l, u, precond=1, **kw)
+    xj, fj, ij = qp_oracle.solve(P, q, A, l, u, mode="J", **kw)
+    xd, fd, idd = qp_oracle.solve(P, q, A, l, u, mode="D", **{k: v for k, v in kw.items() if k != "epsPcg"})
+    its = {int(ic["iterations"]), int(ij["iterations"]), int(idd["iterations"])}
+    assert int(fc) == int(fj) == int(fd) == 2
+    assert max(np.max(np.abs(xc - xj)), np.max(np.abs(xc - xd))) <= 1e-8
+    if len(its) == 1:
+        pytest.skip("the restatements happen to agree on this host")
+
+    def c_at(k):
+        xk, _, ik = c_oracle.solve_sparse(P, q, A, l, u, precond=1, **dict(kw, numIterations=k))
+        return xk, ik
+
+    def j_at(k):
+        xk, _, ik = qp_oracle.solve(P, q, A, l, u, mode="J", **dict(kw, numIterations=k))
+        return xk, ik
+
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        assert assert_parity(xc, fc, ic, xj, fj, ij, resolve_gpu=c_at, resolve_ref=j_at, rho_updates=True) == "trajectory"
+    assert w and "same trajectory" in str(w[0].message)
+    with pytest.raises(AssertionError):                       # without the re-solve hooks the criterion is the strict one
+        assert_parity(xc, fc, ic, xj, fj, ij)
+    with pytest.raises(AssertionError):                       # a wrong iterate at the common iteration is still rejected
+        assert_parity(xc, fc, ic, xj, fj, ij, resolve_gpu=lambda k: (c_at(k)[0] + 1e-3, c_at(k)[1]),
+                      resolve_ref=lambda k: (j_at(k)[0] - 1e-3, j_at(k)[1]))
