@@ -187,13 +187,35 @@ def _public(cb):
     return {k: v for k, v in cb.items() if k not in ("x", "flag", "info")}
 
 
-def parity_check(prob, solve_gpu, iters=25, eps_pcg=1e-10):
+def quiet_gate(dist, key, open_it):
+    """N > 1: the ranks that have nothing to do while rank 0 runs host-only work SLEEP on the process group's
+    rendezvous store (a blocking socket read) instead of spinning in a NCCL barrier -- a spinning rank (host thread
+    polling the stream, NCCL proxy) takes cores away from the OpenMP team of the CPU port: measured on the 2-GPU
+    box, the 25-iteration parity leg took 77-86 s next to a rank waiting in NCCL against 15 s alone."""
+    if dist is None:
+        return
+    try:
+        from datetime import timedelta
+
+        from torch.distributed.distributed_c10d import _get_default_store
+        store = _get_default_store()
+        if open_it:
+            store.set(key, "1")
+        else:
+            store.wait([key], timedelta(seconds=3600))
+    except Exception as e:                      # no store: fall through, the collective that follows still synchronises
+        print(f"quiet_gate({key}): {e}", file=sys.stderr)
+
+
+def parity_check(prob, solve_gpu, iters=25, eps_pcg=1e-10, after_cpu=None):
     """north_star's criterion on the BENCHMARKED problem: the CPU port and the GPU run the same `iters` ADMM
     iterations (tight inner solve so that the trajectory is well defined) and x, flag, iteration count are compared."""
     over = dict(numIterations=iters, epsPcg=eps_pcg)
     t0 = time.time()
     ref = cpu_sample(prob, 1, 0.0, **over)
     cpu_s = time.time() - t0
+    if after_cpu is not None:
+        after_cpu()
     x_gpu, flag_gpu, info_gpu = solve_gpu(over)
     xr = ref["x"]
     err = float(np.max(np.abs(x_gpu - xr)) / (1.0 + np.max(np.abs(xr))))
@@ -328,8 +350,9 @@ def run_b200(args):
                 fl = ds.solve(xx)
                 return xx, fl, ds.info
         if rank == 0:
-            parity = parity_check(prob, solve_gpu)
+            parity = parity_check(prob, solve_gpu, after_cpu=lambda: quiet_gate(dist, "qpb200_parity_cpu_done", True))
         else:
+            quiet_gate(dist, "qpb200_parity_cpu_done", False)      # sleep while rank 0 runs the CPU port
             solve_gpu(dict(numIterations=25, epsPcg=1e-10))
         barrier()
     s.close()

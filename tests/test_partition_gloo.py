@@ -131,3 +131,39 @@ def test_two_rank_gloo_data_flow(tmp_path):
                          env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert out.stdout.count("ok") == 2
+
+
+_GATE_WORKER = textwrap.dedent('''
+    import os, sys, time
+    import torch.distributed as dist
+    sys.path.insert(0, os.environ["QPB_ROOT"])
+    import bench
+    dist.init_process_group("gloo")
+    rank = dist.get_rank()
+    t0 = time.time()
+    if rank == 0:
+        time.sleep(1.5)                                   # "the CPU port runs"
+        bench.quiet_gate(dist, "gate_test", True)
+    else:
+        c0 = time.process_time()
+        bench.quiet_gate(dist, "gate_test", False)
+        waited, cpu = time.time() - t0, time.process_time() - c0
+        assert waited >= 1.2, waited                      # it did wait for rank 0 ...
+        assert cpu <= 0.5, cpu                            # ... asleep, not spinning
+    bench.quiet_gate(None, "gate_test", False)            # single process: no-op
+    dist.barrier()
+    print("rank", rank, "ok", flush=True)
+    dist.destroy_process_group()
+''')
+
+
+def test_bench_quiet_gate_sleeps_until_rank0_opens_it(tmp_path):
+    """bench.py's N > 1 parity leg: the other ranks sleep on the rendezvous store while rank 0 runs the CPU port."""
+    script = tmp_path / "gate_worker.py"
+    script.write_text(_GATE_WORKER)
+    env = dict(os.environ, QPB_ROOT=ROOT, OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29617", str(script)],
+                         env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert out.stdout.count("ok") == 2
