@@ -79,6 +79,64 @@ __device__ __forceinline__ double clamp_julia(double x, double lo, double hi) {
 }
 
 // =============================================================================================
+// The statements of the outer iteration that every arrangement of the solve shares (admm_kernel here, the segments of
+// admm_dist_kernel, admm_peer_sliced_kernel): ONE copy of the reference's update and stop-test arithmetic.
+// =============================================================================================
+// SolveQuadraticProgram.jl:59-61 for constraint row i, given z~_i = (A x~)_i: relaxation, clip, dual update, and
+// g_i = rho_i (z~_i - z_i) + y_i for the next right-hand side.  Returns |z_new - z_old| (the dz of :105).
+__device__ __forceinline__ double admm_row_update(const SparseProblemDev &p, double *y, double *g, int i, double zt_i,
+                                                  double alpha, double alpha1, double rho_i, double rho1_i) {
+    const double z_old = p.z[i], y_old = y[i];
+    const double zr = alpha * zt_i + alpha1 * z_old;
+    const double z_new = clamp_julia(zr + rho1_i * y_old, p.l[i], p.u[i]);   // :60
+    const double y_new = y_old + rho_i * (zr - z_new);                       // :61
+    p.z[i] = z_new;
+    y[i] = y_new;
+    p.zt[i] = zt_i;
+    g[i] = rho_i * (zt_i - z_new) + y_new;
+    return fabs(z_new - z_old);
+}
+
+// SolveQuadraticProgram.jl:57 for variable j: x = alpha x~ + (1 - alpha) x.  Returns |x_new - x_old| (the dx of :105).
+__device__ __forceinline__ double admm_x_relax(double *x, const double *xt, int j, double alpha, double alpha1) {
+    const double x_old = x[j];
+    const double x_new = alpha * xt[j] + alpha1 * x_old;
+    x[j] = x_new;
+    return fabs(x_new - x_old);
+}
+
+// CheckConvergence, primal side (:85-86,90): (A x)_i against z_i -> res = |Ax - z|, mx = max(|Ax|, |z|); e_i = 1 unless
+// the problem was equilibrated (then the norms are those of the unscaled QP)
+__device__ __forceinline__ void admm_prim_norms(double &res, double &mx, double ax_i, double z_i, double e_i) {
+    res = nanmax(res, fabs(ax_i - z_i) * e_i);
+    mx = nanmax(mx, fabs(ax_i) * e_i);
+    mx = nanmax(mx, fabs(z_i) * e_i);
+}
+
+// CheckConvergence, dual side (:87-89,91): res = |Px + q + A'y|, mx = max(|Px|, |A'y|) (|q| joins after the reduction)
+__device__ __forceinline__ void admm_dual_norms(double &res, double &mx, double px_j, double q_j, double aty_j, double d_j) {
+    res = nanmax(res, fabs(px_j + q_j + aty_j) * d_j);
+    mx = nanmax(mx, fabs(px_j) * d_j);
+    mx = nanmax(mx, fabs(aty_j) * d_j);
+}
+
+// CheckConvergence from the reduced norms (:92-107): adaptive-rho proposal (clamped, NaN passes through as in Julia)
+// and the two stop tests in the reference's order -- convAdmm overrides convPrimDual.
+__device__ __forceinline__ void admm_stop_test(const AdmmSettingsDev &s, double rho, double dx, double dz, double res_prim,
+                                               double res_dual, double max_prim, double max_dual, double &rhorho,
+                                               int &conv_flag) {
+    if (s.adaptive_rho) {                                             // :92-96
+        const double num = res_prim * max_dual, den = res_dual * max_prim;
+        rhorho = clamp_julia(rho * sqrt(num / den), 1e-3, 1e6);
+    }
+    const double eps_prim = s.eps_abs + s.eps_rel * max_prim;         // :99
+    const double eps_dual = s.eps_abs + s.eps_rel * max_dual;         // :100
+    if ((res_prim < eps_prim) && (res_dual < eps_dual)) conv_flag = 3;     // :102
+    const double eps_admm = fmin(s.eps_abs, s.eps_rel) * 1e-2;             // :34
+    if ((dx <= eps_admm) && (dz <= eps_admm)) conv_flag = 2;               // :105 (overrides)
+}
+
+// =============================================================================================
 // Stand-alone SpMV (operator unit tests, SpMV roofline measurement).
 //   mode 0: y[rows] = M x            mode 1 (split): y0 = M[:, :split] x[:split], y1 = M[:, split:] x[split:]
 // =============================================================================================
@@ -306,28 +364,17 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) admm_kernel(SparseProblemD
         double nrm[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};          // dx dz rp nAx nZ rd|nPx|nAty packed below
         {
             auto epi = [&](int i, double s0, double) {
-                const double zt_i = s0;
-                const double z_old = p.z[i], y_old = y[i];
-                const double zr = p.s.alpha * zt_i + (1.0 - p.s.alpha) * z_old;
-                const double rho_i = rho_of(i);
-                const double z_new = clamp_julia(zr + rho1_of(i) * y_old, p.l[i], p.u[i]);   // :60
-                const double y_new = y_old + rho_i * (zr - z_new);                     // :61
-                p.z[i] = z_new;
-                y[i] = y_new;
-                p.zt[i] = zt_i;
-                g[i] = rho_i * (zt_i - z_new) + y_new;
+                const double dz_i = admm_row_update(p, y, g, i, s0, p.s.alpha, 1.0 - p.s.alpha, rho_of(i), rho1_of(i));
                 const double ei = (p.Einv && do_check) ? p.Einv[i] : 1.0;
-                nrm[1] = nanmax(nrm[1], fabs(z_new - z_old) * ei);
+                nrm[1] = nanmax(nrm[1], dz_i * ei);
             };
             spmv_tiles<TMA, false>(p.A, xt, sm, ps, epi);
             count(ctr.n_a, 1);
         }
         for (int j = gtid; j < n; j += gstride) {
-            const double x_old = x[j];
-            const double x_new = p.s.alpha * xt[j] + (1.0 - p.s.alpha) * x_old;      // :57
-            x[j] = x_new;
+            const double dx_j = admm_x_relax(x, xt, j, p.s.alpha, 1.0 - p.s.alpha);   // :57
             const double dj = (p.Dv && do_check) ? p.Dv[j] : 1.0;
-            nrm[0] = nanmax(nrm[0], fabs(x_new - x_old) * dj);
+            nrm[0] = nanmax(nrm[0], dx_j * dj);
         }
         grid_barrier(p.gs, st);
 
@@ -336,21 +383,14 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) admm_kernel(SparseProblemD
             //      (ei, dj = 1 unless the problem was equilibrated: then the norms are those of the unscaled QP)
             {
                 auto epi = [&](int i, double s0, double) {
-                    const double zi = p.z[i];
-                    const double ei = p.Einv ? p.Einv[i] : 1.0;
-                    nrm[2] = nanmax(nrm[2], fabs(s0 - zi) * ei);      // |Ax - z|
-                    nrm[3] = nanmax(nrm[3], fabs(s0) * ei);           // |Ax|
-                    nrm[3] = nanmax(nrm[3], fabs(zi) * ei);           // |z|   (maxNormPrim = max of both)
+                    admm_prim_norms(nrm[2], nrm[3], s0, p.z[i], p.Einv ? p.Einv[i] : 1.0);
                 };
                 spmv_tiles<TMA, false>(p.A, x, sm, ps, epi);
                 count(ctr.n_a, 1);
             }
             {
                 auto epi = [&](int j, double s0, double s1) {
-                    const double dj = p.Dinvc ? p.Dinvc[j] : 1.0;
-                    nrm[4] = nanmax(nrm[4], fabs(s0 + p.q[j] + s1) * dj);   // |Px + q + A'y|
-                    nrm[5] = nanmax(nrm[5], fabs(s0) * dj);                 // |Px|
-                    nrm[5] = nanmax(nrm[5], fabs(s1) * dj);                 // |A'y|
+                    admm_dual_norms(nrm[4], nrm[5], s0, p.q[j], s1, p.Dinvc ? p.Dinvc[j] : 1.0);
                 };
                 spmv_tiles<TMA, true>(p.H, p.XY, sm, ps, epi);
                 count(ctr.n_h, 1);
@@ -361,15 +401,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) admm_kernel(SparseProblemD
             if (threadIdx.x == 0) { ctr.res_prim = res_prim; ctr.res_dual = res_dual; }
             const double max_prim = nrm[3];
             const double max_dual = nanmax(nrm[5], p.normQ);
-            if (p.s.adaptive_rho) {                                   // :92-96
-                const double num = res_prim * max_dual, den = res_dual * max_prim;
-                rhorho = clamp_julia(rho * sqrt(num / den), 1e-3, 1e6);
-            }
-            const double eps_prim = p.s.eps_abs + p.s.eps_rel * max_prim;   // :99
-            const double eps_dual = p.s.eps_abs + p.s.eps_rel * max_dual;   // :100
-            if ((res_prim < eps_prim) && (res_dual < eps_dual)) conv_flag = 3;   // :102
-            const double eps_admm = fmin(p.s.eps_abs, p.s.eps_rel) * 1e-2;       // :34
-            if ((dx <= eps_admm) && (dz <= eps_admm)) conv_flag = 2;             // :105 (overrides)
+            admm_stop_test(p.s, rho, dx, dz, res_prim, res_dual, max_prim, max_dual, rhorho, conv_flag);
             if (conv_flag != 1) break;                                // :66
         }
     }

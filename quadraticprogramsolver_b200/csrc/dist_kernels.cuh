@@ -170,35 +170,16 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) admm_dist_kernel(SparsePro
         double nrm[4] = {0.0, 0.0, 0.0, 0.0};
         {
             auto epi = [&](int i, double s0, double) {
-                const double zt_i = s0;
-                const double z_old = p.z[i], y_old = y[i];
-                const double zr = alpha * zt_i + alpha1 * z_old;
-                const double z_new = clamp_julia(zr + rho1 * y_old, p.l[i], p.u[i]);
-                const double y_new = y_old + rho * (zr - z_new);
-                p.z[i] = z_new;
-                y[i] = y_new;
-                p.zt[i] = zt_i;
-                g[i] = rho * (zt_i - z_new) + y_new;
-                nrm[1] = nanmax(nrm[1], fabs(z_new - z_old));
+                nrm[1] = nanmax(nrm[1], admm_row_update(p, y, g, i, s0, alpha, alpha1, rho, rho1));
             };
             spmv_tiles<TMA, false>(p.A, xt, sm, ps, epi);
             ++n_a;
         }
-        for (int j = gtid; j < n; j += gstride) {
-            const double x_old = x[j];
-            const double x_new = alpha * xt[j] + alpha1 * x_old;
-            x[j] = x_new;
-            nrm[0] = nanmax(nrm[0], fabs(x_new - x_old));
-        }
+        for (int j = gtid; j < n; j += gstride) nrm[0] = nanmax(nrm[0], admm_x_relax(x, xt, j, alpha, alpha1));
         if (do_check) {
             grid_barrier(p.gs, st);
             {
-                auto epi = [&](int i, double s0, double) {
-                    const double zi = p.z[i];
-                    nrm[2] = nanmax(nrm[2], fabs(s0 - zi));
-                    nrm[3] = nanmax(nrm[3], fabs(s0));
-                    nrm[3] = nanmax(nrm[3], fabs(zi));
-                };
+                auto epi = [&](int i, double s0, double) { admm_prim_norms(nrm[2], nrm[3], s0, p.z[i], 1.0); };
                 spmv_tiles<TMA, false>(p.A, x, sm, ps, epi);
                 ++n_a;
             }
@@ -217,26 +198,15 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) admm_dist_kernel(SparsePro
     } else if (seg == kSegCheck) {
         // wbuf2 = [P x ; A' y] (all-reduced), S.lmax = all-reduced (max) local norms
         double nrm[2] = {0.0, 0.0};
-        for (int j = gtid; j < n; j += gstride) {
-            const double px = d.wbuf2[j], aty = d.wbuf2[n + j];
-            nrm[0] = nanmax(nrm[0], fabs(px + p.q[j] + aty));
-            nrm[1] = nanmax(nrm[1], fabs(px));
-            nrm[1] = nanmax(nrm[1], fabs(aty));
-        }
+        for (int j = gtid; j < n; j += gstride) admm_dual_norms(nrm[0], nrm[1], d.wbuf2[j], p.q[j], d.wbuf2[n + j], 1.0);
         grid_barrier_reduce<2, true>(p.gs, st, nrm, sm.red, sm.bcast);
         had_barrier = true;
-        const double eps_admm = fmin(p.s.eps_abs, p.s.eps_rel) * 1e-2;
         const double dx = lmax[0], dz = lmax[1];
         res_prim = lmax[2];
         res_dual = nrm[0];
         const double max_prim = lmax[3];
         const double max_dual = nanmax(nrm[1], p.normQ);
-        if (p.s.adaptive_rho) {
-            const double num = res_prim * max_dual, den = res_dual * max_prim;
-            rhorho = clamp_julia(rho * sqrt(num / den), 1e-3, 1e6);
-        }
-        if ((res_prim < p.s.eps_abs + p.s.eps_rel * max_prim) && (res_dual < p.s.eps_abs + p.s.eps_rel * max_dual)) conv_flag = 3;
-        if ((dx <= eps_admm) && (dz <= eps_admm)) conv_flag = 2;
+        admm_stop_test(p.s, rho, dx, dz, res_prim, res_dual, max_prim, max_dual, rhorho, conv_flag);
     }
 
     // write the control block back.  Segments that changed a value every block must re-read next time

@@ -408,35 +408,17 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) admm_peer_sliced_kernel(Sp
         double nrm[4] = {0.0, 0.0, 0.0, 0.0};
         {
             auto epi = [&](int i, double sum, double) {
-                const double zt_i = sum;
-                const double z_old = p.z[i], y_old = y[i];
-                const double zr = p.s.alpha * zt_i + (1.0 - p.s.alpha) * z_old;
-                const double z_new = clamp_julia(zr + rho1 * y_old, p.l[i], p.u[i]);
-                const double y_new = y_old + rho * (zr - z_new);
-                p.z[i] = z_new;
-                y[i] = y_new;
-                p.zt[i] = zt_i;
-                g[i] = rho * (zt_i - z_new) + y_new;
-                nrm[1] = nanmax(nrm[1], fabs(z_new - z_old));
+                nrm[1] = nanmax(nrm[1], admm_row_update(p, y, g, i, sum, p.s.alpha, 1.0 - p.s.alpha, rho, rho1));
             };
             spmv_tiles<TMA, false>(p.A, xt, sm, ps, epi);
             count(ctr.n_a, 1);
         }
-        for (int j = gtid; j < n; j += gstride) {
-            const double x_old = x[j];
-            const double x_new = p.s.alpha * xt[j] + (1.0 - p.s.alpha) * x_old;
-            x[j] = x_new;
-            nrm[0] = nanmax(nrm[0], fabs(x_new - x_old));
-        }
+        for (int j = gtid; j < n; j += gstride)
+            nrm[0] = nanmax(nrm[0], admm_x_relax(x, xt, j, p.s.alpha, 1.0 - p.s.alpha));
         grid_barrier(p.gs, st);
         if (do_check) {
             {
-                auto epi = [&](int i, double sum, double) {
-                    const double zi = p.z[i];
-                    nrm[2] = nanmax(nrm[2], fabs(sum - zi));
-                    nrm[3] = nanmax(nrm[3], fabs(sum));
-                    nrm[3] = nanmax(nrm[3], fabs(zi));
-                };
+                auto epi = [&](int i, double sum, double) { admm_prim_norms(nrm[2], nrm[3], sum, p.z[i], 1.0); };
                 spmv_tiles<TMA, false>(p.A, x, sm, ps, epi);
                 count(ctr.n_a, 1);
             }
@@ -452,25 +434,14 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) admm_peer_sliced_kernel(Sp
             peer_allmax4(p.gs, st, pd, xs, nrm);
             peer_allreduce(p.gs, st, pd, xs, pd.off_w2part, pd.off_w2red, 2 * n);
             double nd[2] = {0.0, 0.0};
-            for (int j = gtid; j < n; j += gstride) {
-                const double px = w2red[j], aty = w2red[n + j];
-                nd[0] = nanmax(nd[0], fabs(px + p.q[j] + aty));
-                nd[1] = nanmax(nd[1], fabs(px));
-                nd[1] = nanmax(nd[1], fabs(aty));
-            }
+            for (int j = gtid; j < n; j += gstride) admm_dual_norms(nd[0], nd[1], w2red[j], p.q[j], w2red[n + j], 1.0);
             grid_barrier_reduce<2, true>(p.gs, st, nd, sm.red, sm.bcast);
             const double dx = nrm[0], dz = nrm[1];
             const double res_prim = nrm[2], res_dual = nd[0];
             if (threadIdx.x == 0) { ctr.res_prim = res_prim; ctr.res_dual = res_dual; }
             const double max_prim = nrm[3];
             const double max_dual = nanmax(nd[1], p.normQ);
-            if (p.s.adaptive_rho) {
-                const double num = res_prim * max_dual, den = res_dual * max_prim;
-                rhorho = clamp_julia(rho * sqrt(num / den), 1e-3, 1e6);
-            }
-            const double eps_admm = fmin(p.s.eps_abs, p.s.eps_rel) * 1e-2;
-            if ((res_prim < p.s.eps_abs + p.s.eps_rel * max_prim) && (res_dual < p.s.eps_abs + p.s.eps_rel * max_dual)) conv_flag = 3;
-            if ((dx <= eps_admm) && (dz <= eps_admm)) conv_flag = 2;
+            admm_stop_test(p.s, rho, dx, dz, res_prim, res_dual, max_prim, max_dual, rhorho, conv_flag);
             if (conv_flag != 1) break;
         }
     }
