@@ -75,7 +75,7 @@ typedef struct qpb200_settings {
     double pcg_rel_eps;   /* reltol of cg!; <0 means the library default sqrt(eps(Float64))       */
     int32_t precond;      /* QPB200_PRECOND_* (default JACOBI)                                    */
     int32_t device;       /* CUDA device ordinal; -1 = the calling thread's current device        */
-    int32_t spmv_loader;  /* 0 = auto (2), 1 = coalesced LDG, 2 = TMA bulk staged, 3 = TMA + pipelined */
+    int32_t spmv_loader;  /* accepted and ignored since round 2: one tile loader (TMA bulk staged)   */
     int32_t reserved_i[7]; /* [QPB200_RSV_*] below; the rest must be 0                            */
     double reserved_d[4];
 } qpb200_settings;
