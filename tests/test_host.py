@@ -239,17 +239,12 @@ def test_host_equilibration_matches_oracle(lib, case):
     np.testing.assert_allclose(Av[:As.nnz], As.data, rtol=1e-13)
 
 
-@pytest.mark.parametrize("n,m,dens,base", [(60, 40, 0.2, 0), (60, 0, 0.2, 1), (3000, 5000, 0.02, 1), (40000, 70000, 3e-4, 0)])
-def test_host_operator_assembly_matches_scipy(lib, n, m, dens, base):
-    """qpb200_create's host conversion (CSC inputs -> H = [P A'] row-major, bucketed parallel transpose for the large
-    case, serial counting sort for the small ones) against scipy: same row pointers, split points, columns in
-    ascending order, bit-identical values; plus diag(P) and the column square sums of A."""
+def _assemble_and_compare(lib, P, A, base):
+    """qpb200_debug_assemble_h (the host conversion of qpb200_create) against scipy: same row pointers, split points,
+    columns in ascending order, bit-identical values; plus diag(P) and the column square sums of A."""
     from quadraticprogramsolver_b200.solver import _p64, _pd
-    rng = np.random.default_rng(n + m)
-    M = sprandn(rng, n, n, dens)
-    P = sp.csc_matrix(M.T @ M + 0.01 * sp.identity(n))          # symmetric
-    P = sp.csc_matrix(P + sp.triu(sprandn(rng, n, n, dens / 4), 1))   # ... and a non-symmetric part: rows != columns
-    A = sp.csc_matrix(sprandn(rng, m, n, dens)) if m else sp.csc_matrix((0, n))
+    n, m = P.shape[0], A.shape[0]
+    P, A = sp.csc_matrix(P), sp.csc_matrix(A)
     for X in (P, A):
         X.sort_indices()
     arrs = []
@@ -272,6 +267,48 @@ def test_host_operator_assembly_matches_scipy(lib, n, m, dens, base):
     assert np.array_equal(mid, H.indptr[:-1] + np.diff(sp.csr_matrix(P).indptr))
     np.testing.assert_array_equal(dP, P.diagonal())
     np.testing.assert_allclose(dAA, np.asarray(A.multiply(A).sum(axis=0)).ravel(), rtol=1e-14, atol=0)
+
+
+@pytest.mark.parametrize("n,m,dens,base", [(60, 40, 0.2, 0), (60, 0, 0.2, 1), (3000, 5000, 0.02, 1), (40000, 70000, 3e-4, 0)])
+def test_host_operator_assembly_matches_scipy(lib, n, m, dens, base):
+    """CSC inputs -> H = [P A'] row-major: bucketed parallel transpose for the large case, serial counting sort for the
+    small ones."""
+    rng = np.random.default_rng(n + m)
+    M = sprandn(rng, n, n, dens)
+    P = sp.csc_matrix(M.T @ M + 0.01 * sp.identity(n))          # symmetric
+    P = sp.csc_matrix(P + sp.triu(sprandn(rng, n, n, dens / 4), 1))   # ... and a non-symmetric part: rows != columns
+    A = sp.csc_matrix(sprandn(rng, m, n, dens)) if m else sp.csc_matrix((0, n))
+    _assemble_and_compare(lib, P, A, base)
+
+
+@pytest.mark.parametrize("case", ["arrowhead", "top_rows_only", "dense_512", "dense_600", "last_column_only", "one_row_of_A"])
+def test_host_operator_assembly_skewed_patterns(lib, case):
+    """The bucketed transpose (nnz >= 2^18) on patterns that put everything into one row block, one column block or one
+    thread's share: a dense row and column, all entries in the first rows, dense matrices at the row-block boundaries
+    (512 rows = one row per block, 600 rows = two), a single non-empty column, and a constraint matrix of one dense row."""
+    rng = np.random.default_rng(17)
+    A = None
+    if case == "arrowhead":
+        n = 150000
+        r = np.arange(1, n)
+        P = sp.coo_matrix((rng.standard_normal(3 * n - 2), (np.concatenate([np.arange(n), np.zeros(n - 1, int), r]),
+                                                           np.concatenate([np.arange(n), r, np.zeros(n - 1, int)]))), shape=(n, n))
+    elif case == "top_rows_only":
+        n = 5000
+        P = sp.vstack([sp.csr_matrix(rng.standard_normal((100, n))), sp.csr_matrix((n - 100, n))])
+    elif case in ("dense_512", "dense_600"):
+        n = int(case.split("_")[1])
+        P = sp.csr_matrix(rng.standard_normal((n, n)))
+    elif case == "last_column_only":
+        n = 300000
+        P = sp.coo_matrix((rng.standard_normal(n), (np.arange(n), np.full(n, n - 1))), shape=(n, n))
+    else:
+        n = 300000
+        P = sp.identity(n, format="csc") * 2.0
+        A = sp.csr_matrix(rng.standard_normal((1, n)))
+    if A is None:
+        A = sprandn(rng, 7, n, 0.3)
+    _assemble_and_compare(lib, P, A, 1 if case in ("arrowhead", "dense_600") else 0)
 
 
 def test_bench_reference_arm_prints_exactly_one_json_line():
@@ -349,3 +386,34 @@ def test_julia_shim_binds_exported_symbols_and_mirrors_the_struct_layouts(lib):
     assert fields("Settings") == [f for f, _ in _lib.Settings._fields_]
     assert fields("Info") == [f for f, _ in _lib.Info._fields_]
     assert fields("ProxReport") == [f for f, _ in _lib.ProxReport._fields_]
+
+
+def test_tile_plan_property_random_row_lengths(lib):
+    """Property test of the tile plan (the static work distribution every matrix pass of the kernels follows): for
+    random row-length profiles -- empty rows, rows around the tile size and its multiples, a few very long rows -- and
+    random grid sizes, every non-zero is covered exactly once, in order, rows longer than a tile stay on one CTA, and
+    the emulated pass reproduces M x."""
+    from hypothesis import given, settings, strategies as st
+
+    T = lib.qpb200_debug_tile_nnz()
+    length = st.one_of(st.just(0), st.integers(0, 12), st.integers(T - 3, T + 3), st.sampled_from([2 * T, 3 * T, 2 * T + 1]),
+                       st.integers(0, 5 * T))
+    profile = st.lists(length, min_size=1, max_size=120)
+
+    @settings(max_examples=120, deadline=None, derandomize=True)
+    @given(profile, st.integers(1, 600), st.integers(0, 3))
+    def run(lengths, grid, repeat):
+        lengths = np.array(lengths * (1 + repeat), dtype=np.int64)
+        ptr = np.concatenate([[0], np.cumsum(lengths)])
+        nnz = int(ptr[-1])
+        ncols = max(1, int(lengths.max()))
+        idx = np.concatenate([np.arange(k) for k in lengths]) if nnz else np.zeros(0, dtype=np.int64)
+        rng = np.random.default_rng(nnz + grid)
+        M = sp.csr_matrix((rng.standard_normal(nnz), idx.astype(np.int32), ptr.astype(np.int32)), shape=(len(lengths), ncols))
+        x = rng.standard_normal(ncols)
+        tiles, cta, lpr = _plan(lib, M, grid)
+        assert lpr in (1, 2, 4, 8, 16, 32)
+        y = _emulate(M, x, tiles, cta, T)
+        assert np.allclose(y, M @ x, rtol=1e-12, atol=1e-12)
+
+    run()
