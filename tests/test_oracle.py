@@ -255,3 +255,41 @@ def test_noise_triggered_exit_and_the_same_trajectory_criterion():
     with pytest.raises(AssertionError):                       # a wrong iterate at the common iteration is still rejected
         assert_parity(xc, fc, ic, xj, fj, ij, resolve_gpu=lambda k: (c_at(k)[0] + 1e-3, c_at(k)[1]),
                       resolve_ref=lambda k: (j_at(k)[0] - 1e-3, j_at(k)[1]))
+
+
+def test_runtests_sweep_python_restatement_vs_c_restatement(capsys):
+    """The RunTests-shaped sweep (RunTests.jl:62-99 settings, 9 classes x 3 seeds at n = 10, four classes at n = 100)
+    between the two CPU restatements, tight inner solve: the same criterion the GPU sweep is held to -- strict parity,
+    or, where the stop test fired on rounding noise, the same-trajectory criterion -- so the GPU-vs-oracle statistics of
+    tests/test_gpu_parity.py::test_runtests_sweep can be read next to CPU-vs-CPU ones."""
+    import warnings
+
+    from parity_util import assert_parity
+
+    kw = dict(numIterations=50000, epsAbs=1e-7, epsRel=1e-7, rho=0.1, adptRho=True, epsPcg=1e-11)
+    cases = [(pc, 10, s) for pc in ProblemClass for s in (1234, 1235, 1236)]
+    cases += [(pc, 100, 1234) for pc in (ProblemClass.randomQp, ProblemClass.equalityConstrainedQp,
+                                         ProblemClass.portfolioOptimization, ProblemClass.isotonicRegression)]
+    routes = {"strict": 0, "trajectory": 0}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for pc, n, seed in cases:
+            m = (5 if n == 10 else 50) if pc == ProblemClass.equalityConstrainedQp else 0
+            P, q, A, l, u = GenerateRandomQP(pc, n, numConstraints=m, seed=seed)
+            xc, fc, ic = c_oracle.solve_sparse(P, q, A, l, u, precond=1, **kw)
+            xj, fj, ij = qp_oracle.solve(P, q, A, l, u, mode="J", **kw)
+
+            def c_at(k):
+                xk, _, ik = c_oracle.solve_sparse(P, q, A, l, u, precond=1, **dict(kw, numIterations=k))
+                return xk, ik
+
+            def j_at(k):
+                xk, _, ik = qp_oracle.solve(P, q, A, l, u, mode="J", **dict(kw, numIterations=k))
+                return xk, ik
+
+            routes[assert_parity(xc, fc, ic, xj, fj, ij, resolve_gpu=c_at, resolve_ref=j_at, rho_updates=True,
+                                 what=f"{pc.name} n={n} seed={seed}")] += 1
+    with capsys.disabled():
+        print(f"\n[C port vs Python oracle, RunTests sweep] strict parity: {routes['strict']}, same trajectory (noise-triggered exit): "
+              f"{routes['trajectory']} of {len(cases)}")
+    assert routes["trajectory"] <= 3
