@@ -262,9 +262,7 @@ def run_reference(args):
 
 
 def run_b200(args):
-    import ctypes as C
-
-    from quadraticprogramsolver_b200 import _lib, solver as S
+    from quadraticprogramsolver_b200 import solver as S
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -8,7 +8,6 @@ import sys
 import textwrap
 
 import numpy as np
-import scipy.sparse as sp
 
 from quadraticprogramsolver_b200 import partition
 from workloads.problems import config_sparse

@@ -2,7 +2,6 @@
 restatement, GPU parity of polish_kernels.cuh against it."""
 import numpy as np
 import pytest
-import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 
 from oracle import qp_oracle
