@@ -293,3 +293,33 @@ def test_runtests_sweep_python_restatement_vs_c_restatement(capsys):
         print(f"\n[C port vs Python oracle, RunTests sweep] strict parity: {routes['strict']}, same trajectory (noise-triggered exit): "
               f"{routes['trajectory']} of {len(cases)}")
     assert routes["trajectory"] <= 3
+
+
+def test_qp_model_mat_file_round_trip(tmp_path):
+    """QpModel.mat, the file the reference's MATLAB and Julia scripts exchange problems through
+    (SolveQuadraticProgramUnitTest.m:84, SolveQuadraticProgramUnitTest.jl:47-55): write, read back bit for bit
+    (incl. +-Inf bounds and a problem without constraints), and solve what was read."""
+    import scipy.io
+
+    from workloads.matfile import load_qp_model, save_qp_model
+
+    for k, prob in enumerate((GenerateRandomQP(ProblemClass.supportVectorMachine, 10, seed=3), config_cfg1(1234),
+                              (sp.identity(4, format="csc") * 2.0, np.ones(4), sp.csc_matrix((0, 4)), np.zeros(0), np.zeros(0)))):
+        path = str(tmp_path / f"QpModel{k}.mat")
+        save_qp_model(path, *prob)
+        P, q, A, l, u = load_qp_model(path)
+        assert (P != sp.csc_matrix(prob[0])).nnz == 0 and (A != sp.csc_matrix(prob[2])).nnz == 0
+        assert np.array_equal(q, prob[1]) and np.array_equal(l, prob[3]) and np.array_equal(u, prob[4])
+        assert q.ndim == 1 and l.ndim == 1
+    P, q, A, l, u = load_qp_model(str(tmp_path / "QpModel1.mat"))
+    x, flag, info = qp_oracle.solve(P, q, A, l, u, mode="D")
+    x0, flag0, _ = qp_oracle.solve(*config_cfg1(1234), mode="D")
+    assert int(flag) == int(flag0) and np.array_equal(x, x0)
+    scipy.io.savemat(str(tmp_path / "bad.mat"), {"mP": np.eye(2)})
+    with pytest.raises(KeyError):
+        load_qp_model(str(tmp_path / "bad.mat"))
+    # full (dense) matrices in the file, as MATLAB writes them when the caller never made them sparse
+    scipy.io.savemat(str(tmp_path / "full.mat"), {"mP": np.eye(3), "vQ": np.ones((3, 1)), "mA": np.ones((2, 3)),
+                                                  "vL": -np.ones((2, 1)), "vU": np.array([[1.0], [np.inf]])})
+    P, q, A, l, u = load_qp_model(str(tmp_path / "full.mat"))
+    assert sp.issparse(P) and A.shape == (2, 3) and np.isinf(u[1]) and q.shape == (3,)
